@@ -1,0 +1,554 @@
+// cabi.cu -- the extern "C" layer declared in include/cacao_img.h: device contexts, the
+// device-buffer / upload / readback layer, and the host-memory pipelines around the kernels.
+//
+// There is deliberately no CPU implementation of any pixel loop in this file or anywhere in the
+// library: without a CUDA device every compute entry point returns CACAO_E_NO_DEVICE.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "cacao_img.h"
+#include "convert_dispatch.cuh"
+#include "equirect.cuh"
+#include "misc_kernels.cuh"
+
+namespace {
+
+	using namespace cacao;
+
+	// ---- error plumbing ------------------------------------------------------------------------
+	thread_local std::string t_last_error;
+
+	int fail(int status, const char* fmt, ...) {
+		char buf[512];
+		va_list ap;
+		va_start(ap, fmt);
+		vsnprintf(buf, sizeof buf, fmt, ap);
+		va_end(ap);
+		t_last_error = buf;
+		return status;
+	}
+
+	int fail_cuda(cudaError_t e, const char* what) {
+		// "no device" style failures get their own status so callers can tell them from kernel faults
+		const bool nodev = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice || e == cudaErrorInitializationError);
+		return fail(nodev ? CACAO_E_NO_DEVICE : CACAO_E_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+	}
+
+#define CU_TRY(expr)                                         \
+	do {                                                     \
+		cudaError_t e__ = (expr);                            \
+		if(e__ != cudaSuccess) return fail_cuda(e__, #expr); \
+	} while(0)
+
+	// ---- the 16->8 table -----------------------------------------------------------------------
+	const uint16_t kLutThresholds[254] = {
+#include "lut_thresholds.inc"
+	};
+
+	struct HostLut {
+		uint8_t table[65536];
+		HostLut() {
+			// level k starts at kLutThresholds[k-1]; the table is monotone with unit steps
+			int level = 0;
+			for(uint32_t i = 0; i < 65536u; ++i) {
+				while(level < 254 && i >= kLutThresholds[level]) ++level;
+				table[i] = static_cast<uint8_t>(level);
+			}
+		}
+	};
+	const HostLut& host_lut() {
+		static const HostLut lut;
+		return lut;
+	}
+
+	// ---- per-device context --------------------------------------------------------------------
+	constexpr int kMaxDevices = 64;
+	constexpr int kSlots = 3; // staging ring depth of the host-memory pipeline
+
+	struct DeviceCtx {
+		int device = -1;
+		int sm_count = 0;
+		size_t smem_optin = 0;
+		uint8_t* lut_dev = nullptr;
+		cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+		cudaEvent_t ev_in[kSlots] = {}, ev_run[kSlots] = {}, ev_out[kSlots] = {};
+		uint8_t* stage_in[kSlots] = {};
+		uint8_t* stage_out[kSlots] = {};
+		size_t stage_in_cap = 0, stage_out_cap = 0;
+		unsigned long long* checksum_dev = nullptr;
+		std::mutex pipe_mutex; // one host-memory pipeline call per device at a time
+	};
+
+	std::mutex g_ctx_mutex;
+	DeviceCtx* g_ctx[kMaxDevices] = {};
+	std::atomic<uint64_t> g_launches{0};
+
+	struct DeviceGuard {
+		int prev = -1;
+		bool active = false;
+		int enter(int device) {
+			cudaError_t e = cudaGetDevice(&prev);
+			if(e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
+			if(prev != device) {
+				e = cudaSetDevice(device);
+				if(e != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
+				active = true;
+			}
+			return CACAO_OK;
+		}
+		~DeviceGuard() {
+			if(active) cudaSetDevice(prev);
+		}
+	};
+
+	int resolve_device(int device, int* out) {
+		int n = 0;
+		cudaError_t e = cudaGetDeviceCount(&n);
+		if(e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+		if(n <= 0) return fail(CACAO_E_NO_DEVICE, "no CUDA device is visible; libcacaoimage-b200 has no CPU fallback");
+		if(device < 0) {
+			e = cudaGetDevice(&device);
+			if(e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
+		}
+		if(device >= n || device >= kMaxDevices) return fail(CACAO_E_BAD_ARG, "device %d out of range (%d visible)", device, n);
+		*out = device;
+		return CACAO_OK;
+	}
+
+	// Returns the context for `device` (creating it on first use) with the device made current.
+	int get_ctx(int device, DeviceCtx** out, DeviceGuard& guard) {
+		int dev = 0;
+		int rc = resolve_device(device, &dev);
+		if(rc) return rc;
+		rc = guard.enter(dev);
+		if(rc) return rc;
+		std::lock_guard<std::mutex> lock(g_ctx_mutex);
+		if(!g_ctx[dev]) {
+			DeviceCtx* c = new DeviceCtx();
+			c->device = dev;
+			cudaDeviceProp prop;
+			CU_TRY(cudaGetDeviceProperties(&prop, dev));
+			if(prop.major < 10) {
+				delete c;
+				return fail(CACAO_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+			}
+			c->sm_count = prop.multiProcessorCount;
+			c->smem_optin = prop.sharedMemPerBlockOptin;
+			CU_TRY(cudaMalloc(&c->lut_dev, 65536));
+			CU_TRY(cudaMemcpy(c->lut_dev, host_lut().table, 65536, cudaMemcpyHostToDevice));
+			CU_TRY(cudaMalloc(&c->checksum_dev, sizeof(unsigned long long)));
+			CU_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+			CU_TRY(cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking));
+			CU_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+			for(int s = 0; s < kSlots; ++s) {
+				CU_TRY(cudaEventCreateWithFlags(&c->ev_in[s], cudaEventDisableTiming));
+				CU_TRY(cudaEventCreateWithFlags(&c->ev_run[s], cudaEventDisableTiming));
+				CU_TRY(cudaEventCreateWithFlags(&c->ev_out[s], cudaEventDisableTiming));
+			}
+			g_ctx[dev] = c;
+		}
+		*out = g_ctx[dev];
+		return CACAO_OK;
+	}
+
+	void destroy_ctx(DeviceCtx* c) {
+		int prev = 0;
+		cudaGetDevice(&prev);
+		cudaSetDevice(c->device);
+		cudaDeviceSynchronize();
+		for(int s = 0; s < kSlots; ++s) {
+			if(c->stage_in[s]) cudaFree(c->stage_in[s]);
+			if(c->stage_out[s]) cudaFree(c->stage_out[s]);
+			if(c->ev_in[s]) cudaEventDestroy(c->ev_in[s]);
+			if(c->ev_run[s]) cudaEventDestroy(c->ev_run[s]);
+			if(c->ev_out[s]) cudaEventDestroy(c->ev_out[s]);
+		}
+		if(c->s_in) cudaStreamDestroy(c->s_in);
+		if(c->s_run) cudaStreamDestroy(c->s_run);
+		if(c->s_out) cudaStreamDestroy(c->s_out);
+		if(c->lut_dev) cudaFree(c->lut_dev);
+		if(c->checksum_dev) cudaFree(c->checksum_dev);
+		cudaSetDevice(prev);
+		delete c;
+	}
+
+	int ensure_stage(DeviceCtx* c, size_t in_bytes, size_t out_bytes) {
+		if(in_bytes > c->stage_in_cap) {
+			for(int s = 0; s < kSlots; ++s) {
+				if(c->stage_in[s]) cudaFree(c->stage_in[s]);
+				c->stage_in[s] = nullptr;
+			}
+			c->stage_in_cap = 0;
+			for(int s = 0; s < kSlots; ++s) {
+				cudaError_t e = cudaMalloc(&c->stage_in[s], in_bytes);
+				if(e != cudaSuccess) return fail(CACAO_E_NO_MEMORY, "cudaMalloc(%zu) for the upload ring failed: %s", in_bytes, cudaGetErrorString(e));
+			}
+			c->stage_in_cap = in_bytes;
+		}
+		if(out_bytes > c->stage_out_cap) {
+			for(int s = 0; s < kSlots; ++s) {
+				if(c->stage_out[s]) cudaFree(c->stage_out[s]);
+				c->stage_out[s] = nullptr;
+			}
+			c->stage_out_cap = 0;
+			for(int s = 0; s < kSlots; ++s) {
+				cudaError_t e = cudaMalloc(&c->stage_out[s], out_bytes);
+				if(e != cudaSuccess) return fail(CACAO_E_NO_MEMORY, "cudaMalloc(%zu) for the readback ring failed: %s", out_bytes, cudaGetErrorString(e));
+			}
+			c->stage_out_cap = out_bytes;
+		}
+		return CACAO_OK;
+	}
+
+	// ---- argument checks -----------------------------------------------------------------------
+	bool ch_ok(int ch) {
+		return ch == 1 || ch == 3 || ch == 4;
+	}
+	bool fmt_ok(int f) {
+		return f >= CACAO_FMT_U8 && f <= CACAO_FMT_F32;
+	}
+
+	int check_convert_args(const void* src, void* dst, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, int mem) {
+		if(!ch_ok(src_ch) || !ch_ok(dst_ch)) return fail(CACAO_E_BAD_ARG, "channel counts must be 1, 3 or 4 (got %d -> %d)", src_ch, dst_ch);
+		if(!fmt_ok(src_fmt) || !fmt_ok(dst_fmt)) return fail(CACAO_E_BAD_ARG, "unknown sample format (%d -> %d)", src_fmt, dst_fmt);
+		if(mode != CACAO_MODE_REF_EXACT && mode != CACAO_MODE_FIXED) return fail(CACAO_E_BAD_ARG, "unknown mode %d", mode);
+		if(mem != CACAO_MEM_HOST && mem != CACAO_MEM_DEVICE) return fail(CACAO_E_BAD_ARG, "unknown memory kind %d", mem);
+		if(src_ch == dst_ch && src_fmt == dst_fmt) return fail(CACAO_E_SAME_LAYOUT, "%s", cacao_img_status_string(CACAO_E_SAME_LAYOUT));
+		if(!src || !dst) return fail(CACAO_E_BAD_ARG, "null image pointer");
+		return CACAO_OK;
+	}
+
+	int enqueue_convert(DeviceCtx* c, const void* src, void* dst, uint64_t pixels, uint64_t ppi, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, cudaStream_t stream) {
+		ConvertJob job;
+		job.src = src;
+		job.dst = dst;
+		job.pixels = pixels;
+		job.pixels_per_image = ppi ? ppi : 1;
+		job.src_ch = src_ch;
+		job.dst_ch = dst_ch;
+		job.src_fmt = src_fmt;
+		job.dst_fmt = dst_fmt;
+		job.mode = mode;
+		job.lut_dev = c->lut_dev;
+		job.dev.sm_count = c->sm_count;
+		job.dev.max_smem_optin = c->smem_optin;
+		job.stream = stream;
+		job.launches = 0;
+		cudaError_t e;
+		switch(src_fmt) {
+			case CACAO_FMT_U8: e = convert_from_u8(job); break;
+			case CACAO_FMT_U16: e = convert_from_u16(job); break;
+			case CACAO_FMT_F16: e = convert_from_f16(job); break;
+			default: e = convert_from_f32(job); break;
+		}
+		g_launches.fetch_add(job.launches, std::memory_order_relaxed);
+		if(e != cudaSuccess) return fail_cuda(e, "convert kernel launch");
+		return CACAO_OK;
+	}
+
+	// Host-memory conversion: chunks flow upload -> kernel -> readback over three streams, so PCIe
+	// moves in both directions while the SMs convert the chunk in between.
+	int convert_host_pipeline(DeviceCtx* c, const uint8_t* src, uint8_t* dst, uint64_t pixels, uint64_t ppi, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode) {
+		const uint64_t sbpp = static_cast<uint64_t>(src_ch) * fmt_bytes(src_fmt);
+		const uint64_t dbpp = static_cast<uint64_t>(dst_ch) * fmt_bytes(dst_fmt);
+		const bool quirk = (src_fmt == CACAO_FMT_U8 || src_fmt == CACAO_FMT_U16) && src_ch == 1 && dst_ch == 4 && mode == CACAO_MODE_REF_EXACT;
+		// chunk = a multiple of 8192 pixels (every tile size divides it; chunk byte offsets stay
+		// 16-byte aligned) moving about 32 MiB across PCIe in the heavier direction
+		uint64_t chunk_px = (32ull << 20) / (sbpp > dbpp ? sbpp : dbpp);
+		chunk_px = (chunk_px / 8192) * 8192;
+		if(chunk_px == 0) chunk_px = 8192;
+		if(quirk || chunk_px > pixels) chunk_px = pixels; // the pixel-0 quirk needs each image whole
+		std::lock_guard<std::mutex> lock(c->pipe_mutex);
+		int rc = ensure_stage(c, chunk_px * sbpp, chunk_px * dbpp);
+		if(rc) return rc;
+		uint64_t done = 0;
+		for(uint64_t k = 0; done < pixels; ++k) {
+			const int s = static_cast<int>(k % kSlots);
+			const uint64_t n = (pixels - done < chunk_px) ? pixels - done : chunk_px;
+			// the slot is free once its previous readback has finished
+			if(k >= kSlots) CU_TRY(cudaStreamWaitEvent(c->s_in, c->ev_out[s], 0));
+			CU_TRY(cudaMemcpyAsync(c->stage_in[s], src + done * sbpp, n * sbpp, cudaMemcpyHostToDevice, c->s_in));
+			CU_TRY(cudaEventRecord(c->ev_in[s], c->s_in));
+			CU_TRY(cudaStreamWaitEvent(c->s_run, c->ev_in[s], 0));
+			if(k >= kSlots) CU_TRY(cudaStreamWaitEvent(c->s_run, c->ev_out[s], 0));
+			rc = enqueue_convert(c, c->stage_in[s], c->stage_out[s], n, quirk ? ppi : n, src_ch, dst_ch, src_fmt, dst_fmt, mode, c->s_run);
+			if(rc) return rc;
+			CU_TRY(cudaEventRecord(c->ev_run[s], c->s_run));
+			CU_TRY(cudaStreamWaitEvent(c->s_out, c->ev_run[s], 0));
+			CU_TRY(cudaMemcpyAsync(dst + done * dbpp, c->stage_out[s], n * dbpp, cudaMemcpyDeviceToHost, c->s_out));
+			CU_TRY(cudaEventRecord(c->ev_out[s], c->s_out));
+			done += n;
+		}
+		CU_TRY(cudaStreamSynchronize(c->s_out));
+		return CACAO_OK;
+	}
+
+} // namespace
+
+extern "C" {
+
+int cacao_img_abi_version(void) {
+	return CACAO_IMG_ABI_VERSION;
+}
+
+const char* cacao_img_last_error(void) {
+	return t_last_error.c_str();
+}
+
+const char* cacao_img_status_string(int status) {
+	switch(status) {
+		case CACAO_OK: return "ok";
+		// the reference's exception texts, verbatim, so the C++ wrappers throw what callers expect
+		case CACAO_E_SAME_LAYOUT: return "Cannot change an image's channel layout to its current layout!";                           // Layout.cpp:9
+		case CACAO_E_NOT_16BIT: return "Source image for 16 to 8-bit color conversion does not have a 16-bit color depth!";            // Colordepth.cpp:8
+		case CACAO_E_ZERO_DIM: return "Cannot flip an image with zeroed dimensions!";                                                  // Flip.cpp:8
+		case CACAO_E_BAD_DEPTH: return "Invalid color depth; only 8 and 16 are allowed.";                                              // Flip.cpp:9
+		case CACAO_E_EMPTY: return "Cannot flip an image with a zero-sized data buffer!";                                              // Flip.cpp:10
+		case CACAO_E_BAD_ARG: return "invalid argument";
+		case CACAO_E_CUDA: return "CUDA error";
+		case CACAO_E_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+		case CACAO_E_NO_MEMORY: return "out of device memory";
+	}
+	return "unknown status";
+}
+
+int cacao_img_device_count(void) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return 0;
+	if(e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+	return n;
+}
+
+int cacao_img_init(int device) {
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	return get_ctx(device, &c, g);
+}
+
+int cacao_img_shutdown(void) {
+	std::lock_guard<std::mutex> lock(g_ctx_mutex);
+	for(int d = 0; d < kMaxDevices; ++d) {
+		if(g_ctx[d]) {
+			destroy_ctx(g_ctx[d]);
+			g_ctx[d] = nullptr;
+		}
+	}
+	return CACAO_OK;
+}
+
+uint64_t cacao_img_launch_count(void) {
+	return g_launches.load(std::memory_order_relaxed);
+}
+
+int cacao_img_malloc(int device, void** dev_ptr, uint64_t bytes) {
+	if(!dev_ptr) return fail(CACAO_E_BAD_ARG, "null out-pointer");
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	cudaError_t e = cudaMalloc(dev_ptr, bytes ? bytes : 1);
+	if(e == cudaErrorMemoryAllocation) {
+		cudaGetLastError();
+		return fail(CACAO_E_NO_MEMORY, "cudaMalloc(%llu) failed", static_cast<unsigned long long>(bytes));
+	}
+	if(e != cudaSuccess) return fail_cuda(e, "cudaMalloc");
+	return CACAO_OK;
+}
+
+int cacao_img_free(int device, void* dev_ptr) {
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	CU_TRY(cudaFree(dev_ptr));
+	return CACAO_OK;
+}
+
+int cacao_img_host_alloc(void** host_ptr, uint64_t bytes) {
+	if(!host_ptr) return fail(CACAO_E_BAD_ARG, "null out-pointer");
+	cudaError_t e = cudaHostAlloc(host_ptr, bytes ? bytes : 1, cudaHostAllocPortable);
+	if(e != cudaSuccess) return fail_cuda(e, "cudaHostAlloc");
+	return CACAO_OK;
+}
+
+int cacao_img_host_free(void* host_ptr) {
+	CU_TRY(cudaFreeHost(host_ptr));
+	return CACAO_OK;
+}
+
+int cacao_img_upload(int device, void* dst_dev, const void* src_host, uint64_t bytes, void* stream) {
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	CU_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+	return CACAO_OK;
+}
+
+int cacao_img_download(int device, void* dst_host, const void* src_dev, uint64_t bytes, void* stream) {
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	CU_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+	return CACAO_OK;
+}
+
+int cacao_img_sync(int device, void* stream) {
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	if(stream)
+		CU_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+	else
+		CU_TRY(cudaDeviceSynchronize());
+	return CACAO_OK;
+}
+
+int cacao_img_convert_batch(int device, const void* src, void* dst, uint64_t pixels_per_image, uint64_t count, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, int mem, void* stream) {
+	int rc = check_convert_args(src, dst, src_ch, dst_ch, src_fmt, dst_fmt, mode, mem);
+	if(rc) return rc;
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	const uint64_t pixels = pixels_per_image * count;
+	if(pixels == 0) return CACAO_OK;
+	if(mem == CACAO_MEM_DEVICE) return enqueue_convert(c, src, dst, pixels, pixels_per_image, src_ch, dst_ch, src_fmt, dst_fmt, mode, static_cast<cudaStream_t>(stream));
+	return convert_host_pipeline(c, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), pixels, pixels_per_image, src_ch, dst_ch, src_fmt, dst_fmt, mode);
+}
+
+int cacao_img_convert(int device, const void* src, void* dst, uint64_t pixels, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, int mem, void* stream) {
+	return cacao_img_convert_batch(device, src, dst, pixels, 1, src_ch, dst_ch, src_fmt, dst_fmt, mode, mem, stream);
+}
+
+int cacao_img_flip_rows(int device, const void* src, void* dst, uint32_t w, uint32_t h, uint32_t bytes_per_pixel, int mem, void* stream) {
+	if(w == 0 || h == 0) return fail(CACAO_E_ZERO_DIM, "%s", cacao_img_status_string(CACAO_E_ZERO_DIM));
+	if(bytes_per_pixel == 0) return fail(CACAO_E_BAD_DEPTH, "%s", cacao_img_status_string(CACAO_E_BAD_DEPTH));
+	if(!src || !dst) return fail(CACAO_E_EMPTY, "%s", cacao_img_status_string(CACAO_E_EMPTY));
+	if(mem != CACAO_MEM_HOST && mem != CACAO_MEM_DEVICE) return fail(CACAO_E_BAD_ARG, "unknown memory kind %d", mem);
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	const uint64_t pitch = static_cast<uint64_t>(w) * bytes_per_pixel;
+	if(mem == CACAO_MEM_DEVICE) {
+		cudaError_t e = flip_rows_launch(src, dst, pitch, h, c->sm_count, static_cast<cudaStream_t>(stream));
+		if(e != cudaSuccess) return fail_cuda(e, "flip kernel launch");
+		g_launches.fetch_add(1, std::memory_order_relaxed);
+		return CACAO_OK;
+	}
+	std::lock_guard<std::mutex> lock(c->pipe_mutex);
+	const uint64_t bytes = pitch * h;
+	rc = ensure_stage(c, bytes, bytes);
+	if(rc) return rc;
+	CU_TRY(cudaMemcpyAsync(c->stage_in[0], src, bytes, cudaMemcpyHostToDevice, c->s_run));
+	cudaError_t e = flip_rows_launch(c->stage_in[0], c->stage_out[0], pitch, h, c->sm_count, c->s_run);
+	if(e != cudaSuccess) return fail_cuda(e, "flip kernel launch");
+	g_launches.fetch_add(1, std::memory_order_relaxed);
+	CU_TRY(cudaMemcpyAsync(dst, c->stage_out[0], bytes, cudaMemcpyDeviceToHost, c->s_run));
+	CU_TRY(cudaStreamSynchronize(c->s_run));
+	return CACAO_OK;
+}
+
+int cacao_img_equirect_src_window(uint32_t W, uint32_t H, uint32_t N, uint32_t face_mask, uint32_t row_begin, uint32_t row_end, uint32_t* src_row0, uint32_t* src_rows) {
+	if(!src_row0 || !src_rows) return fail(CACAO_E_BAD_ARG, "null out-pointer");
+	if(W == 0 || H == 0 || N == 0) return fail(CACAO_E_ZERO_DIM, "equirect: zero-sized image or face");
+	equirect_src_window(W, H, N, face_mask & 0x3Fu, row_begin, row_end, src_row0, src_rows);
+	return CACAO_OK;
+}
+
+int cacao_img_equirect_to_cube(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, uint32_t face_mask, uint32_t row_begin, uint32_t row_end, int mem, void* stream) {
+	if(!ch_ok(ch) || !fmt_ok(fmt)) return fail(CACAO_E_BAD_ARG, "equirect: bad channel count %d or format %d", ch, fmt);
+	if(W == 0 || H == 0 || N == 0) return fail(CACAO_E_ZERO_DIM, "equirect: zero-sized image or face");
+	if(!src || !dst) return fail(CACAO_E_BAD_ARG, "null image pointer");
+	if(mem != CACAO_MEM_HOST && mem != CACAO_MEM_DEVICE) return fail(CACAO_E_BAD_ARG, "unknown memory kind %d", mem);
+	if(W > (1u << 24) || H > (1u << 24) || N > (1u << 23)) return fail(CACAO_E_BAD_ARG, "equirect: dimensions beyond exact float range");
+	face_mask &= 0x3Fu;
+	if(row_end > N) row_end = N;
+	if(src_rows == 0 || src_row0 + static_cast<uint64_t>(src_rows) > H) return fail(CACAO_E_BAD_ARG, "equirect: source window [%u,+%u) outside the image (H=%u)", src_row0, src_rows, H);
+	if(face_mask == 0 || row_begin >= row_end) return CACAO_OK;
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	const uint64_t bpp = static_cast<uint64_t>(ch) * fmt_bytes(fmt);
+	if(mem == CACAO_MEM_DEVICE) {
+		if(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) != 0) return fail(CACAO_E_BAD_ARG, "equirect: device buffers must be 16-byte aligned");
+		cudaError_t e = equirect_launch(src, dst, ch, fmt, W, H, src_row0, src_rows, N, face_mask, row_begin, row_end, static_cast<cudaStream_t>(stream));
+		if(e != cudaSuccess) return fail_cuda(e, "equirect kernel launch");
+		g_launches.fetch_add(1, std::memory_order_relaxed);
+		return CACAO_OK;
+	}
+	// host memory: upload only the source rows this work unit reads, read back only what it wrote
+	uint32_t need0 = 0, need_rows = 0;
+	equirect_src_window(W, H, N, face_mask, row_begin, row_end, &need0, &need_rows);
+	if(need0 < src_row0) need0 = src_row0;
+	if(need0 + need_rows > src_row0 + src_rows) need_rows = src_row0 + src_rows - need0;
+	const uint64_t pitch = static_cast<uint64_t>(W) * bpp;
+	const uint64_t cube_bytes = 6ull * N * N * bpp;
+	std::lock_guard<std::mutex> lock(c->pipe_mutex);
+	rc = ensure_stage(c, need_rows * pitch, cube_bytes);
+	if(rc) return rc;
+	const uint8_t* hsrc = static_cast<const uint8_t*>(src) + static_cast<uint64_t>(need0 - src_row0) * pitch;
+	CU_TRY(cudaMemcpyAsync(c->stage_in[0], hsrc, need_rows * pitch, cudaMemcpyHostToDevice, c->s_run));
+	cudaError_t e = equirect_launch(c->stage_in[0], c->stage_out[0], ch, fmt, W, H, need0, need_rows, N, face_mask, row_begin, row_end, c->s_run);
+	if(e != cudaSuccess) return fail_cuda(e, "equirect kernel launch");
+	g_launches.fetch_add(1, std::memory_order_relaxed);
+	for(uint32_t f = 0; f < 6; ++f) {
+		if(!(face_mask & (1u << f))) continue;
+		const uint64_t off = (static_cast<uint64_t>(f) * N + row_begin) * N * bpp;
+		CU_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, c->stage_out[0] + off, static_cast<uint64_t>(row_end - row_begin) * N * bpp, cudaMemcpyDeviceToHost, c->s_run));
+	}
+	CU_TRY(cudaStreamSynchronize(c->s_run));
+	return CACAO_OK;
+}
+
+int cacao_img_synth(int device, void* dst_dev, uint64_t first_sample, uint64_t samples, int fmt, int ch, uint32_t seed, void* stream) {
+	if(!fmt_ok(fmt) || !ch_ok(ch) || !dst_dev) return fail(CACAO_E_BAD_ARG, "synth: bad argument");
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	if(samples == 0) return CACAO_OK;
+	cudaError_t e = synth_launch(dst_dev, first_sample, samples, fmt, ch, seed, c->sm_count, static_cast<cudaStream_t>(stream));
+	if(e != cudaSuccess) return fail_cuda(e, "synth kernel launch");
+	g_launches.fetch_add(1, std::memory_order_relaxed);
+	return CACAO_OK;
+}
+
+int cacao_img_checksum(int device, const void* src_dev, uint64_t bytes, uint64_t* out, void* stream) {
+	if(!src_dev || !out || (bytes & 3u)) return fail(CACAO_E_BAD_ARG, "checksum: null pointer or size not a multiple of 4");
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	std::lock_guard<std::mutex> lock(c->pipe_mutex);
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	CU_TRY(cudaMemsetAsync(c->checksum_dev, 0, sizeof(unsigned long long), s));
+	if(bytes) {
+		cudaError_t e = checksum_launch(src_dev, bytes / 4, c->checksum_dev, c->sm_count, s);
+		if(e != cudaSuccess) return fail_cuda(e, "checksum kernel launch");
+		g_launches.fetch_add(1, std::memory_order_relaxed);
+	}
+	unsigned long long host = 0;
+	CU_TRY(cudaMemcpyAsync(&host, c->checksum_dev, sizeof host, cudaMemcpyDeviceToHost, s));
+	CU_TRY(cudaStreamSynchronize(s));
+	*out = host;
+	return CACAO_OK;
+}
+
+int cacao_img_get_lut(uint8_t* out65536) {
+	if(!out65536) return fail(CACAO_E_BAD_ARG, "null out-pointer");
+	std::memcpy(out65536, host_lut().table, 65536);
+	return CACAO_OK;
+}
+
+} // extern "C"

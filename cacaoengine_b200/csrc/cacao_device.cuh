@@ -1,0 +1,90 @@
+// cacao_device.cuh -- shared device-side helpers for the sm_100a pixel kernels.
+//
+// Compiled with -fmad=false: the float spec (DESIGN.md "Spec B") fixes where fused
+// multiply-adds happen, so every FMA in this library is an explicit fmaf()/__fmaf_rn().
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "cacao_img.h"
+
+namespace cacao {
+
+	constexpr int kWarp = 32;
+
+	// ---- sample-format traits ------------------------------------------------------------------
+	template<int Fmt>
+	struct FmtTraits;
+	template<>
+	struct FmtTraits<CACAO_FMT_U8> {
+		using type = uint8_t;
+		static constexpr int bytes = 1;
+		static constexpr bool is_int = true;
+	};
+	template<>
+	struct FmtTraits<CACAO_FMT_U16> {
+		using type = uint16_t;
+		static constexpr int bytes = 2;
+		static constexpr bool is_int = true;
+	};
+	template<>
+	struct FmtTraits<CACAO_FMT_F16> {
+		using type = uint16_t; // raw binary16 bits
+		static constexpr int bytes = 2;
+		static constexpr bool is_int = false;
+	};
+	template<>
+	struct FmtTraits<CACAO_FMT_F32> {
+		using type = float;
+		static constexpr int bytes = 4;
+		static constexpr bool is_int = false;
+	};
+
+	__host__ __device__ constexpr int fmt_bytes(int fmt) {
+		return fmt == CACAO_FMT_U8 ? 1 : (fmt == CACAO_FMT_F32 ? 4 : 2);
+	}
+
+	constexpr int cgcd(int a, int b) {
+		return b == 0 ? a : cgcd(b, a % b);
+	}
+	constexpr int clcm(int a, int b) {
+		return a / cgcd(a, b) * b;
+	}
+
+	// ---- 16-byte global / shared accessors -----------------------------------------------------
+	// Streaming data is touched exactly once: keep it out of L1 (no_allocate) so the LUT and the
+	// resampler's reused texels own the cache.
+	__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+		uint4 r;
+		asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+		return r;
+	}
+	__device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
+		asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+	}
+
+	// ---- binary16 <-> binary32, round-to-nearest-even ------------------------------------------
+	__device__ __forceinline__ uint16_t f32_to_f16_bits(float f) {
+		return __half_as_ushort(__float2half_rn(f));
+	}
+	__device__ __forceinline__ float f16_bits_to_f32(uint16_t h) {
+		return __half2float(__ushort_as_half(h));
+	}
+
+	// ---- hashing (synthetic inputs, checksum) --------------------------------------------------
+	__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+		h ^= h >> 16;
+		h *= 0x85EBCA6Bu;
+		h ^= h >> 13;
+		h *= 0xC2B2AE35u;
+		h ^= h >> 16;
+		return h;
+	}
+	__host__ __device__ __forceinline__ uint32_t hash32(uint32_t seed, uint64_t idx) {
+		return fmix32(seed ^ (static_cast<uint32_t>(idx) * 0x9E3779B9u) ^ (static_cast<uint32_t>(idx >> 32) * 0x85EBCA6Bu));
+	}
+
+} // namespace cacao

@@ -1,0 +1,146 @@
+// convert_pixel.cuh -- the per-pixel arithmetic of the fused layout + sample-format conversion.
+//
+// One place defines what a converted pixel is; the tiled vector kernel (convert_tiles.cuh) and the
+// scalar edge kernel (convert_scalar.cu) both call it.
+//
+// Reference semantics reproduced here (paths relative to /root/reference/):
+//   ->Gray (int)   trunc(0.2126*r)+trunc(0.7152*g)+trunc(0.0722*b), double products truncated
+//                  one by one, sum clamped to 255 even at 16 bit      libs/image/src/Layout.cpp:33-41,69-77
+//   Gray->RGB(A)   replicate; alpha = opaque max                         Layout.cpp:47-61,93-94
+//   RGB<->RGBA     copy / drop / add opaque alpha                        Layout.cpp:49-62
+//   U16->U8        table lookup                                          libs/image/src/Colordepth.cpp:32-35
+// Everything touching F16/F32 is DESIGN.md "Spec B.1" (no reference counterpart).
+#pragma once
+
+#include "cacao_device.cuh"
+
+namespace cacao {
+
+	// trunc(c * (double)x) for the three BT.709 weights, x <= 65535, without touching the FP64 pipe
+	// on the common path.  (x*num)/10000 equals the reference's double product truncated for every
+	// x in [0,65535] for 0.2126 and 0.0722; for 0.7152 = 447/625 the double product of a multiple of
+	// 625 can land one ulp under the exact integer, so those inputs (1 in 625) take the reference's
+	// own double multiply.  tests/test_convert_gpu.py checks all 3 x 65536 inputs against the oracle.
+	__device__ __forceinline__ uint32_t trunc_2126(uint32_t x) {
+		return (x * 2126u) / 10000u;
+	}
+	__device__ __forceinline__ uint32_t trunc_0722(uint32_t x) {
+		return (x * 722u) / 10000u;
+	}
+	template<bool Wide>
+	__device__ __forceinline__ uint32_t trunc_7152(uint32_t x) {
+		uint32_t t = (x * 7152u) / 10000u;
+		if constexpr(Wide) {
+			if(x % 625u == 0u) t = static_cast<uint32_t>(0.7152 * static_cast<double>(x));
+		}
+		return t;
+	}
+
+	// unorm -> float, bit-identical to IEEE (float)v / (float)M for every v in [0,M] (M = 255 or
+	// 65535): one multiply by the rounded reciprocal plus one Newton correction.  Checked
+	// exhaustively on the host (tests/test_oracle.py::test_division_forms) and on the device.
+	template<int M>
+	__device__ __forceinline__ float unorm_to_f32(uint32_t v) {
+		constexpr float fm = static_cast<float>(M);
+		constexpr float r = 1.0f / fm;
+		const float fv = static_cast<float>(v);
+		const float q = fv * r;
+		const float e = __fmaf_rn(-q, fm, fv);
+		return __fmaf_rn(e, r, q);
+	}
+	// RNE_f16((float)v / (float)M): the single multiply already rounds to the same binary16 for
+	// every v (exhaustively checked), so the correction step is skipped.
+	template<int M>
+	__device__ __forceinline__ uint16_t unorm_to_f16(uint32_t v) {
+		constexpr float r = 1.0f / static_cast<float>(M);
+		return f32_to_f16_bits(static_cast<float>(v) * r);
+	}
+
+	// float -> unorm: (x != x) ? 0 : uintN(min(max(x,0),1)*M + 0.5f)
+	template<int M>
+	__device__ __forceinline__ uint32_t f32_to_unorm(float x) {
+		if(x != x) return 0u;
+		const float c = fminf(fmaxf(x, 0.0f), 1.0f);
+		return __float2uint_rz(__fadd_rn(__fmul_rn(c, static_cast<float>(M)), 0.5f));
+	}
+
+	struct PixelCtx {
+		const uint8_t* lut; // 65536-entry table (shared or global memory); only read for U16 -> U8
+		uint32_t gray16_cap; // 255 in REF_EXACT mode (Layout.cpp:75), 65535 in FIXED mode
+	};
+
+	// in[]: SC source samples; integer formats as their integer value, F16 as raw bits, F32 as
+	// float bits.  out[]: DC destination samples in the same register convention.
+	template<int SF, int DF, int SC, int DC>
+	__device__ __forceinline__ void convert_pixel(const uint32_t (&in)[SC], uint32_t (&out)[DC], const PixelCtx& ctx) {
+		constexpr bool src_int = FmtTraits<SF>::is_int;
+		if constexpr(src_int) {
+			// ---- step 1: layout change in the integer domain
+			uint32_t mid[DC];
+			if constexpr(SC == DC) {
+#pragma unroll
+				for(int c = 0; c < DC; ++c) mid[c] = in[c];
+			} else if constexpr(DC == 1) {
+				constexpr bool wide = (SF == CACAO_FMT_U16);
+				const uint32_t sum = trunc_2126(in[0]) + trunc_7152<wide>(in[1]) + trunc_0722(in[2]);
+				mid[0] = min(sum, wide ? ctx.gray16_cap : 255u);
+			} else if constexpr(SC == 1) {
+				mid[0] = mid[1] = mid[2] = in[0];
+				if constexpr(DC == 4) mid[3] = (SF == CACAO_FMT_U8) ? 255u : 65535u;
+			} else {
+				mid[0] = in[0];
+				mid[1] = in[1];
+				mid[2] = in[2];
+				if constexpr(DC == 4) mid[3] = (SF == CACAO_FMT_U8) ? 255u : 65535u;
+			}
+			// ---- step 2: sample-format change
+			constexpr int M = (SF == CACAO_FMT_U8) ? 255 : 65535;
+#pragma unroll
+			for(int c = 0; c < DC; ++c) {
+				if constexpr(DF == SF) {
+					out[c] = mid[c];
+				} else if constexpr(DF == CACAO_FMT_U8) {
+					out[c] = ctx.lut[mid[c]];
+				} else if constexpr(DF == CACAO_FMT_U16) {
+					out[c] = mid[c] * 257u;
+				} else if constexpr(DF == CACAO_FMT_F32) {
+					out[c] = __float_as_uint(unorm_to_f32<M>(mid[c]));
+				} else {
+					out[c] = unorm_to_f16<M>(mid[c]);
+				}
+			}
+		} else {
+			// ---- float source: widen, layout change in fp32, narrow / quantise
+			float f[SC];
+#pragma unroll
+			for(int c = 0; c < SC; ++c) f[c] = (SF == CACAO_FMT_F32) ? __uint_as_float(in[c]) : f16_bits_to_f32(static_cast<uint16_t>(in[c]));
+			float mid[DC];
+			if constexpr(SC == DC) {
+#pragma unroll
+				for(int c = 0; c < DC; ++c) mid[c] = f[c];
+			} else if constexpr(DC == 1) {
+				mid[0] = __fmaf_rn(0.0722f, f[2], __fmaf_rn(0.7152f, f[1], __fmul_rn(0.2126f, f[0])));
+			} else if constexpr(SC == 1) {
+				mid[0] = mid[1] = mid[2] = f[0];
+				if constexpr(DC == 4) mid[3] = 1.0f;
+			} else {
+				mid[0] = f[0];
+				mid[1] = f[1];
+				mid[2] = f[2];
+				if constexpr(DC == 4) mid[3] = 1.0f;
+			}
+#pragma unroll
+			for(int c = 0; c < DC; ++c) {
+				if constexpr(DF == CACAO_FMT_F32)
+					out[c] = __float_as_uint(mid[c]);
+				else if constexpr(DF == CACAO_FMT_F16)
+					out[c] = f32_to_f16_bits(mid[c]);
+				else if constexpr(DF == CACAO_FMT_U16)
+					out[c] = f32_to_unorm<65535>(mid[c]);
+				else
+					out[c] = f32_to_unorm<255>(mid[c]);
+			}
+		}
+	}
+
+} // namespace cacao

@@ -1,0 +1,233 @@
+// equirect.cu -- equirectangular -> cubemap resampling kernel (DESIGN.md "Spec B.2").
+//
+// New functionality behind `ce-cubetool project`; the reference's cubetool only packs/unpacks six
+// ready-made faces (tools/cubetool/create.cpp:32-102, extract.cpp:50-101).
+//
+// One thread = one output pixel; a block covers a 32 x 8 patch of one face so the four bilinear
+// taps of neighbouring threads fall on the same or adjacent source lines (L1 absorbs the 4x tap
+// overlap, L2 the reuse between neighbouring patches, and HBM sees each source texel about once).
+#include "equirect.cuh"
+
+#include "cacao_device.cuh"
+#include "projection.cuh"
+
+namespace cacao {
+
+	namespace {
+
+		// ---- one texel as CH floats -------------------------------------------------------------
+		template<int F, int CH>
+		__device__ __forceinline__ void load_texel(const uint8_t* __restrict__ p, float (&v)[CH]) {
+			constexpr int sb = FmtTraits<F>::bytes;
+			constexpr int bpp = sb * CH;
+			uint32_t w[4] = {0, 0, 0, 0};
+			if constexpr(bpp == 16) {
+				const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+				w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+			} else if constexpr(bpp == 8) {
+				const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+				w[0] = q.x; w[1] = q.y;
+			} else if constexpr(bpp == 4) {
+				w[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+			} else if constexpr(bpp == 12) {
+				const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+				w[0] = __ldg(q); w[1] = __ldg(q + 1); w[2] = __ldg(q + 2);
+			} else if constexpr(bpp == 6) {
+				const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
+				w[0] = __ldg(q) | (static_cast<uint32_t>(__ldg(q + 1)) << 16);
+				w[1] = __ldg(q + 2);
+			} else if constexpr(bpp == 3) {
+				w[0] = __ldg(p) | (static_cast<uint32_t>(__ldg(p + 1)) << 8) | (static_cast<uint32_t>(__ldg(p + 2)) << 16);
+			} else if constexpr(bpp == 2) {
+				w[0] = __ldg(reinterpret_cast<const uint16_t*>(p));
+			} else {
+				w[0] = __ldg(p);
+			}
+#pragma unroll
+			for(int c = 0; c < CH; ++c) {
+				if constexpr(F == CACAO_FMT_U8)
+					v[c] = static_cast<float>((w[c >> 2] >> ((c & 3) * 8)) & 0xFFu);
+				else if constexpr(F == CACAO_FMT_U16)
+					v[c] = static_cast<float>((w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu);
+				else if constexpr(F == CACAO_FMT_F16)
+					v[c] = f16_bits_to_f32(static_cast<uint16_t>((w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu));
+				else
+					v[c] = __uint_as_float(w[c]);
+			}
+		}
+
+		template<int F, int CH>
+		__device__ __forceinline__ void store_texel(uint8_t* __restrict__ p, const float (&v)[CH]) {
+			constexpr int sb = FmtTraits<F>::bytes;
+			constexpr int bpp = sb * CH;
+			uint32_t s[CH];
+#pragma unroll
+			for(int c = 0; c < CH; ++c) {
+				if constexpr(F == CACAO_FMT_F32)
+					s[c] = __float_as_uint(v[c]);
+				else if constexpr(F == CACAO_FMT_F16)
+					s[c] = f32_to_f16_bits(v[c]);
+				else if constexpr(F == CACAO_FMT_U16)
+					s[c] = __float2uint_rz(fminf(fmaxf(v[c], 0.0f), 65535.0f) + 0.5f);
+				else
+					s[c] = __float2uint_rz(fminf(fmaxf(v[c], 0.0f), 255.0f) + 0.5f);
+			}
+			uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+			for(int c = 0; c < CH; ++c) {
+				if constexpr(sb == 1)
+					w[c >> 2] |= s[c] << ((c & 3) * 8);
+				else if constexpr(sb == 2)
+					w[c >> 1] |= s[c] << ((c & 1) * 16);
+				else
+					w[c] = s[c];
+			}
+			if constexpr(bpp == 16) {
+				*reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+			} else if constexpr(bpp == 8) {
+				*reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
+			} else if constexpr(bpp == 4) {
+				*reinterpret_cast<uint32_t*>(p) = w[0];
+			} else if constexpr(bpp == 12) {
+				uint32_t* q = reinterpret_cast<uint32_t*>(p);
+				q[0] = w[0]; q[1] = w[1]; q[2] = w[2];
+			} else if constexpr(bpp == 6) {
+				uint16_t* q = reinterpret_cast<uint16_t*>(p);
+				q[0] = static_cast<uint16_t>(w[0]); q[1] = static_cast<uint16_t>(w[0] >> 16); q[2] = static_cast<uint16_t>(w[1]);
+			} else if constexpr(bpp == 3) {
+				p[0] = static_cast<uint8_t>(w[0]); p[1] = static_cast<uint8_t>(w[0] >> 8); p[2] = static_cast<uint8_t>(w[0] >> 16);
+			} else if constexpr(bpp == 2) {
+				*reinterpret_cast<uint16_t*>(p) = static_cast<uint16_t>(w[0]);
+			} else {
+				p[0] = static_cast<uint8_t>(w[0]);
+			}
+		}
+
+		template<int F, int CH>
+		__global__ void __launch_bounds__(256) equirect_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, EquirectParams prm) {
+			constexpr int bpp = FmtTraits<F>::bytes * CH;
+			const uint32_t i = blockIdx.x * 32u + threadIdx.x;
+			const uint32_t j = prm.row_begin + blockIdx.y * 8u + threadIdx.y;
+			const uint32_t face = (prm.faces >> (4u * blockIdx.z)) & 7u;
+			if(i >= prm.N || j >= prm.row_end) return;
+
+			float xs, ys;
+			project_pixel(face, i, j, prm.pc, xs, ys);
+
+			const float fx0 = floorf(xs), fy0 = floorf(ys);
+			const float fx = xs - fx0, fy = ys - fy0;
+			int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0);
+			int x1 = x0 + 1, y1 = y0 + 1;
+			const int W = static_cast<int>(prm.W), H = static_cast<int>(prm.H);
+			// columns wrap (xs lies in [-0.5, W-0.5] so one conditional step is enough), rows clamp
+			if(x0 < 0) x0 += W;
+			if(x0 >= W) x0 -= W;
+			if(x1 < 0) x1 += W;
+			if(x1 >= W) x1 -= W;
+			y0 = min(max(y0, 0), H - 1);
+			y1 = min(max(y1, 0), H - 1);
+			// rows are stored from src_row0 on; the window was planned on the host with the same
+			// arithmetic, the clamp below only guards memory if a caller passes a short window
+			const int r0 = min(max(y0 - static_cast<int>(prm.src_row0), 0), static_cast<int>(prm.src_rows) - 1);
+			const int r1 = min(max(y1 - static_cast<int>(prm.src_row0), 0), static_cast<int>(prm.src_rows) - 1);
+
+			const size_t pitch = static_cast<size_t>(prm.W) * bpp;
+			const uint8_t* row0 = src + static_cast<size_t>(r0) * pitch;
+			const uint8_t* row1 = src + static_cast<size_t>(r1) * pitch;
+			float a[CH], b[CH], c[CH], d[CH], out[CH];
+			load_texel<F, CH>(row0 + static_cast<size_t>(x0) * bpp, a);
+			load_texel<F, CH>(row0 + static_cast<size_t>(x1) * bpp, b);
+			load_texel<F, CH>(row1 + static_cast<size_t>(x0) * bpp, c);
+			load_texel<F, CH>(row1 + static_cast<size_t>(x1) * bpp, d);
+#pragma unroll
+			for(int k = 0; k < CH; ++k) {
+				const float top = fmaf(fx, b[k] - a[k], a[k]);
+				const float bot = fmaf(fx, d[k] - c[k], c[k]);
+				out[k] = fmaf(fy, bot - top, top);
+			}
+			uint8_t* o = dst + ((static_cast<size_t>(face) * prm.N + j) * prm.N + i) * bpp;
+			store_texel<F, CH>(o, out);
+		}
+
+		template<int F, int CH>
+		cudaError_t launch(const void* src, void* dst, const EquirectParams& prm, unsigned nfaces, cudaStream_t stream) {
+			const dim3 block(32, 8, 1);
+			const dim3 grid((prm.N + 31) / 32, (prm.row_end - prm.row_begin + 7) / 8, nfaces);
+			equirect_kernel<F, CH><<<grid, block, 0, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), prm);
+			return cudaGetLastError();
+		}
+
+		template<int F>
+		cudaError_t launch_ch(const void* src, void* dst, int ch, const EquirectParams& prm, unsigned nfaces, cudaStream_t stream) {
+			switch(ch) {
+				case 1: return launch<F, 1>(src, dst, prm, nfaces, stream);
+				case 3: return launch<F, 3>(src, dst, prm, nfaces, stream);
+				case 4: return launch<F, 4>(src, dst, prm, nfaces, stream);
+			}
+			return cudaErrorInvalidValue;
+		}
+	}
+
+	cudaError_t equirect_launch(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, uint32_t face_mask, uint32_t row_begin, uint32_t row_end, cudaStream_t stream) {
+		EquirectParams prm;
+		prm.W = W;
+		prm.H = H;
+		prm.N = N;
+		prm.src_row0 = src_row0;
+		prm.src_rows = src_rows;
+		prm.row_begin = row_begin;
+		prm.row_end = row_end;
+		prm.pc = make_proj_const(N, W, H);
+		prm.faces = 0;
+		unsigned nfaces = 0;
+		for(uint32_t f = 0; f < 6; ++f)
+			if(face_mask & (1u << f)) prm.faces |= f << (4u * nfaces++);
+		if(nfaces == 0 || row_begin >= row_end) return cudaSuccess;
+		switch(fmt) {
+			case CACAO_FMT_U8: return launch_ch<CACAO_FMT_U8>(src, dst, ch, prm, nfaces, stream);
+			case CACAO_FMT_U16: return launch_ch<CACAO_FMT_U16>(src, dst, ch, prm, nfaces, stream);
+			case CACAO_FMT_F16: return launch_ch<CACAO_FMT_F16>(src, dst, ch, prm, nfaces, stream);
+			case CACAO_FMT_F32: return launch_ch<CACAO_FMT_F32>(src, dst, ch, prm, nfaces, stream);
+		}
+		return cudaErrorInvalidValue;
+	}
+
+	// Host-side planning with the same arithmetic as the kernel.  theta (hence ys) is monotone in tc
+	// for fixed sc on the side faces and a function of sc^2+tc^2 on the +-Y faces, so its extremes over
+	// a full-width row band lie on the band's first/last row or on the centre/edge columns.
+	void equirect_src_window(uint32_t W, uint32_t H, uint32_t N, uint32_t face_mask, uint32_t row_begin, uint32_t row_end, uint32_t* src_row0, uint32_t* src_rows) {
+		const ProjConst pc = make_proj_const(N, W, H);
+		float lo = 3.0e38f, hi = -3.0e38f;
+		auto visit = [&](uint32_t f, uint32_t i, uint32_t j) {
+			float xs, ys;
+			project_pixel(f, i, j, pc, xs, ys);
+			lo = ys < lo ? ys : lo;
+			hi = ys > hi ? ys : hi;
+		};
+		if(row_end > N) row_end = N;
+		for(uint32_t f = 0; f < 6; ++f) {
+			if(!(face_mask & (1u << f)) || row_begin >= row_end) continue;
+			const uint32_t cols[4] = {0, (N - 1) / 2, N / 2, N - 1};
+			for(uint32_t j = row_begin; j < row_end; ++j)
+				for(uint32_t i : cols) visit(f, i, j);
+			for(uint32_t i = 0; i < N; ++i) {
+				visit(f, i, row_begin);
+				visit(f, i, row_end - 1);
+			}
+		}
+		if(hi < lo) {
+			*src_row0 = 0;
+			*src_rows = 0;
+			return;
+		}
+		// floor(lo) .. floor(hi)+1 are the rows the taps touch; one more row of slack each side
+		long long first = static_cast<long long>(floorf(lo)) - 1;
+		long long last = static_cast<long long>(floorf(hi)) + 2;
+		if(first < 0) first = 0;
+		if(last > static_cast<long long>(H) - 1) last = static_cast<long long>(H) - 1;
+		if(last < first) last = first;
+		*src_row0 = static_cast<uint32_t>(first);
+		*src_rows = static_cast<uint32_t>(last - first + 1);
+	}
+
+} // namespace cacao

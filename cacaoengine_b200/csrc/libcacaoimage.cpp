@@ -1,0 +1,215 @@
+// libcacaoimage.cpp -- the reference's C++ image API (include/libcacaoimage.hpp) and its extensions
+// (include/libcacaoimage_ext.hpp) implemented over the C ABI in cacao_img.h.
+//
+// Mirrors the reference's conventions: inputs by const&, results by value owning a fresh
+// std::vector, metadata copied through (libs/image/src/Layout.cpp:12-13, Colordepth.cpp:11-18),
+// failures as std::runtime_error carrying the reference's message texts
+// (libs/common/include/libcacaocommon.hpp:20-25).
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <thread>
+
+#include "cacao_img.h"
+#include "libcacaoimage.hpp"
+#include "libcacaoimage_ext.hpp"
+
+namespace {
+	// status -> exception.  Argument errors that the reference reports get the reference's text;
+	// everything else (CUDA, no device) carries the C layer's detailed message.
+	void check(int status) {
+		if(status == CACAO_OK) return;
+		switch(status) {
+			case CACAO_E_SAME_LAYOUT:
+			case CACAO_E_NOT_16BIT:
+			case CACAO_E_ZERO_DIM:
+			case CACAO_E_BAD_DEPTH:
+			case CACAO_E_EMPTY: throw std::runtime_error(cacao_img_status_string(status));
+			default: throw std::runtime_error(std::string("libcacaoimage-b200: ") + cacao_img_last_error());
+		}
+	}
+
+	int fmt_of_bits(uint8_t bits) {
+		return bits == 16 ? CACAO_FMT_U16 : CACAO_FMT_U8;
+	}
+	std::size_t bytes_of(int fmt) {
+		return fmt == CACAO_FMT_U8 ? 1 : (fmt == CACAO_FMT_F32 ? 4 : 2);
+	}
+}
+
+namespace libcacaoimage {
+
+	Image Convert16To8BitColor(const Image& src) {
+		if(src.bitsPerChannel != 16) check(CACAO_E_NOT_16BIT); // Colordepth.cpp:8
+		Image out = {};
+		out.w = src.w;
+		out.h = src.h;
+		out.format = src.format;
+		out.layout = src.layout;
+		out.bitsPerChannel = 8;
+		out.lossy = src.lossy;
+		out.quality = src.quality;
+		// the reference sizes the result from the buffer, not from w*h (Colordepth.cpp:21-23)
+		const int ch = static_cast<int>(src.layout);
+		out.data.resize(src.data.size() / 2);
+		const uint64_t pixels = src.data.size() / 2 / ch;
+		if(pixels) check(cacao_img_convert(-1, src.data.data(), out.data.data(), pixels, ch, ch, CACAO_FMT_U16, CACAO_FMT_U8, CACAO_MODE_REF_EXACT, CACAO_MEM_HOST, nullptr));
+		return out;
+	}
+
+	Image ChangeChannelLayout(const Image& src, Image::Layout layout) {
+		if(src.layout == layout) check(CACAO_E_SAME_LAYOUT); // Layout.cpp:9
+		Image out = {};
+		out.w = src.w;
+		out.h = src.h;
+		out.layout = layout;
+		out.bitsPerChannel = src.bitsPerChannel;
+		out.format = src.format;
+		out.quality = src.quality;
+		out.lossy = src.lossy;
+		const int fmt = fmt_of_bits(src.bitsPerChannel);
+		const uint64_t pixels = static_cast<uint64_t>(src.w) * src.h;
+		out.data.resize(pixels * static_cast<int>(layout) * bytes_of(fmt));
+		if(pixels) check(cacao_img_convert(-1, src.data.data(), out.data.data(), pixels, static_cast<int>(src.layout), static_cast<int>(layout), fmt, fmt, CACAO_MODE_REF_EXACT, CACAO_MEM_HOST, nullptr));
+		return out;
+	}
+
+	Image Flip(const Image& src) {
+		// validation order and texts: Flip.cpp:8-10
+		if(!(src.w > 0 && src.h > 0)) check(CACAO_E_ZERO_DIM);
+		if(!(src.bitsPerChannel == 8 || src.bitsPerChannel == 16)) check(CACAO_E_BAD_DEPTH);
+		if(src.data.empty()) check(CACAO_E_EMPTY);
+		if(src.h == 1) return src; // Flip.cpp:13
+		Image out = {};
+		out.w = src.w;
+		out.h = src.h;
+		out.layout = src.layout;
+		out.bitsPerChannel = src.bitsPerChannel;
+		out.format = src.format;
+		out.quality = src.quality;
+		out.lossy = src.lossy;
+		out.data.resize(src.data.size());
+		const uint32_t bpp = static_cast<uint32_t>(src.layout) * (src.bitsPerChannel / 8);
+		check(cacao_img_flip_rows(-1, src.data.data(), out.data.data(), src.w, src.h, bpp, CACAO_MEM_HOST, nullptr));
+		return out;
+	}
+
+	// ---- extensions ----------------------------------------------------------------------------
+
+	std::size_t BytesPerPixel(Image::Layout layout, SampleFormat format) {
+		return static_cast<std::size_t>(layout) * bytes_of(static_cast<int>(format));
+	}
+
+	ImageEx FromImage(const Image& src) {
+		ImageEx out;
+		out.w = src.w;
+		out.h = src.h;
+		out.layout = src.layout;
+		out.format = src.bitsPerChannel == 16 ? SampleFormat::U16 : SampleFormat::U8;
+		out.data = src.data;
+		return out;
+	}
+
+	Image ToImage(const ImageEx& src) {
+		if(src.format != SampleFormat::U8 && src.format != SampleFormat::U16) throw std::runtime_error("libcacaoimage::Image holds only 8- or 16-bit integer samples");
+		Image out = {};
+		out.w = src.w;
+		out.h = src.h;
+		out.layout = src.layout;
+		out.bitsPerChannel = src.format == SampleFormat::U16 ? 16 : 8;
+		out.data = src.data;
+		out.format = Image::Format::PNG;
+		out.quality = 100;
+		out.lossy = false;
+		return out;
+	}
+
+	ImageEx Convert(const ImageEx& src, Image::Layout layout, SampleFormat format, ConvertMode mode) {
+		ImageEx out;
+		out.w = src.w;
+		out.h = src.h;
+		out.layout = layout;
+		out.format = format;
+		const uint64_t pixels = static_cast<uint64_t>(src.w) * src.h;
+		out.data.resize(pixels * BytesPerPixel(layout, format));
+		if(src.layout == layout && src.format == format) check(CACAO_E_SAME_LAYOUT);
+		if(pixels) check(cacao_img_convert(-1, src.data.data(), out.data.data(), pixels, static_cast<int>(src.layout), static_cast<int>(layout), static_cast<int>(src.format), static_cast<int>(format), static_cast<int>(mode), CACAO_MEM_HOST, nullptr));
+		return out;
+	}
+
+	Image ToRGB8(const Image& src) {
+		if(src.bitsPerChannel == 8 && src.layout == Image::Layout::RGB) return src;
+		Image out = {};
+		out.w = src.w;
+		out.h = src.h;
+		out.layout = Image::Layout::RGB;
+		out.bitsPerChannel = 8;
+		out.format = src.format;
+		out.quality = src.quality;
+		out.lossy = src.lossy;
+		const uint64_t pixels = static_cast<uint64_t>(src.w) * src.h;
+		out.data.resize(pixels * 3);
+		if(pixels) check(cacao_img_convert(-1, src.data.data(), out.data.data(), pixels, static_cast<int>(src.layout), 3, fmt_of_bits(src.bitsPerChannel), CACAO_FMT_U8, CACAO_MODE_REF_EXACT, CACAO_MEM_HOST, nullptr));
+		return out;
+	}
+
+	ImageEx Flip(const ImageEx& src) {
+		if(!(src.w > 0 && src.h > 0)) check(CACAO_E_ZERO_DIM);
+		if(src.data.empty()) check(CACAO_E_EMPTY);
+		ImageEx out = src;
+		if(src.h == 1) return out;
+		check(cacao_img_flip_rows(-1, src.data.data(), out.data.data(), src.w, src.h, static_cast<uint32_t>(BytesPerPixel(src.layout, src.format)), CACAO_MEM_HOST, nullptr));
+		return out;
+	}
+
+	std::array<ImageEx, 6> EquirectToCubemap(const ImageEx& src, unsigned int faceSize, const std::vector<int>& devices) {
+		if(src.w == 0 || src.h == 0 || faceSize == 0) check(CACAO_E_ZERO_DIM);
+		const std::size_t bpp = BytesPerPixel(src.layout, src.format);
+		if(src.data.size() < static_cast<std::size_t>(src.w) * src.h * bpp) throw std::runtime_error("equirect source buffer is smaller than w*h*bytes-per-pixel");
+		const std::size_t face_bytes = static_cast<std::size_t>(faceSize) * faceSize * bpp;
+		std::vector<unsigned char> cube(6 * face_bytes);
+
+		// work units: (face, row band); bands sized so every device gets several units
+		std::vector<int> devs = devices.empty() ? std::vector<int>{-1} : devices;
+		const unsigned bands = devs.size() > 1 ? 4u : 1u;
+		struct Unit {
+			unsigned face, r0, r1;
+		};
+		std::vector<Unit> units;
+		for(unsigned f = 0; f < 6; ++f)
+			for(unsigned b = 0; b < bands; ++b) {
+				const unsigned r0 = static_cast<unsigned>(static_cast<uint64_t>(faceSize) * b / bands);
+				const unsigned r1 = static_cast<unsigned>(static_cast<uint64_t>(faceSize) * (b + 1) / bands);
+				if(r1 > r0) units.push_back({f, r0, r1});
+			}
+		std::vector<std::string> errors(devs.size());
+		auto worker = [&](std::size_t k) {
+			for(std::size_t u = k; u < units.size(); u += devs.size()) {
+				const Unit& un = units[u];
+				const int rc = cacao_img_equirect_to_cube(devs[k], src.data.data(), src.w, src.h, 0, src.h, static_cast<int>(src.layout), static_cast<int>(src.format), cube.data(), faceSize, 1u << un.face, un.r0, un.r1, CACAO_MEM_HOST, nullptr);
+				if(rc != CACAO_OK) {
+					errors[k] = cacao_img_last_error();
+					return;
+				}
+			}
+		};
+		if(devs.size() == 1) {
+			// single device: all six faces in one launch
+			check(cacao_img_equirect_to_cube(devs[0], src.data.data(), src.w, src.h, 0, src.h, static_cast<int>(src.layout), static_cast<int>(src.format), cube.data(), faceSize, 0x3F, 0, faceSize, CACAO_MEM_HOST, nullptr));
+		} else {
+			std::vector<std::thread> pool;
+			for(std::size_t k = 0; k < devs.size(); ++k) pool.emplace_back(worker, k);
+			for(auto& t : pool) t.join();
+			for(const auto& e : errors)
+				if(!e.empty()) throw std::runtime_error("libcacaoimage-b200: " + e);
+		}
+		std::array<ImageEx, 6> faces;
+		for(unsigned f = 0; f < 6; ++f) {
+			faces[f].w = faces[f].h = faceSize;
+			faces[f].layout = src.layout;
+			faces[f].format = src.format;
+			faces[f].data.assign(cube.begin() + f * face_bytes, cube.begin() + (f + 1) * face_bytes);
+		}
+		return faces;
+	}
+}

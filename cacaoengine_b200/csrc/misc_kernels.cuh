@@ -1,0 +1,19 @@
+// misc_kernels.cuh -- flip, synthetic-input and checksum kernels (see misc_kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace cacao {
+
+	// out.row[y] = src.row[h-1-y]; pitch in bytes (the semantics libs/image/src/Flip.cpp:6-42 intends)
+	cudaError_t flip_rows_launch(const void* src, void* dst, uint64_t pitch, uint32_t h, int sm_count, cudaStream_t stream);
+
+	// counter-hash synthetic samples (DESIGN.md "Synthetic inputs")
+	cudaError_t synth_launch(void* dst, uint64_t first_sample, uint64_t samples, int fmt, int ch, uint32_t seed, int sm_count, cudaStream_t stream);
+
+	// sum over 32-bit words of fmix32(word + index * 0x9E3779B9) into *accum (device, pre-zeroed)
+	cudaError_t checksum_launch(const void* src, uint64_t words, unsigned long long* accum, int sm_count, cudaStream_t stream);
+
+} // namespace cacao

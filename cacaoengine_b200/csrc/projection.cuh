@@ -1,0 +1,100 @@
+// projection.cuh -- cube-face pixel -> equirect sample position, DESIGN.md "Spec B.2".
+//
+// No reference counterpart (tools/cubetool/main.cpp:31-33 has only create/extract).  What the
+// reference does constrain: face order +X,-X,+Y,-Y,+Z,-Z = right,left,up,down,front,back
+// (libs/formats/include/libcacaoformats.hpp:213, tools/cubetool/commands.hpp:31) and top-row-first
+// storage consumed by Vulkan without a flip (engine/src/vulkan/impls/VulkanCubemap.cpp:30-34).
+//
+// The whole chain is fp32 with a FIXED operation order: IEEE add/mul/div/sqrt plus fused
+// multiply-adds only where written as fmaf().  The library is compiled with -fmad=false (device)
+// so the compiler fuses nothing else; the host planner below runs the same code on the CPU.  The
+// oracle restates this spec independently in C (oracle/cacao_oracle.c), and the two agree bit for
+// bit in (xs, ys) -- so the filtered faces agree bit for bit too.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+
+#ifdef __CUDACC__
+#define CACAO_HD __host__ __device__ __forceinline__
+#else
+#define CACAO_HD inline
+#endif
+
+namespace cacao {
+
+	constexpr float kPi = 3.14159265358979323846f;
+	constexpr float kPi2 = 1.57079632679489661923f;
+	constexpr float kPi4 = 0.78539816339744830962f;
+	constexpr float kInv2Pi = 0.15915494309189533577f;
+	constexpr float kInvPi = 0.31830988618379067154f;
+	constexpr float kTanPi8 = 0.41421356237309504880f;
+
+	// atan2 with one division: reduce to t in [-(sqrt2-1), sqrt2-1] via
+	// atan(a/b) = pi/4 + atan((a-b)/(a+b)), then a 4-term odd polynomial (the classic single-precision
+	// coefficient set); |error| <= ~1.1 ulp of pi against libm over the cube's directions.
+	CACAO_HD float atan2_spec(float y, float x) {
+		const float ax = fabsf(x), ay = fabsf(y);
+		const float a = ax < ay ? ax : ay;
+		const float b = ax < ay ? ay : ax;
+		if(b == 0.0f) return 0.0f;
+		const bool hi = a > kTanPi8 * b;
+		const float num = hi ? a - b : a;
+		const float den = hi ? a + b : b;
+		const float off = hi ? kPi4 : 0.0f;
+		const float t = num / den;
+		const float z = t * t;
+		float p = fmaf(8.05374449538e-2f, z, -1.38776856032e-1f);
+		p = fmaf(p, z, 1.99777106478e-1f);
+		p = fmaf(p, z, -3.33329491539e-1f);
+		float r = fmaf(p * z, t, t);
+		r = r + off;
+		if(ay > ax) r = kPi2 - r;
+		if(x < 0.0f) r = kPi - r;
+		if(y < 0.0f) r = -r;
+		return r;
+	}
+
+	struct ProjConst {
+		float invN;   // 1.0f / N
+		float kx, ky; // W/(2 pi), H/pi
+		float cx, cy; // W/2 - 1/2, H/2 - 1/2
+	};
+
+	CACAO_HD ProjConst make_proj_const(uint32_t N, uint32_t W, uint32_t H) {
+		ProjConst c;
+		c.invN = 1.0f / static_cast<float>(N);
+		c.kx = static_cast<float>(W) * kInv2Pi;
+		c.ky = static_cast<float>(H) * kInvPi;
+		c.cx = 0.5f * static_cast<float>(W) - 0.5f;
+		c.cy = 0.5f * static_cast<float>(H) - 0.5f;
+		return c;
+	}
+
+	// Khronos cube-map face table
+	CACAO_HD void face_direction(uint32_t face, float sc, float tc, float& x, float& y, float& z) {
+		switch(face) {
+			case 0: x = 1.0f; y = -tc; z = -sc; break;   // +X right
+			case 1: x = -1.0f; y = -tc; z = sc; break;   // -X left
+			case 2: x = sc; y = 1.0f; z = tc; break;     // +Y up
+			case 3: x = sc; y = -1.0f; z = -tc; break;   // -Y down
+			case 4: x = sc; y = -tc; z = 1.0f; break;    // +Z front
+			default: x = -sc; y = -tc; z = -1.0f; break; // -Z back
+		}
+	}
+
+	// face pixel (column i, row j) -> continuous source position (texel centres at integer + 0.5
+	// already removed: xs, ys index texel centres directly)
+	CACAO_HD void project_pixel(uint32_t face, uint32_t i, uint32_t j, const ProjConst& c, float& xs, float& ys) {
+		const float sc = fmaf(static_cast<float>(2u * i + 1u), c.invN, -1.0f);
+		const float tc = fmaf(static_cast<float>(2u * j + 1u), c.invN, -1.0f);
+		float x, y, z;
+		face_direction(face, sc, tc, x, y, z);
+		const float phi = atan2_spec(x, z);
+		const float rxz = sqrtf(fmaf(x, x, z * z));
+		const float theta = atan2_spec(y, rxz);
+		xs = fmaf(phi, c.kx, c.cx);
+		ys = fmaf(-theta, c.ky, c.cy);
+	}
+
+} // namespace cacao

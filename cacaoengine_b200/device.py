@@ -1,0 +1,101 @@
+"""Device-buffer layer: thin wrappers over cacao_img_malloc / upload / download and the
+device-pointer forms of the hot-path calls.  Pointers are plain ints (CUDA device addresses), so
+torch tensors (`t.data_ptr()`) and cacao_img_malloc buffers both work; `stream` is a cudaStream_t
+handle as an int (e.g. torch.cuda.current_stream().cuda_stream) or None for the default stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+
+
+def device_count() -> int:
+	return capi.lib().cacao_img_device_count()
+
+
+def init(device: int = -1) -> None:
+	capi.check(capi.lib().cacao_img_init(device))
+
+
+def launch_count() -> int:
+	return int(capi.lib().cacao_img_launch_count())
+
+
+def malloc(nbytes: int, device: int = -1) -> int:
+	p = C.c_void_p()
+	capi.check(capi.lib().cacao_img_malloc(device, C.byref(p), nbytes))
+	return int(p.value)
+
+
+def free(ptr: int, device: int = -1) -> None:
+	capi.check(capi.lib().cacao_img_free(device, ptr))
+
+
+def host_alloc(nbytes: int) -> tuple[int, np.ndarray]:
+	"""Pinned host buffer: (address, uint8 numpy view).  Release with host_free(address)."""
+	p = C.c_void_p()
+	capi.check(capi.lib().cacao_img_host_alloc(C.byref(p), nbytes))
+	arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))
+	return int(p.value), arr
+
+
+def host_free(ptr: int) -> None:
+	capi.check(capi.lib().cacao_img_host_free(ptr))
+
+
+def upload(dst_dev: int, src: np.ndarray, device: int = -1, stream=None) -> None:
+	s = np.ascontiguousarray(src)
+	capi.check(capi.lib().cacao_img_upload(device, dst_dev, s.ctypes.data, s.nbytes, stream))
+	if stream is None:
+		sync(device)
+
+
+def download(dst: np.ndarray, src_dev: int, device: int = -1, stream=None) -> None:
+	assert dst.flags["C_CONTIGUOUS"]
+	capi.check(capi.lib().cacao_img_download(device, dst.ctypes.data, src_dev, dst.nbytes, stream))
+	sync(device, stream)
+
+
+def sync(device: int = -1, stream=None) -> None:
+	capi.check(capi.lib().cacao_img_sync(device, stream))
+
+
+def convert(src: int, dst: int, pixels: int, src_ch: int, dst_ch: int, src_fmt: int, dst_fmt: int, mode: int = capi.MODE_REF_EXACT, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> None:
+	capi.check(capi.lib().cacao_img_convert(device, src, dst, pixels, src_ch, dst_ch, src_fmt, dst_fmt, mode, mem, stream))
+
+
+def convert_batch(src: int, dst: int, pixels_per_image: int, count: int, src_ch: int, dst_ch: int, src_fmt: int, dst_fmt: int, mode: int = capi.MODE_REF_EXACT, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> None:
+	capi.check(capi.lib().cacao_img_convert_batch(device, src, dst, pixels_per_image, count, src_ch, dst_ch, src_fmt, dst_fmt, mode, mem, stream))
+
+
+def flip_rows(src: int, dst: int, w: int, h: int, bytes_per_pixel: int, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> None:
+	capi.check(capi.lib().cacao_img_flip_rows(device, src, dst, w, h, bytes_per_pixel, mem, stream))
+
+
+def equirect_to_cube(src: int, W: int, H: int, ch: int, fmt: int, dst: int, N: int, face_mask: int = 0x3F, row_begin: int = 0, row_end: int | None = None, src_row0: int = 0, src_rows: int | None = None, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> None:
+	capi.check(capi.lib().cacao_img_equirect_to_cube(device, src, W, H, src_row0, H if src_rows is None else src_rows, ch, fmt, dst, N, face_mask, row_begin, N if row_end is None else row_end, mem, stream))
+
+
+def equirect_src_window(W: int, H: int, N: int, face_mask: int, row_begin: int, row_end: int) -> tuple[int, int]:
+	r0, n = C.c_uint32(), C.c_uint32()
+	capi.check(capi.lib().cacao_img_equirect_src_window(W, H, N, face_mask, row_begin, row_end, C.byref(r0), C.byref(n)))
+	return int(r0.value), int(n.value)
+
+
+def synth(dst: int, samples: int, fmt: int, ch: int, seed: int, first_sample: int = 0, device: int = -1, stream=None) -> None:
+	capi.check(capi.lib().cacao_img_synth(device, dst, first_sample, samples, fmt, ch, seed, stream))
+
+
+def checksum(src: int, nbytes: int, device: int = -1, stream=None) -> int:
+	out = C.c_uint64()
+	capi.check(capi.lib().cacao_img_checksum(device, src, nbytes, C.byref(out), stream))
+	return int(out.value)
+
+
+def get_lut() -> np.ndarray:
+	out = np.empty(65536, np.uint8)
+	capi.check(capi.lib().cacao_img_get_lut(out.ctypes.data))
+	return out

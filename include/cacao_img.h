@@ -1,0 +1,150 @@
+/*
+ * cacao_img.h -- C ABI of the B200-native libcacaoimage / cubetool pixel hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer around this path: the
+ * interface is the C++ header libs/image/include/libcacaoimage.hpp (free functions taking
+ * `const Image&`, returning `Image`, throwing std::runtime_error).  include/libcacaoimage.hpp
+ * in this repo keeps that header's API and forwards every pixel loop to the entry points
+ * below; INTEGRATION.md shows the change a reference maintainer would make.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types; nothing throws across this boundary.
+ *   - every function returns 0 (CACAO_OK) or a negative cacao_status; the text for the calling
+ *     thread's last failure is cacao_img_last_error().
+ *   - `device` is a CUDA ordinal, or -1 for the calling thread's current CUDA device.
+ *   - `mem` says where src/dst live.  CACAO_MEM_DEVICE: both are device pointers on `device`;
+ *     the work is enqueued on `stream` (a cudaStream_t, NULL = legacy default stream) and the call
+ *     returns without synchronising.  CACAO_MEM_HOST: both are host pointers; the call uploads,
+ *     converts and reads back through an internal chunked three-stream pipeline and returns when
+ *     dst is complete (`stream` is ignored).
+ *   - images are tightly packed, interleaved, top row first, pitch = w*channels*bytes(sample)
+ *     (libs/image/src/Layout.cpp:18-19); 16-bit samples are native little-endian
+ *     (libs/image/src/Colordepth.cpp:32).
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point fails
+ *     with CACAO_E_NO_DEVICE.
+ */
+#ifndef CACAO_IMG_H
+#define CACAO_IMG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CACAO_IMG_ABI_VERSION 1
+
+typedef enum cacao_sample_fmt {
+	CACAO_FMT_U8 = 0,  /* Image::bitsPerChannel == 8  (libcacaoimage.hpp:20) */
+	CACAO_FMT_U16 = 1, /* Image::bitsPerChannel == 16 */
+	CACAO_FMT_F16 = 2, /* extension: IEEE binary16 */
+	CACAO_FMT_F32 = 3  /* extension: IEEE binary32 */
+} cacao_sample_fmt;
+
+typedef enum cacao_mode {
+	CACAO_MODE_REF_EXACT = 0, /* bit-exact with the reference, quirks included ("Quirks") */
+	CACAO_MODE_FIXED = 1      /* Gray->RGBA replicates per pixel; 16-bit gray clamps to 65535 */
+} cacao_mode;
+
+typedef enum cacao_mem { CACAO_MEM_HOST = 0, CACAO_MEM_DEVICE = 1 } cacao_mem;
+
+typedef enum cacao_status {
+	CACAO_OK = 0,
+	CACAO_E_SAME_LAYOUT = -1, /* Layout.cpp:9   "Cannot change an image's channel layout to its current layout!" */
+	CACAO_E_NOT_16BIT = -2,   /* Colordepth.cpp:8 "Source image for 16 to 8-bit color conversion does not have a 16-bit color depth!" */
+	CACAO_E_BAD_ARG = -3,
+	CACAO_E_CUDA = -4,
+	CACAO_E_NO_DEVICE = -5,
+	CACAO_E_ZERO_DIM = -6,  /* Flip.cpp:8  "Cannot flip an image with zeroed dimensions!" */
+	CACAO_E_BAD_DEPTH = -7, /* Flip.cpp:9  "Invalid color depth; only 8 and 16 are allowed." */
+	CACAO_E_EMPTY = -8,     /* Flip.cpp:10 "Cannot flip an image with a zero-sized data buffer!" */
+	CACAO_E_NO_MEMORY = -9
+} cacao_status;
+
+/* ---- library / device ------------------------------------------------------------------ */
+int cacao_img_abi_version(void);
+const char* cacao_img_last_error(void);          /* thread-local, never NULL */
+const char* cacao_img_status_string(int status); /* the reference's exception text where one exists */
+int cacao_img_device_count(void);                /* >= 0, or a negative status */
+int cacao_img_init(int device);                  /* idempotent; builds the device context (LUT upload, streams) */
+int cacao_img_shutdown(void);                    /* releases every context */
+uint64_t cacao_img_launch_count(void);           /* kernels launched by this library so far (all threads) */
+
+/* ---- device-buffer / upload / readback layer (new; no reference counterpart) -------------- */
+int cacao_img_malloc(int device, void** dev_ptr, uint64_t bytes);
+int cacao_img_free(int device, void* dev_ptr);
+int cacao_img_host_alloc(void** host_ptr, uint64_t bytes); /* pinned, portable across devices */
+int cacao_img_host_free(void* host_ptr);
+int cacao_img_upload(int device, void* dst_dev, const void* src_host, uint64_t bytes, void* stream);
+int cacao_img_download(int device, void* dst_host, const void* src_dev, uint64_t bytes, void* stream);
+int cacao_img_sync(int device, void* stream); /* stream == NULL: whole device */
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+
+/*
+ * Fused channel-layout + sample-format conversion of `pixels` pixels.
+ *   replaces  ChangeChannelLayout   (libs/image/src/Layout.cpp:8-103)      src_fmt == dst_fmt in {U8,U16}
+ *             Convert16To8BitColor  (libs/image/src/Colordepth.cpp:7-41)   U16 -> U8, src_ch == dst_ch
+ *             both in one pass      (engine/src/core/Cubemap.cpp:28-31)    e.g. RGBA16 -> RGB8
+ *   extends   to F16/F32 per DESIGN.md "Spec B.1" (no reference counterpart).
+ * Channel counts are Image::Layout values: 1 (Grayscale), 3 (RGB), 4 (RGBA).
+ * src_ch == dst_ch && src_fmt == dst_fmt -> CACAO_E_SAME_LAYOUT (Layout.cpp:9).
+ */
+int cacao_img_convert(int device, const void* src, void* dst, uint64_t pixels, int src_ch, int dst_ch,
+					  int src_fmt, int dst_fmt, int mode, int mem, void* stream);
+
+/*
+ * The same conversion over `count` equal-size images stored back to back (image k starts at
+ * byte k*pixels_per_image*src_bytes_per_pixel).  One launch for the whole batch; each image is its
+ * own domain for the Gray->RGBA pixel-0 quirk.
+ */
+int cacao_img_convert_batch(int device, const void* src, void* dst, uint64_t pixels_per_image, uint64_t count,
+							int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, int mem, void* stream);
+
+/*
+ * Vertical mirror, out.row[y] = src.row[h-1-y], src untouched: the semantics
+ * libs/image/src/Flip.cpp:6-42 intends (the reference itself overruns its buffer for h >= 2).
+ */
+int cacao_img_flip_rows(int device, const void* src, void* dst, uint32_t w, uint32_t h,
+						uint32_t bytes_per_pixel, int mem, void* stream);
+
+/*
+ * Equirectangular -> cubemap, direction->UV projection + bilinear (DESIGN.md "Spec B.2"; new
+ * `ce-cubetool project` subcommand -- the reference's cubetool has only create/extract,
+ * tools/cubetool/main.cpp:31-33).
+ *   src       rows [src_row0, src_row0+src_rows) of a W x H equirect image, `ch` channels of `fmt`
+ *             (pass src_row0 = 0, src_rows = H for the whole image; a shard passes the window
+ *             returned by cacao_img_equirect_src_window)
+ *   dst       base of the FULL cube buffer: 6 faces x N x N pixels, face-major in the order
+ *             +X,-X,+Y,-Y,+Z,-Z (libs/formats/include/libcacaoformats.hpp:213), rows top first
+ *   face_mask bit f set = produce face f;  rows [row_begin,row_end) of each selected face are written
+ * With CACAO_MEM_HOST only the written rows are read back into dst.
+ */
+int cacao_img_equirect_to_cube(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0,
+							   uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, uint32_t face_mask,
+							   uint32_t row_begin, uint32_t row_end, int mem, void* stream);
+
+/* Host-side planning: the inclusive-exclusive window of source rows that the work unit
+ * (face_mask, [row_begin,row_end)) reads, so a shard can upload just that band. */
+int cacao_img_equirect_src_window(uint32_t W, uint32_t H, uint32_t N, uint32_t face_mask, uint32_t row_begin,
+								  uint32_t row_end, uint32_t* src_row0, uint32_t* src_rows);
+
+/* ---- support for measurement and verification (device-side, deterministic) ---------------- */
+
+/* Fill dst_dev with the counter-hash synthetic samples [first_sample, first_sample+samples)
+ * (DESIGN.md "Synthetic inputs"; identical to oracle/cacao_oracle.c orc_synth on the host). */
+int cacao_img_synth(int device, void* dst_dev, uint64_t first_sample, uint64_t samples, int fmt, int ch,
+					uint32_t seed, void* stream);
+
+/* Position-sensitive 64-bit checksum of a device buffer (sum over 32-bit words of
+ * hash(word, index)); bytes must be a multiple of 4.  Synchronises `stream`. */
+int cacao_img_checksum(int device, const void* src_dev, uint64_t bytes, uint64_t* out, void* stream);
+
+/* The 65536-entry 16->8 table in use (libs/image/LUTGen.cpp:20-28), copied to out. */
+int cacao_img_get_lut(uint8_t* out65536);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CACAO_IMG_H */
