@@ -67,8 +67,17 @@ namespace cacao {
 	}
 
 	// ---- binary16 <-> binary32, round-to-nearest-even ------------------------------------------
-	__device__ __forceinline__ uint16_t f32_to_f16_bits(float f) {
-		return __half_as_ushort(__float2half_rn(f));
+	// The bits come out of the packed two-lane convert into a 32-bit register on purpose: ptxas
+	// 12.9 miscompiles "cvt.rn.f16.f32 into a .b16 register, then store/extract its low byte" into
+	// F2I.U8.F16 (a VALUE conversion of the half) -- seen in the byte-wise edge kernel.  A .b32
+	// result keeps that pattern from forming.  tests/test_abi.py greps the SASS for it.
+	__device__ __forceinline__ uint32_t f32x2_to_f16x2_bits(float lo, float hi) {
+		uint32_t r;
+		asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+		return r;
+	}
+	__device__ __forceinline__ uint32_t f32_to_f16_bits(float f) {
+		return f32x2_to_f16x2_bits(f, 0.0f) & 0xFFFFu;
 	}
 	__device__ __forceinline__ float f16_bits_to_f32(uint16_t h) {
 		return __half2float(__ushort_as_half(h));

@@ -51,7 +51,7 @@ namespace cacao {
 	// RNE_f16((float)v / (float)M): the single multiply already rounds to the same binary16 for
 	// every v (exhaustively checked), so the correction step is skipped.
 	template<int M>
-	__device__ __forceinline__ uint16_t unorm_to_f16(uint32_t v) {
+	__device__ __forceinline__ uint32_t unorm_to_f16(uint32_t v) {
 		constexpr float r = 1.0f / static_cast<float>(M);
 		return f32_to_f16_bits(static_cast<float>(v) * r);
 	}

@@ -51,6 +51,17 @@ def test_sass_is_sm100a_only(built_lib):
 	assert archs == {"100a"}, archs
 
 
+def test_sass_free_of_known_ptxas_miscompile(built_lib):
+	"""ptxas 12.9 turns 'cvt.rn.f16.f32 into a .b16 register, then take its low byte' into F2I.U8.F16,
+	a value conversion of the half (first GPU run: byte-wise edge kernel wrote 0x3400 for 0x34F5).
+	cacao_device.cuh routes every f32->f16 through a .b32 register; make sure the pattern stays gone."""
+	from cacaoengine_b200 import _capi
+
+	sass = subprocess.run(["cuobjdump", "-sass", _capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+	assert not re.search(r"F2I\.[US](8|16)\.F16", sass)
+	assert "STG.E.128" in sass and "LDG.E.128" in sass  # 16-byte vectorised global access is really there
+
+
 def test_status_strings_are_the_reference_messages(built_lib):
 	from cacaoengine_b200 import _capi as c
 

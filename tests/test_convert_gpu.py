@@ -1,0 +1,260 @@
+"""GPU parity: the CUDA conversion path (through the C ABI) against the CPU oracle, bit for bit.
+
+Integer ops are reference parity (the oracle is pinned to the compiled reference, test_oracle.py);
+float-format ops are parity with our CPU restatement of DESIGN.md Spec B.1 -- the reference has no
+float formats, so those are "parity unpinned vs reference".
+"""
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+from gpu_util import FMTS, NAME, NP, convert_device, convert_host, random_samples, same_bits
+
+pytestmark = pytest.mark.gpu
+
+CH = (1, 3, 4)
+SHAPES = [(sf, df, sc, dc) for sf, df, sc, dc in itertools.product(FMTS, FMTS, CH, CH) if not (sf == df and sc == dc)]
+# 1 pixel; under one tile; tiles + tail; many tiles with a partial unroll group
+SIZES = (1, 17, 1000, 40961)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib(built_lib):
+	from cacaoengine_b200 import device
+
+	device.init()
+	yield
+
+
+@pytest.mark.parametrize("sf,df,sc,dc", SHAPES, ids=[f"{NAME[a]}x{c}-{NAME[b]}x{d}" for a, b, c, d in SHAPES])
+def test_every_shape_matches_oracle(oracle, sf, df, sc, dc):
+	rng = np.random.default_rng(hash((sf, df, sc, dc)) & 0xFFFF)
+	for mode in (0, 1):
+		for px in SIZES:
+			src = random_samples(rng, px * sc, sf)
+			want = oracle.convert(src, sc, dc, sf, df, mode)
+			got_d = convert_device(src, sc, dc, sf, df, mode)
+			assert same_bits(got_d, want), (mode, px, "device")
+			if px in (17, 40961):
+				got_h = convert_host(src, sc, dc, sf, df, mode)
+				assert same_bits(got_h, want), (mode, px, "host")
+
+
+def test_golden_reference_vectors(golden):
+	"""Outputs of the UNMODIFIED reference (tests/golden/ref_golden.npz) reproduced on the GPU."""
+	from cacaoengine_b200 import _capi as c
+
+	n = 0
+	for key in golden.files:
+		if not key.endswith("_in"):
+			continue
+		base = key[:-3]
+		src, want = golden[key], golden[base + "_out"]
+		if base.startswith("layout_"):
+			_, bits, pair, _ = base.split("_")
+			sc, dc = (int(x) for x in pair.split("to"))
+			fmt = c.FMT_U8 if bits == "8" else c.FMT_U16
+			got = convert_device(src, sc, dc, fmt, fmt)
+			got_h = convert_host(src, sc, dc, fmt, fmt)
+		else:
+			ch = 4 if "rgba" in base else 1
+			got = convert_device(src, ch, ch, c.FMT_U16, c.FMT_U8)
+			got_h = convert_host(src, ch, ch, c.FMT_U16, c.FMT_U8)
+		assert (got == want).all() and (got_h == want).all(), base
+		n += 1
+	assert n >= 26
+
+
+def test_gray_weights_exhaustive(golden):
+	"""All 65536 inputs through each BT.709 weight: the integer form + 1-in-625 double path must equal
+	the reference's truncated double products (Layout.cpp:70-72)."""
+	from cacaoengine_b200 import _capi as c
+
+	allv = np.arange(65536, dtype=np.uint16)
+	for k, name in enumerate("rgb"):
+		px = np.zeros((65536, 3), np.uint16)
+		px[:, k] = allv
+		got = convert_device(px.reshape(-1), 3, 1, c.FMT_U16, c.FMT_U16)
+		assert (got == golden[f"gray16_{name}_out"]).all(), name
+	# 8-bit: all 2^24 RGB triples would be overkill; all values per channel + a random cloud
+	for k in range(3):
+		px = np.zeros((256, 4), np.uint8)
+		px[:, k] = np.arange(256)
+		want_k = (np.float64([0.2126, 0.7152, 0.0722][k]) * np.arange(256)).astype(np.uint8)
+		assert (convert_device(px.reshape(-1), 4, 1, c.FMT_U8, c.FMT_U8) == want_k).all()
+
+
+def test_unorm_to_float_exhaustive(oracle):
+	from cacaoengine_b200 import _capi as c
+
+	for fmt, n in ((c.FMT_U8, 256), (c.FMT_U16, 65536)):
+		v = np.arange(n).astype(NP[fmt])
+		f32 = convert_device(v, 1, 3, fmt, c.FMT_F32).reshape(-1, 3)
+		assert same_bits(f32[:, 0].copy(), v.astype(np.float32) / np.float32(n - 1))
+		f16 = convert_device(v, 1, 3, fmt, c.FMT_F16).reshape(-1, 3)
+		assert same_bits(f16[:, 2].copy(), (v.astype(np.float32) / np.float32(n - 1)).astype(np.float16))
+		assert same_bits(convert_device(v, 1, 3, fmt, c.FMT_F32), oracle.convert(v, 1, 3, fmt, c.FMT_F32))
+
+
+def test_float_to_unorm_rounding_boundaries(oracle):
+	from cacaoengine_b200 import _capi as c
+
+	# values straddling every u8 rounding boundary (k + 0.5)/255 by a few ulps
+	k = np.arange(255, dtype=np.float64)
+	mid = ((k + 0.5) / 255.0).astype(np.float32)
+	pts = np.concatenate([np.nextafter(mid, np.float32(0)), mid, np.nextafter(mid, np.float32(1)), np.float32([np.nan, -1e30, 1e30])])
+	src = np.repeat(pts, 3)
+	assert same_bits(convert_device(src, 3, 4, c.FMT_F32, c.FMT_U8), oracle.convert(src, 3, 4, c.FMT_F32, c.FMT_U8))
+	assert same_bits(convert_device(src, 3, 4, c.FMT_F32, c.FMT_U16), oracle.convert(src, 3, 4, c.FMT_F32, c.FMT_U16))
+
+
+def test_batch_pixel0_quirk_is_per_image(oracle):
+	"""Gray->RGBA in REF_EXACT mode repeats pixel 0 of EACH image (Layout.cpp:50-51)."""
+	from cacaoengine_b200 import _capi as c
+
+	rng = np.random.default_rng(9)
+	count, ppi = 5, 700
+	src = rng.integers(0, 256, count * ppi).astype(np.uint8)
+	want = np.concatenate([oracle.change_layout(src[k * ppi:(k + 1) * ppi], 1, 4) for k in range(count)])
+	assert (convert_device(src, 1, 4, c.FMT_U8, c.FMT_U8, count=count) == want).all()
+	assert (convert_host(src, 1, 4, c.FMT_U8, c.FMT_U8, count=count) == want).all()
+	fixed = convert_device(src, 1, 4, c.FMT_U8, c.FMT_U8, mode=c.MODE_FIXED, count=count).reshape(-1, 4)
+	assert (fixed[:, 0] == src).all() and (fixed[:, 3] == 255).all()
+
+
+def test_unaligned_device_pointers_take_the_edge_path(oracle):
+	from cacaoengine_b200 import _capi as c
+
+	rng = np.random.default_rng(10)
+	src = rng.integers(0, 256, 5000 * 3).astype(np.uint8)
+	want = oracle.change_layout(src, 3, 4)
+	assert (convert_device(src, 3, 4, c.FMT_U8, c.FMT_U8, src_off=1) == want).all()
+	assert (convert_device(src, 3, 4, c.FMT_U8, c.FMT_U8, dst_off=4) == want).all()
+
+
+def test_fused_engine_composition(oracle):
+	"""RGBA16 -> RGB8 in one kernel == Convert16To8BitColor then ChangeChannelLayout (Cubemap.cpp:28-31)."""
+	from cacaoengine_b200 import _capi as c
+
+	rng = np.random.default_rng(12)
+	src = rng.integers(0, 65536, 1024 * 64 * 4).astype(np.uint16)
+	two_step = oracle.change_layout(oracle.depth16to8(src), 4, 3)
+	assert (convert_device(src, 4, 3, c.FMT_U16, c.FMT_U8) == two_step).all()
+
+
+def test_python_mirror_of_reference_api(oracle):
+	import cacaoengine_b200 as ce
+
+	rng = np.random.default_rng(13)
+	w, h = 67, 29
+	data = rng.integers(0, 65536, w * h * 4).astype(np.uint16)
+	img = ce.Image(w, h, ce.Layout.RGBA, 16, data.view(np.uint8), format=2, quality=55, lossy=True)
+	out8 = ce.Convert16To8BitColor(img)
+	assert (out8.w, out8.h, out8.layout, out8.bitsPerChannel, out8.format, out8.quality, out8.lossy) == (w, h, ce.Layout.RGBA, 8, 2, 55, True)
+	assert (out8.data == oracle.depth16to8(data)).all()
+	rgb = ce.ChangeChannelLayout(out8, ce.Layout.RGB)
+	assert rgb.layout == ce.Layout.RGB and (rgb.data == oracle.change_layout(out8.data, 4, 3)).all()
+	assert (ce.ToRGB8(img).data == rgb.data).all()
+	gray = ce.ChangeChannelLayout(img, ce.Layout.Grayscale)
+	assert (gray.data.view(np.uint16) == oracle.change_layout(data, 4, 1)).all()
+	fl = ce.Flip(rgb)
+	assert (fl.data.reshape(h, -1) == rgb.data.reshape(h, -1)[::-1]).all() and (rgb.data == oracle.change_layout(out8.data, 4, 3)).all()
+	ex = ce.Convert(ce.ImageEx(w, h, ce.Layout.RGBA, ce.FMT_U16, data.view(np.uint8)), ce.Layout.RGB, ce.FMT_F16)
+	assert same_bits(ex.data.view(np.float16), oracle.convert(data, 4, 3, oracle.U16, oracle.F16))
+
+
+@pytest.mark.parametrize("w,h,bpp", [(1, 1, 4), (5, 2, 3), (64, 33, 4), (67, 29, 6), (128, 128, 16), (3, 1000, 1)])
+def test_flip_rows(oracle, w, h, bpp):
+	from cacaoengine_b200 import _capi as c, device
+	from gpu_util import DevBuf
+
+	rng = np.random.default_rng(w * h)
+	src = rng.integers(0, 256, w * h * bpp).astype(np.uint8)
+	want = oracle.flip_rows(src, w, h, bpp)
+	out = np.empty_like(src)
+	c.check(c.lib().cacao_img_flip_rows(-1, src.ctypes.data, out.ctypes.data, w, h, bpp, c.MEM_HOST, None))
+	assert (out == want).all()
+	a, b = DevBuf(src.nbytes), DevBuf(src.nbytes)
+	device.upload(a.ptr, src)
+	device.flip_rows(a.ptr, b.ptr, w, h, bpp)
+	out2 = np.empty_like(src)
+	device.download(out2, b.ptr)
+	a.free(), b.free()
+	assert (out2 == want).all()
+	# involution: flipping twice is the identity
+	assert (oracle.flip_rows(out2, w, h, bpp) == src).all()
+
+
+def test_device_synth_and_checksum_match_host(oracle):
+	from cacaoengine_b200 import _capi as c, device
+	from gpu_util import DevBuf
+
+	for fmt, ch in ((c.FMT_U8, 3), (c.FMT_U16, 4), (c.FMT_F16, 4), (c.FMT_F32, 4), (c.FMT_F32, 3)):
+		n = 100003 if fmt != c.FMT_U8 else 100004
+		want = oracle.synth(n, fmt, ch, 0xC0FFEE, first_sample=12345)
+		buf = DevBuf(want.nbytes)
+		device.synth(buf.ptr, n, fmt, ch, 0xC0FFEE, first_sample=12345)
+		got = np.empty_like(want)
+		device.download(got, buf.ptr)
+		assert same_bits(got, want), fmt
+		nb = want.nbytes // 4 * 4
+		words = want.view(np.uint8)[:nb].view(np.uint32).astype(np.uint64)
+		idx = np.arange(words.size, dtype=np.uint64)
+		h = (words + idx * np.uint64(0x9E3779B9)) & np.uint64(0xFFFFFFFF)
+		h ^= h >> np.uint64(16); h = (h * np.uint64(0x85EBCA6B)) & np.uint64(0xFFFFFFFF)
+		h ^= h >> np.uint64(13); h = (h * np.uint64(0xC2B2AE35)) & np.uint64(0xFFFFFFFF)
+		h ^= h >> np.uint64(16)
+		assert device.checksum(buf.ptr, nb) == int(h.sum(dtype=np.uint64))
+		buf.free()
+
+
+def test_full_size_cfg2_batch_by_sampling(oracle):
+	"""BASELINE config 2 at full size (256 x 1920x1080 RGBA8 -> RGBA16F), inputs generated on the
+	device; sampled frames are read back and compared bit for bit, and a linearity-style property
+	holds for the whole batch: converting the batch == converting each half (checksum of checksums)."""
+	from cacaoengine_b200 import _capi as c, device
+	from gpu_util import DevBuf
+
+	ppi, count = 1920 * 1080, 256
+	src, dst = DevBuf(ppi * count * 4), DevBuf(ppi * count * 8)
+	device.synth(src.ptr, ppi * count * 4, c.FMT_U8, 4, 0xC0FFEE + 2)
+	device.convert_batch(src.ptr, dst.ptr, ppi, count, 4, 4, c.FMT_U8, c.FMT_F16)
+	whole = device.checksum(dst.ptr, ppi * count * 8)
+	for k in (0, 101, 255):
+		got = np.empty(ppi * 4, np.float16)
+		device.download(got, dst.ptr + k * ppi * 8)
+		want = oracle.convert(oracle.synth(ppi * 4, c.FMT_U8, 4, 0xC0FFEE + 2, first_sample=k * ppi * 4), 4, 4, c.FMT_U8, c.FMT_F16)
+		assert same_bits(got, want), k
+	# same batch converted as two independent halves into a fresh buffer
+	dst2 = DevBuf(ppi * count * 8)
+	half = count // 2
+	device.convert_batch(src.ptr, dst2.ptr, ppi, half, 4, 4, c.FMT_U8, c.FMT_F16)
+	device.convert_batch(src.ptr + half * ppi * 4, dst2.ptr + half * ppi * 8, ppi, count - half, 4, 4, c.FMT_U8, c.FMT_F16)
+	assert device.checksum(dst2.ptr, ppi * count * 8) == whole
+	for b in (src, dst, dst2):
+		b.free()
+
+
+def test_round_trip_properties():
+	"""Size-independent properties at a large size: RGB->RGBA->RGB is the identity, U8->U16->(>>8) too,
+	and U8->F32->U8 returns every byte."""
+	from cacaoengine_b200 import _capi as c, device
+	from gpu_util import DevBuf
+
+	px = 4096 * 4096
+	a, b, d = DevBuf(px * 3), DevBuf(px * 16), DevBuf(px * 3)
+	device.synth(a.ptr, px * 3, c.FMT_U8, 3, 77)
+	ref = device.checksum(a.ptr, px * 3)
+	device.convert(a.ptr, b.ptr, px, 3, 4, c.FMT_U8, c.FMT_U8)
+	device.convert(b.ptr, d.ptr, px, 4, 3, c.FMT_U8, c.FMT_U8)
+	assert device.checksum(d.ptr, px * 3) == ref
+	device.convert(a.ptr, b.ptr, px, 3, 4, c.FMT_U8, c.FMT_F32)
+	device.convert(b.ptr, d.ptr, px, 4, 3, c.FMT_F32, c.FMT_U8)
+	assert device.checksum(d.ptr, px * 3) == ref
+	device.convert(a.ptr, b.ptr, px, 3, 3, c.FMT_U8, c.FMT_F16)
+	device.convert(b.ptr, d.ptr, px, 3, 3, c.FMT_F16, c.FMT_U8)
+	assert device.checksum(d.ptr, px * 3) == ref
+	for x in (a, b, d):
+		x.free()

@@ -1,0 +1,160 @@
+"""GPU parity for the equirect -> cubemap resampler against the CPU restatement of DESIGN.md Spec
+B.2.  The reference has no such code (tools/cubetool/main.cpp:31-33), so this is parity with OUR
+oracle -- "parity unpinned vs reference".  The tolerance north_star allows is 1 LSB (u8/u16) or
+1e-5 relative (f16/f32); the design goal is stricter -- bit-exact -- and that is what is asserted,
+with the tolerance check kept as the documented floor."""
+import numpy as np
+import pytest
+
+from gpu_util import FMTS, NAME, NP, DevBuf, same_bits
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib(built_lib):
+	from cacaoengine_b200 import device
+
+	device.init()
+	yield
+
+
+def gpu_equirect_host(src, W, H, ch, fmt, N, mask=0x3F, r0=0, r1=None):
+	from cacaoengine_b200 import _capi as c
+
+	out = np.zeros(6 * N * N * ch, NP[fmt])
+	c.check(c.lib().cacao_img_equirect_to_cube(-1, src.ctypes.data, W, H, 0, H, ch, fmt, out.ctypes.data, N, mask, r0, N if r1 is None else r1, c.MEM_HOST, None))
+	return out
+
+
+def gpu_equirect_device(src, W, H, ch, fmt, N, mask=0x3F, r0=0, r1=None, window=None):
+	from cacaoengine_b200 import device
+
+	out = np.zeros(6 * N * N * ch, NP[fmt])
+	row_bytes = W * ch * src.itemsize
+	w0, wn = window if window else (0, H)
+	a, b = DevBuf(wn * row_bytes), DevBuf(out.nbytes)
+	device.upload(a.ptr, src.reshape(H, -1)[w0:w0 + wn].copy())
+	device.upload(b.ptr, out)
+	device.equirect_to_cube(a.ptr, W, H, ch, fmt, b.ptr, N, mask, r0, r1, src_row0=w0, src_rows=wn)
+	device.download(out, b.ptr)
+	a.free(), b.free()
+	return out
+
+
+def within_tolerance(got, want, fmt):
+	from cacaoengine_b200 import _capi as c
+
+	if fmt in (c.FMT_U8, c.FMT_U16):
+		return np.abs(got.astype(np.int64) - want.astype(np.int64)).max() <= 1
+	g, w = got.astype(np.float64), want.astype(np.float64)
+	return (np.abs(g - w) <= 1e-5 * np.abs(w) + 1e-30).all()
+
+
+@pytest.mark.parametrize("fmt", FMTS, ids=[NAME[f] for f in FMTS])
+@pytest.mark.parametrize("ch", (1, 3, 4))
+def test_every_format_and_layout_matches_oracle(oracle, fmt, ch):
+	W, H, N = 200, 100, 37  # odd face size: centre pixel has sc == 0 exactly
+	src = oracle.synth(W * H * ch, fmt, ch, 0xC0FFEE + 1)
+	want = oracle.equirect_to_cube(src, W, H, ch, fmt, N)
+	for got in (gpu_equirect_device(src, W, H, ch, fmt, N), gpu_equirect_host(src, W, H, ch, fmt, N)):
+		assert within_tolerance(got, want, fmt)
+		assert same_bits(got, want)
+
+
+def test_cfg1_shape_rgba8(oracle):
+	"""BASELINE config 1: 2048x1024 RGBA8 -> 6x512^2."""
+	from cacaoengine_b200 import _capi as c
+
+	W, H, N = 2048, 1024, 512
+	src = oracle.synth(W * H * 4, c.FMT_U8, 4, 0xC0FFEE)
+	want = oracle.equirect_to_cube(src, W, H, 4, c.FMT_U8, N)
+	got = gpu_equirect_device(src, W, H, 4, c.FMT_U8, N)
+	assert same_bits(got, want)
+
+
+def test_smooth_panorama_f32_against_double_truth(oracle):
+	"""End-to-end accuracy of the GPU result against the float64 libm resampler (not just against the
+	fp32 restatement): within 1e-5 relative on a smooth HDR-like panorama."""
+	from cacaoengine_b200 import _capi as c
+
+	W, H, N = 1024, 512, 256
+	y, x = np.mgrid[0:H, 0:W]
+	phi, th = (x + 0.5) / W * 2 * np.pi, (y + 0.5) / H * np.pi
+	img = np.stack([2.0 + np.sin(phi) * np.sin(th), 2.0 + np.cos(2 * phi) * np.sin(th) ** 2, 2.0 + np.cos(th), np.ones_like(phi)], -1).astype(np.float32).reshape(-1)
+	got = gpu_equirect_device(img, W, H, 4, c.FMT_F32, N).astype(np.float64)
+	truth = oracle.equirect_to_cube_f64(img, W, H, 4, c.FMT_F32, N)
+	assert (np.abs(got - truth) / np.abs(truth)).max() < 1e-5
+
+
+def test_face_masks_row_bands_and_source_windows(oracle):
+	"""Work units (face, row band) fed only their planned source-row window reproduce the full result:
+	the sharding scheme of DESIGN.md "Multi-GPU"."""
+	from cacaoengine_b200 import _capi as c, device
+
+	W, H, N, ch, fmt = 512, 256, 96, 4, c.FMT_F32
+	src = oracle.synth(W * H * ch, fmt, ch, 5)
+	full = oracle.equirect_to_cube(src, W, H, ch, fmt, N)
+	acc = np.zeros_like(full)
+	for f in range(6):
+		for (r0, r1) in ((0, 24), (24, 48), (48, 96)):
+			win = device.equirect_src_window(W, H, N, 1 << f, r0, r1)
+			part = gpu_equirect_device(src, W, H, ch, fmt, N, 1 << f, r0, r1, window=win)
+			sl = slice((f * N + r0) * N * ch, (f * N + r1) * N * ch)
+			assert same_bits(part[sl], full[sl]), (f, r0, r1, win)
+			assert (np.delete(part, np.arange(sl.start, sl.stop)) == 0).all()  # nothing else written
+			acc[sl] = part[sl]
+			if f in (0, 1, 4, 5):
+				assert win[1] < H  # side-face bands never need the whole panorama
+	assert same_bits(acc, full)
+
+
+def test_seam_and_poles(oracle):
+	"""One-hot panoramas: a texel on the u=0/1 seam and texels in the pole rows land identically."""
+	from cacaoengine_b200 import _capi as c
+
+	W, H, N = 64, 32, 33
+	for (yy, xx) in ((16, 0), (16, 63), (0, 10), (31, 40)):
+		img = np.zeros((H, W, 1), np.float32)
+		img[yy, xx, 0] = 1000.0
+		src = img.reshape(-1)
+		assert same_bits(gpu_equirect_device(src, W, H, 1, c.FMT_F32, N), oracle.equirect_to_cube(src, W, H, 1, c.FMT_F32, N))
+
+
+def test_python_mirror_equirect(oracle):
+	import cacaoengine_b200 as ce
+
+	W, H, N = 128, 64, 20
+	src = oracle.synth(W * H * 3, ce.FMT_U16, 3, 8)
+	out = ce.EquirectToCubemap(ce.ImageEx(W, H, ce.Layout.RGB, ce.FMT_U16, src.view(np.uint8)), N)
+	assert same_bits(out, oracle.equirect_to_cube(src, W, H, 3, ce.FMT_U16, N))
+
+
+def test_cfg3_shape_band_sample(oracle):
+	"""BASELINE config 3 at full size (8192x4096 RGBA32F -> 6x2048^2) on the device; three row bands
+	per face are compared with the oracle bit for bit, and the whole cube is checked through a
+	size-independent property: producing it as 6x4 separate (face, band) launches gives the same
+	checksum as one launch."""
+	from cacaoengine_b200 import _capi as c, device
+
+	W, H, N, ch, fmt = 8192, 4096, 2048, 4, c.FMT_F32
+	src = DevBuf(W * H * 16)
+	device.synth(src.ptr, W * H * 4, fmt, 4, 0xC0FFEE + 3)
+	cube = DevBuf(6 * N * N * 16)
+	device.equirect_to_cube(src.ptr, W, H, ch, fmt, cube.ptr, N)
+	whole = device.checksum(cube.ptr, 6 * N * N * 16)
+	host_src = oracle.synth(W * H * 4, fmt, 4, 0xC0FFEE + 3)
+	for (r0, r1) in ((0, 8), (1020, 1028), (2040, 2048)):
+		want = oracle.equirect_to_cube(host_src, W, H, ch, fmt, N, row_begin=r0, row_end=r1)
+		for f in range(6):
+			got = np.empty((r1 - r0) * N * 4, np.float32)
+			off = (f * N + r0) * N
+			device.download(got, cube.ptr + off * 16)
+			assert same_bits(got, want[off * 4: off * 4 + got.size]), (f, r0)
+	cube2 = DevBuf(6 * N * N * 16)
+	for f in range(6):
+		for b in range(4):
+			device.equirect_to_cube(src.ptr, W, H, ch, fmt, cube2.ptr, N, 1 << f, b * 512, (b + 1) * 512)
+	assert device.checksum(cube2.ptr, 6 * N * N * 16) == whole
+	for x in (src, cube, cube2):
+		x.free()
