@@ -52,12 +52,26 @@ namespace {
 
 	struct HostLut {
 		uint8_t table[65536];
+		uint16_t two_level[4096]; // see lut_16to8<true> in convert_pixel.cuh
+		bool two_level_ok = true;
 		HostLut() {
 			// level k starts at kLutThresholds[k-1]; the table is monotone with unit steps
 			int level = 0;
 			for(uint32_t i = 0; i < 65536u; ++i) {
 				while(level < 254 && i >= kLutThresholds[level]) ++level;
 				table[i] = static_cast<uint8_t>(level);
+			}
+			for(uint32_t k = 0; k < 4096u; ++k) {
+				const uint32_t base = table[16 * k];
+				uint32_t step = 16;
+				for(uint32_t o = 1; o < 16; ++o)
+					if(table[16 * k + o] != base) {
+						step = o;
+						break;
+					}
+				two_level[k] = static_cast<uint16_t>(base | (step << 8));
+				for(uint32_t o = 0; o < 16; ++o) // the compact form must reproduce every entry
+					if(base + (o >= step ? 1u : 0u) != table[16 * k + o]) two_level_ok = false;
 			}
 		}
 	};
@@ -75,6 +89,7 @@ namespace {
 		int sm_count = 0;
 		size_t smem_optin = 0;
 		uint8_t* lut_dev = nullptr;
+		uint16_t* lut2_dev = nullptr;
 		cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
 		cudaEvent_t ev_in[kSlots] = {}, ev_run[kSlots] = {}, ev_out[kSlots] = {};
 		uint8_t* stage_in[kSlots] = {};
@@ -141,6 +156,9 @@ namespace {
 			c->smem_optin = prop.sharedMemPerBlockOptin;
 			CU_TRY(cudaMalloc(&c->lut_dev, 65536));
 			CU_TRY(cudaMemcpy(c->lut_dev, host_lut().table, 65536, cudaMemcpyHostToDevice));
+			if(!host_lut().two_level_ok) return fail(CACAO_E_BAD_ARG, "internal: two-level 16->8 table does not reproduce the reference table");
+			CU_TRY(cudaMalloc(&c->lut2_dev, sizeof(host_lut().two_level)));
+			CU_TRY(cudaMemcpy(c->lut2_dev, host_lut().two_level, sizeof(host_lut().two_level), cudaMemcpyHostToDevice));
 			CU_TRY(cudaMalloc(&c->checksum_dev, sizeof(unsigned long long)));
 			CU_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
 			CU_TRY(cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking));
@@ -172,6 +190,7 @@ namespace {
 		if(c->s_run) cudaStreamDestroy(c->s_run);
 		if(c->s_out) cudaStreamDestroy(c->s_out);
 		if(c->lut_dev) cudaFree(c->lut_dev);
+		if(c->lut2_dev) cudaFree(c->lut2_dev);
 		if(c->checksum_dev) cudaFree(c->checksum_dev);
 		cudaSetDevice(prev);
 		delete c;
@@ -235,6 +254,7 @@ namespace {
 		job.dst_fmt = dst_fmt;
 		job.mode = mode;
 		job.lut_dev = c->lut_dev;
+		job.lut2_dev = c->lut2_dev;
 		job.dev.sm_count = c->sm_count;
 		job.dev.max_smem_optin = c->smem_optin;
 		job.stream = stream;

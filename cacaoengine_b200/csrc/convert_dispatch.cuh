@@ -15,7 +15,8 @@ namespace cacao {
 		uint64_t pixels_per_image; // domain of the Gray->RGBA pixel-0 quirk
 		int src_ch, dst_ch, src_fmt, dst_fmt;
 		int mode;
-		const uint8_t* lut_dev; // 65536-byte table in device global memory
+		const uint8_t* lut_dev;   // 65536-byte table in device global memory
+		const uint16_t* lut2_dev; // its 4096-entry two-level form (convert_pixel.cuh)
 		TileLaunch dev;
 		cudaStream_t stream;
 		unsigned launches; // out: kernels launched
@@ -29,6 +30,7 @@ namespace cacao {
 		constexpr int sb = FmtTraits<SF>::bytes, db = FmtTraits<DF>::bytes;
 		PixelCtx ctx;
 		ctx.lut = lut_global;
+		ctx.lut2 = nullptr;
 		ctx.gray16_cap = gray16_cap;
 		const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
 		for(uint64_t p = p_begin + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < p_end; p += stride) {
@@ -60,7 +62,7 @@ namespace cacao {
 		const uint32_t gray16_cap = (job.mode == CACAO_MODE_REF_EXACT) ? 255u : 65535u;
 		uint64_t n_tiles = (quirk || !aligned) ? 0 : job.pixels / S::tile_pixels;
 		if(n_tiles > 0) {
-			cudaError_t e = launch_convert_tiles<SF, DF, SC, DC>(job.src, job.dst, n_tiles, job.lut_dev, gray16_cap, job.dev, job.stream);
+			cudaError_t e = launch_convert_tiles<SF, DF, SC, DC>(job.src, job.dst, n_tiles, job.lut2_dev, gray16_cap, job.dev, job.stream);
 			if(e != cudaSuccess) return e;
 			job.launches += 1;
 		}

@@ -65,13 +65,30 @@ namespace cacao {
 	}
 
 	struct PixelCtx {
-		const uint8_t* lut; // 65536-entry table (shared or global memory); only read for U16 -> U8
-		uint32_t gray16_cap; // 255 in REF_EXACT mode (Layout.cpp:75), 65535 in FIXED mode
+		const uint8_t* lut;   // 65536-entry table in global memory (edge kernel); only read for U16 -> U8
+		const uint16_t* lut2; // 4096-entry two-level form of the same table in shared memory (tile kernel)
+		uint32_t gray16_cap;  // 255 in REF_EXACT mode (Layout.cpp:75), 65535 in FIXED mode
 	};
+
+	// The reference's 16->8 table (Colordepth.cpp:35) is monotone, moves in unit steps, and its steps
+	// are never closer than 19 inputs apart -- so a run of 16 consecutive inputs holds at most one
+	// step.  Entry k of the two-level form describes inputs [16k, 16k+16): low byte = level at 16k,
+	// high byte = offset of the step inside the run (16 = no step).  8 KiB instead of 64 KiB: it loads
+	// 8x faster, leaves shared memory for 8 blocks per SM, and costs the same single LDS per sample.
+	// cabi.cu builds it from the 65536-entry table and verifies it reproduces every entry.
+	template<bool TwoLevel>
+	__device__ __forceinline__ uint32_t lut_16to8(const PixelCtx& ctx, uint32_t v) {
+		if constexpr(TwoLevel) {
+			const uint32_t e = ctx.lut2[v >> 4];
+			return (e & 0xFFu) + (((v & 15u) >= (e >> 8)) ? 1u : 0u);
+		} else {
+			return ctx.lut[v];
+		}
+	}
 
 	// in[]: SC source samples; integer formats as their integer value, F16 as raw bits, F32 as
 	// float bits.  out[]: DC destination samples in the same register convention.
-	template<int SF, int DF, int SC, int DC>
+	template<int SF, int DF, int SC, int DC, bool TwoLevelLut = false>
 	__device__ __forceinline__ void convert_pixel(const uint32_t (&in)[SC], uint32_t (&out)[DC], const PixelCtx& ctx) {
 		constexpr bool src_int = FmtTraits<SF>::is_int;
 		if constexpr(src_int) {
@@ -100,7 +117,7 @@ namespace cacao {
 				if constexpr(DF == SF) {
 					out[c] = mid[c];
 				} else if constexpr(DF == CACAO_FMT_U8) {
-					out[c] = ctx.lut[mid[c]];
+					out[c] = lut_16to8<TwoLevelLut>(ctx, mid[c]);
 				} else if constexpr(DF == CACAO_FMT_U16) {
 					out[c] = mid[c] * 257u;
 				} else if constexpr(DF == CACAO_FMT_F32) {

