@@ -30,11 +30,12 @@ namespace cacao {
 	constexpr float kInvPi = 0.31830988618379067154f;
 	constexpr float kTanPi8 = 0.41421356237309504880f;
 
-	// atan2 with one division: reduce to t in [-(sqrt2-1), sqrt2-1] via
-	// atan(a/b) = pi/4 + atan((a-b)/(a+b)), then a 4-term odd polynomial (the classic single-precision
-	// coefficient set); |error| <= ~1.1 ulp of pi against libm over the cube's directions.
-	CACAO_HD float atan2_spec(float y, float x) {
-		const float ax = fabsf(x), ay = fabsf(y);
+	// atan2 with one division, in two steps so that callers can share the expensive one.
+	//
+	// atan2_core(|x|, |y|): the angle of (|x|, |y|) in [0, pi/2].  Reduce to t in [-(sqrt2-1), sqrt2-1]
+	// via atan(a/b) = pi/4 + atan((a-b)/(a+b)), then a 4-term odd polynomial (the classic
+	// single-precision coefficient set); |error| <= ~1.1 ulp of pi against libm over the cube's directions.
+	CACAO_HD float atan2_core(float ax, float ay) {
 		const float a = ax < ay ? ax : ay;
 		const float b = ax < ay ? ay : ax;
 		if(b == 0.0f) return 0.0f;
@@ -50,12 +51,21 @@ namespace cacao {
 		float r = fmaf(p * z, t, t);
 		r = r + off;
 		if(ay > ax) r = kPi2 - r;
+		return r;
+	}
+	// atan2_quadrant: place the first-quadrant angle by the signs of x and y.  Mirrored cube pixels
+	// differ only here, which is what lets the kernel compute atan2_core once per mirrored pair.
+	CACAO_HD float atan2_quadrant(float r, float y, float x) {
 		if(x < 0.0f) r = kPi - r;
 		if(y < 0.0f) r = -r;
 		return r;
 	}
+	CACAO_HD float atan2_spec(float y, float x) {
+		return atan2_quadrant(atan2_core(fabsf(x), fabsf(y)), y, x);
+	}
 
 	struct ProjConst {
+		int32_t n;    // N
 		float invN;   // 1.0f / N
 		float kx, ky; // W/(2 pi), H/pi
 		float cx, cy; // W/2 - 1/2, H/2 - 1/2
@@ -63,12 +73,19 @@ namespace cacao {
 
 	CACAO_HD ProjConst make_proj_const(uint32_t N, uint32_t W, uint32_t H) {
 		ProjConst c;
+		c.n = static_cast<int32_t>(N);
 		c.invN = 1.0f / static_cast<float>(N);
 		c.kx = static_cast<float>(W) * kInv2Pi;
 		c.ky = static_cast<float>(H) * kInvPi;
 		c.cx = 0.5f * static_cast<float>(W) - 0.5f;
 		c.cy = 0.5f * static_cast<float>(H) - 0.5f;
 		return c;
+	}
+
+	// Face-plane coordinate of pixel index k in [-1, 1]: (2k + 1 - N) / N, computed as an exact
+	// integer times 1/N so that face_coord(N-1-k) == -face_coord(k) bit for bit (mirror symmetry).
+	CACAO_HD float face_coord(uint32_t k, const ProjConst& c) {
+		return static_cast<float>(static_cast<int32_t>(2u * k + 1u) - c.n) * c.invN;
 	}
 
 	// Khronos cube-map face table
@@ -86,8 +103,8 @@ namespace cacao {
 	// face pixel (column i, row j) -> continuous source position (texel centres at integer + 0.5
 	// already removed: xs, ys index texel centres directly)
 	CACAO_HD void project_pixel(uint32_t face, uint32_t i, uint32_t j, const ProjConst& c, float& xs, float& ys) {
-		const float sc = fmaf(static_cast<float>(2u * i + 1u), c.invN, -1.0f);
-		const float tc = fmaf(static_cast<float>(2u * j + 1u), c.invN, -1.0f);
+		const float sc = face_coord(i, c);
+		const float tc = face_coord(j, c);
 		float x, y, z;
 		face_direction(face, sc, tc, x, y, z);
 		const float phi = atan2_spec(x, z);

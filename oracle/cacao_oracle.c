@@ -434,8 +434,9 @@ static void face_dir(uint32_t face, float sc, float tc, float* x, float* y, floa
 void orc_project(uint32_t face, uint32_t i, uint32_t j, uint32_t N, uint32_t W, uint32_t H, float* xs,
 				 float* ys) {
 	const float invN = 1.0f / (float)N;
-	const float sc = fmaf((float)(2u * i + 1u), invN, -1.0f);
-	const float tc = fmaf((float)(2u * j + 1u), invN, -1.0f);
+	/* (2k + 1 - N) / N as exact integer times 1/N: antisymmetric under k -> N-1-k */
+	const float sc = (float)((int32_t)(2u * i + 1u) - (int32_t)N) * invN;
+	const float tc = (float)((int32_t)(2u * j + 1u) - (int32_t)N) * invN;
 	float x, y, z;
 	face_dir(face, sc, tc, &x, &y, &z);
 	const float phi = orc_atan2(x, z);
