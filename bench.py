@@ -184,48 +184,91 @@ def time_device(torch, fn, steps, warmup):
 	return evs[0].elapsed_time(evs[steps]), per
 
 
-def extra_configs(torch, dev, stream, peak):
-	"""The other BASELINE configs that fit one GPU, device-resident, each with its own roofline."""
-	from cacaoengine_b200 import FMT_F16, FMT_F32, FMT_U8, device  # noqa: F401
+def timed_region(torch, dist, world, fn, steps, warmup):
+	"""`steps` calls of fn bracketed by barrier + synchronize; returns ms per step, max over ranks."""
+	for _ in range(warmup):
+		fn()
+	torch.cuda.synchronize()
+	if world > 1:
+		dist.barrier()
+	torch.cuda.synchronize()
+	a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	a.record()
+	for _ in range(steps):
+		fn()
+	b.record()
+	torch.cuda.synchronize()
+	ms = a.elapsed_time(b) / steps
+	if world > 1:
+		t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+		dist.all_reduce(t, op=dist.ReduceOp.MAX)
+		ms = float(t.item())
+	return ms
+
+
+def roof(alg_bytes, ms, peak, traffic=None):
+	return {"bound": "hbm", "achieved": alg_bytes / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg_bytes / ms / 1e6 / peak, "traffic": traffic}
+
+
+def extra_configs(torch, dist, world, rank, dev, stream, peak):
+	"""The other BASELINE configs, device-resident, sharded over the ranks exactly as DESIGN.md
+	"Multi-GPU" says (images by index, cube by face/row band); rooflines are per GPU (x world)."""
+	from cacaoengine_b200 import FMT_F32, FMT_U8, device, sharding
 
 	out = {}
 
 	def alloc(n):
-		return torch.empty(n, dtype=torch.uint8, device=f"cuda:{dev}")
+		return torch.empty(max(n, 16), dtype=torch.uint8, device=f"cuda:{dev}")
 
-	# cfg3: 8192x4096 RGBA32F equirect -> 6 x 2048^2, bilinear
-	W, H, N = 8192, 4096, 2048
-	src, dst = alloc(W * H * 16), alloc(6 * N * N * 16)
-	device.synth(src.data_ptr(), W * H * 4, FMT_F32, 4, 0xC0FFEE + 3, device=dev, stream=stream)
-	fn = lambda: device.equirect_to_cube(src.data_ptr(), W, H, 4, FMT_F32, dst.data_ptr(), N, device=dev, stream=stream)  # noqa: E731
-	_, per = time_device(torch, fn, 20, 3)
-	ms = statistics.mean(per)
-	alg = W * H * 16 + 6 * N * N * 16
-	out["cfg3_equirect_8192x4096_rgba32f_to_6x2048"] = {"value": 6 * N * N / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / ms / 1e6 / peak, "traffic": traffic_for("equirect_f32x4")}}
-	del src, dst
-	# cfg1 shape on the GPU for context (launch-latency bound)
-	W, H, N = 2048, 1024, 512
-	src, dst = alloc(W * H * 4), alloc(6 * N * N * 4)
-	device.synth(src.data_ptr(), W * H * 4, FMT_U8, 4, 0xC0FFEE, device=dev, stream=stream)
-	fn = lambda: device.equirect_to_cube(src.data_ptr(), W, H, 4, FMT_U8, dst.data_ptr(), N, device=dev, stream=stream)  # noqa: E731
-	_, per = time_device(torch, fn, 50, 5)
-	ms = statistics.mean(per)
-	alg = W * H * 4 + 6 * N * N * 4
-	out["cfg1_equirect_2048x1024_rgba8_to_6x512"] = {"value": 6 * N * N / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / ms / 1e6 / peak, "traffic": None}, "note": "14.7 MB problem: fits L2, launch-latency bound"}
-	del src, dst
-	# cfg4 slice: a resident ring of 4096^2 RGB8 images -> RGBA8 and -> RGBA32F (per-GPU share of the
-	# sharded batch; the full 4096-image batch does not fit in HBM, SURVEY.md 8d)
-	px = 4096 * 4096
-	ring = 16
+	def equirect(key, W, H, N, ch, fmt, bps, steps, note=None):
+		bpp = ch * bps
+		units = sharding.units_for_rank(rank, world, N) if world > 1 else [sharding.CubeUnit(-1, 0, N)]
+		if world > 1:
+			w0, wn = sharding.source_window(units, W, H, N)
+		else:
+			w0, wn = 0, H
+		src, dst = alloc(wn * W * bpp), alloc(6 * N * N * bpp)
+		# counter-hash synthetic panorama: a rank generates just its window of rows
+		device.synth(src.data_ptr(), wn * W * ch, fmt, ch, 0xC0FFEE + 3, first_sample=w0 * W * ch, device=dev, stream=stream)
+
+		def fn():
+			for u in units:
+				mask = 0x3F if u.face < 0 else (1 << u.face)
+				device.equirect_to_cube(src.data_ptr(), W, H, ch, fmt, dst.data_ptr(), N, mask, u.row_begin, u.row_end, src_row0=w0, src_rows=wn, device=dev, stream=stream)
+
+		ms = timed_region(torch, dist, world, fn, steps, 3)
+		alg = W * H * bpp + 6 * N * N * bpp
+		out[key] = {"value": 6 * N * N / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "units_per_rank": len(units), "source_rows_per_rank": wn, "roofline": roof(alg, ms, peak * world, traffic_for(key))}
+		if note:
+			out[key]["note"] = note
+		del src, dst
+
+	if world == 1:
+		equirect("cfg1_equirect_2048x1024_rgba8_to_6x512", 2048, 1024, 512, 4, FMT_U8, 1, 50, "14.7 MB problem: fits L2, launch-latency bound")
+		equirect("cfg3_equirect_8192x4096_rgba32f_to_6x2048", 8192, 4096, 2048, 4, FMT_F32, 4, 20)
+	equirect("cfg5_equirect_16384x8192_rgba32f_to_6x4096", 16384, 8192, 4096, 4, FMT_F32, 4, 10)
+
+	# cfg4: 4096 x 4096^2 RGB8 -> RGBA8 / RGBA32F sharded by image index.  206 GB of input and up to
+	# 1.1 TB of output fit nowhere (SURVEY.md 8d): each rank walks its logical image range over a
+	# resident ring of `ring` distinct synthetic inputs and `ring` output slots (1 GB / 4.3 GB >> L2),
+	# converting every logical image in full.
+	px, ring, total = 4096 * 4096, 16, 4096
+	lo, hi = sharding.image_range(rank, world, total)
 	src = alloc(ring * px * 3)
-	device.synth(src.data_ptr(), ring * px * 3, FMT_U8, 3, 0xC0FFEE + 4, device=dev, stream=stream)
-	for name, dfmt, dbytes in (("cfg4a_rgb8_to_rgba8", FMT_U8, 4), ("cfg4b_rgb8_to_rgba32f", FMT_F32, 16)):
+	device.synth(src.data_ptr(), ring * px * 3, FMT_U8, 3, 0xC0FFEE + 4 + rank, device=dev, stream=stream)
+	for key, dfmt, dbytes in (("cfg4a_4096x_4096sq_rgb8_to_rgba8", FMT_U8, 4), ("cfg4b_4096x_4096sq_rgb8_to_rgba32f", FMT_F32, 16)):
 		dst = alloc(ring * px * dbytes)
-		fn = lambda: device.convert_batch(src.data_ptr(), dst.data_ptr(), px, ring, 3, 4, FMT_U8, dfmt, device=dev, stream=stream)  # noqa: E731
-		_, per = time_device(torch, fn, 20, 3)
-		ms = statistics.mean(per)
-		alg = ring * px * (3 + dbytes)
-		out[name] = {"value": ring * px / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "images_per_step": ring, "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / ms / 1e6 / peak, "traffic": traffic_for(name)}}
+
+		def fn():
+			done = lo
+			while done < hi:
+				n = min(ring, hi - done)
+				device.convert_batch(src.data_ptr(), dst.data_ptr(), px, n, 3, 4, FMT_U8, dfmt, device=dev, stream=stream)
+				done += n
+
+		ms = timed_region(torch, dist, world, fn, 3, 3 if world > 1 else 1)
+		alg = total * px * (3 + dbytes)
+		out[key] = {"value": total * px / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "logical_images": total, "images_per_rank": hi - lo, "resident_ring": ring, "roofline": roof(alg, ms, peak * world, traffic_for(key))}
 		del dst
 	del src
 	torch.cuda.empty_cache()
@@ -316,11 +359,15 @@ def run_gpu_arm(args):
 				line["cpu_baseline"] = cpu_baseline_block()
 			except Exception as e:  # the CPU leg must never sink the GPU number
 				line["cpu_baseline"] = {"error": repr(e)}
-			if not args.no_extra:
-				try:
-					line["extra"] = extra_configs(torch, local, stream, peak)
-				except Exception as e:
-					line["extra"] = {"error": repr(e)}
+	extra = None
+	if not args.kernel_only and not args.no_extra:
+		try:  # every rank takes part: the extra configs are sharded too
+			extra = extra_configs(torch, dist, world, rank, local, stream, peak)
+		except Exception as e:
+			extra = {"error": repr(e)}
+	if rank == 0:
+		if extra is not None:
+			line["extra"] = extra
 		print(json.dumps(line), flush=True)
 	if world > 1:
 		dist.barrier()

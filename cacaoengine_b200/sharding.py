@@ -1,0 +1,95 @@
+"""Work partitioning across the GPUs of one box (one process per GPU).
+
+The hot path has no exchange step: pixels, images and cube rows are independent, so ranks take
+disjoint shards and never talk to each other on the data path.  The only
+cross-rank traffic is the barrier / max-reduction that brackets a timed region and the final
+gather of results to the host.
+
+  * conversion batches shard by image index           -> image_range()
+  * a cubemap shards by (face, row band) work units    -> cube_units() / units_for_rank()
+    and each rank needs only the source rows its units read -> source_window()
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+from . import device
+
+FACE_NAMES = ("right", "left", "up", "down", "front", "back")  # +X,-X,+Y,-Y,+Z,-Z (tools/cubetool/commands.hpp:31)
+
+
+def image_range(rank: int, world: int, count: int) -> tuple[int, int]:
+	"""Contiguous, balanced range of image indices [lo, hi) for `rank` (sizes differ by at most 1)."""
+	if not (0 <= rank < world):
+		raise ValueError(f"rank {rank} outside world of {world}")
+	base, extra = divmod(count, world)
+	lo = rank * base + min(rank, extra)
+	return lo, lo + base + (1 if rank < extra else 0)
+
+
+@dataclass(frozen=True)
+class CubeUnit:
+	face: int
+	row_begin: int
+	row_end: int
+
+	@property
+	def rows(self) -> int:
+		return self.row_end - self.row_begin
+
+
+def cube_units(face_size: int, bands_per_face: int) -> list[CubeUnit]:
+	"""6 x bands_per_face work units, band-major so that consecutive units are different faces
+	(round-robin dealing then gives every rank a mix of polar and side faces)."""
+	bands_per_face = max(1, min(bands_per_face, face_size))
+	units = []
+	for b in range(bands_per_face):
+		r0 = face_size * b // bands_per_face
+		r1 = face_size * (b + 1) // bands_per_face
+		for f in range(6):
+			if r1 > r0:
+				units.append(CubeUnit(f, r0, r1))
+	return units
+
+
+def bands_for_world(world: int) -> int:
+	"""Smallest band count whose 6*bands units deal out evenly over `world` ranks."""
+	for bands in range(1, 65):
+		if (6 * bands) % world == 0:
+			return bands
+	return world
+
+
+def units_for_rank(rank: int, world: int, face_size: int, bands_per_face: int | None = None) -> list[CubeUnit]:
+	if not (0 <= rank < world):
+		raise ValueError(f"rank {rank} outside world of {world}")
+	bands = bands_for_world(world) if bands_per_face is None else bands_per_face
+	return cube_units(face_size, bands)[rank::world]
+
+
+def source_window(units: list[CubeUnit], W: int, H: int, face_size: int) -> tuple[int, int]:
+	"""(first_row, rows): the band of equirect rows that covers every unit in the list
+	(host arithmetic identical to the kernel's, cacao_img_equirect_src_window)."""
+	lo, hi = None, None
+	for u in units:
+		r0, n = device.equirect_src_window(W, H, face_size, 1 << u.face, u.row_begin, u.row_end)
+		if n == 0:
+			continue
+		lo = r0 if lo is None else min(lo, r0)
+		hi = r0 + n if hi is None else max(hi, r0 + n)
+	return (0, 0) if lo is None else (lo, hi - lo)
+
+
+def max_over_ranks(value: float) -> float:
+	"""Multi-GPU timings are the max over ranks; single-process callers get the value back."""
+	try:
+		import torch
+		import torch.distributed as dist
+	except ImportError:
+		return value
+	if not (dist.is_available() and dist.is_initialized()):
+		return value
+	dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+	t = torch.tensor([value], dtype=torch.float64, device=dev)
+	dist.all_reduce(t, op=dist.ReduceOp.MAX)
+	return float(t.item())

@@ -1,0 +1,74 @@
+"""Multi-GPU parity (needs >= 2 devices; skipped on a one-GPU box): shards computed on different
+devices through the C ABI's `device` argument reassemble bit for bit to the single-device result.
+Partitioning comes from cacaoengine_b200.sharding, the same code bench.py's ranks use."""
+import numpy as np
+import pytest
+
+from gpu_util import same_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def _devices():
+	from cacaoengine_b200 import device
+
+	return device.device_count()
+
+
+def test_sharded_conversion_matches_single_device(built_lib, oracle):
+	from cacaoengine_b200 import _capi as c, device, sharding
+
+	n = _devices()
+	if n < 2:
+		pytest.skip("needs >= 2 CUDA devices")
+	count, ppi = 13, 40000
+	src = oracle.synth(count * ppi * 3, c.FMT_U8, 3, 21)
+	want = oracle.convert(src, 3, 4, c.FMT_U8, c.FMT_F32)
+	got = np.empty_like(want)
+	for d in range(n):
+		lo, hi = sharding.image_range(d, n, count)
+		if hi == lo:
+			continue
+		device.init(d)
+		a, b = device.malloc((hi - lo) * ppi * 3, d), device.malloc((hi - lo) * ppi * 16, d)
+		device.upload(a, src[lo * ppi * 3: hi * ppi * 3], device=d)
+		device.convert_batch(a, b, ppi, hi - lo, 3, 4, c.FMT_U8, c.FMT_F32, device=d)
+		device.download(got[lo * ppi * 4: hi * ppi * 4], b, device=d)
+		device.free(a, d), device.free(b, d)
+	assert same_bits(got, want)
+
+
+def test_sharded_cubemap_matches_single_device(built_lib, oracle):
+	from cacaoengine_b200 import _capi as c, device, sharding
+
+	n = _devices()
+	if n < 2:
+		pytest.skip("needs >= 2 CUDA devices")
+	W, H, N, ch, fmt = 1024, 512, 256, 4, c.FMT_F32
+	pano = oracle.synth(W * H * ch, fmt, ch, 22)
+	want = oracle.equirect_to_cube(pano, W, H, ch, fmt, N)
+	got = np.zeros_like(want)
+	row_bytes = W * ch * 4
+	for d in range(n):
+		device.init(d)
+		units = sharding.units_for_rank(d, n, N)
+		w0, wn = sharding.source_window(units, W, H, N)
+		a, b = device.malloc(wn * row_bytes, d), device.malloc(want.nbytes, d)
+		device.upload(a, pano.reshape(H, -1)[w0:w0 + wn].copy(), device=d)
+		for u in units:
+			device.equirect_to_cube(a, W, H, ch, fmt, b, N, 1 << u.face, u.row_begin, u.row_end, src_row0=w0, src_rows=wn, device=d)
+			sl = slice((u.face * N + u.row_begin) * N * ch, (u.face * N + u.row_end) * N * ch)
+			device.download(got[sl], b + sl.start * 4, device=d)
+		device.free(a, d), device.free(b, d)
+	assert same_bits(got, want)
+
+
+def test_host_api_on_second_device(built_lib, oracle):
+	from cacaoengine_b200 import _capi as c
+
+	if _devices() < 2:
+		pytest.skip("needs >= 2 CUDA devices")
+	src = oracle.synth(5000 * 4, c.FMT_U16, 4, 23)
+	out = np.empty(5000 * 3, np.uint8)
+	c.check(c.lib().cacao_img_convert(1, src.ctypes.data, out.ctypes.data, 5000, 4, 3, c.FMT_U16, c.FMT_U8, 0, c.MEM_HOST, None))
+	assert (out == oracle.convert(src, 4, 3, c.FMT_U16, c.FMT_U8)).all()

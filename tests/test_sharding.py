@@ -1,0 +1,122 @@
+"""CPU tests of the multi-GPU host logic: world_size-2 (and -3) process groups over gloo.
+
+The data path has no collective, so what needs covering is the partitioning: every image and
+every cube row is owned by exactly one rank, each rank's planned source window contains every
+row its units read, shards computed independently reassemble to the single-rank result, and the
+max-over-ranks timing reduction works.  The pixel work itself is done here by the CPU oracle
+(test infrastructure) -- the product has no CPU path; the same partition drives the GPU ranks
+in bench.py and test_multigpu_gpu.py."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+	s = socket.socket()
+	s.bind(("127.0.0.1", 0))
+	p = s.getsockname()[1]
+	s.close()
+	return p
+
+
+def _worker(rank, world, port, out_dir):
+	sys.path.insert(0, ROOT)
+	import torch
+	import torch.distributed as dist
+
+	from cacaoengine_b200 import sharding
+	from oracle import pyoracle as po
+
+	dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+	try:
+		# --- conversion batch sharded by image index (BASELINE config 4 in miniature)
+		count, ppi = 11, 333
+		lo, hi = sharding.image_range(rank, world, count)
+		src = po.synth(count * ppi * 3, po.U8, 3, 0xC0FFEE + 4)
+		mine = po.convert(src[lo * ppi * 3: hi * ppi * 3], 3, 4, po.U8, po.F32) if hi > lo else np.zeros(0, np.float32)
+		parts = [None] * world
+		dist.all_gather_object(parts, (lo, hi, mine))
+		# --- cubemap sharded by (face, row band) with per-rank source windows (config 5 in miniature)
+		W, H, N = 256, 128, 40
+		pano = po.synth(W * H * 4, po.F32, 4, 0xC0FFEE + 5)
+		units = sharding.units_for_rank(rank, world, N)
+		w0, wn = sharding.source_window(units, W, H, N)
+		window = pano.reshape(H, -1)[w0:w0 + wn]
+		cube = np.zeros(6 * N * N * 4, np.float32)
+		for u in units:
+			# the rank only holds `window`: every tap row of the unit must lie inside it
+			ys = np.array([po.project(u.face, i, j, N, W, H)[1] for j in range(u.row_begin, u.row_end) for i in (0, N // 2, N - 1)])
+			assert w0 <= max(0, int(np.floor(ys.min()))) and min(H - 1, int(np.floor(ys.max())) + 1) < w0 + wn
+			po.equirect_to_cube(pano, W, H, 4, po.F32, N, face_mask=1 << u.face, row_begin=u.row_begin, row_end=u.row_end, out=cube)
+		assert window.shape[0] == wn
+		cubes = [None] * world
+		dist.all_gather_object(cubes, ([(u.face, u.row_begin, u.row_end) for u in units], cube))
+		# --- timing reduction: max over ranks
+		t = sharding.max_over_ranks(1.0 + rank)
+		assert t == float(world)
+		if rank == 0:
+			# images: disjoint, ordered, complete
+			spans = sorted((a, b) for a, b, _ in parts)
+			assert spans[0][0] == 0 and spans[-1][1] == count and all(spans[k][1] == spans[k + 1][0] for k in range(world - 1))
+			assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+			whole = np.concatenate([m for _, _, m in sorted(parts, key=lambda p: p[0])])
+			assert (whole.view(np.uint32) == po.convert(src, 3, 4, po.U8, po.F32).view(np.uint32)).all()
+			# cube rows: every (face, row) exactly once; reassembled cube == single-rank cube
+			owner = np.zeros((6, N), np.int32)
+			total = np.zeros_like(cube)
+			for us, c in cubes:
+				for f, r0, r1 in us:
+					owner[f, r0:r1] += 1
+					sl = slice((f * N + r0) * N * 4, (f * N + r1) * N * 4)
+					total[sl] = c[sl]
+			assert (owner == 1).all()
+			assert (total.view(np.uint32) == po.equirect_to_cube(pano, W, H, 4, po.F32, N).view(np.uint32)).all()
+			open(os.path.join(out_dir, "ok"), "w").write("ok")
+		dist.barrier()
+	finally:
+		dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_partition_over_gloo(built_lib, oracle, tmp_path, world):
+	import torch.multiprocessing as mp
+
+	port = _free_port()
+	mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+	assert (tmp_path / "ok").exists()
+
+
+def test_image_range_properties():
+	from cacaoengine_b200 import sharding
+
+	for world in (1, 2, 3, 4, 8):
+		for count in (0, 1, 7, 8, 256, 4096):
+			spans = [sharding.image_range(r, world, count) for r in range(world)]
+			assert spans[0][0] == 0 and spans[-1][1] == count
+			assert all(spans[k][1] == spans[k + 1][0] for k in range(world - 1))
+			sizes = [b - a for a, b in spans]
+			assert max(sizes) - min(sizes) <= 1
+	with pytest.raises(ValueError):
+		sharding.image_range(2, 2, 10)
+
+
+def test_cube_units_deal_evenly():
+	from cacaoengine_b200 import sharding
+
+	for world in (1, 2, 4, 8):
+		N = 4096
+		per_rank = [sharding.units_for_rank(r, world, N) for r in range(world)]
+		rows = [sum(u.rows for u in us) for us in per_rank]
+		assert max(rows) == min(rows), (world, rows)  # BASELINE config 5: 8 ranks x 3 units of 1024 rows
+		seen = set()
+		for us in per_rank:
+			for u in us:
+				for r in range(u.row_begin, u.row_end, 512):
+					assert (u.face, r) not in seen
+					seen.add((u.face, r))
+	assert len(sharding.units_for_rank(0, 8, 4096)) == 3
