@@ -1,0 +1,118 @@
+// test_cpp_api.cpp -- the reference's C++ interface (include/libcacaoimage.hpp) exercised the way
+// engine/src/core/Cubemap.cpp:20-32 and Tex2D.cpp:18 use it, against the known-answer vectors
+// extracted from the compiled reference.  Built and run by tests/test_cpp_api.py.
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "libcacaoimage.hpp"
+#include "libcacaoimage_ext.hpp"
+
+using namespace libcacaoimage;
+
+static int failures = 0;
+#define EXPECT(cond)                                                    \
+	do {                                                                \
+		if(!(cond)) {                                                   \
+			std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); \
+			++failures;                                                 \
+		}                                                               \
+	} while(0)
+
+static Image make8(unsigned w, unsigned h, Image::Layout l, std::vector<unsigned char> d) {
+	Image im = {};
+	im.w = w;
+	im.h = h;
+	im.layout = l;
+	im.bitsPerChannel = 8;
+	im.data = std::move(d);
+	im.format = Image::Format::TIFF;
+	im.quality = 42;
+	im.lossy = true;
+	return im;
+}
+static Image make16(unsigned w, unsigned h, Image::Layout l, const std::vector<unsigned short>& d) {
+	Image im = make8(w, h, l, {});
+	im.bitsPerChannel = 16;
+	im.data.resize(d.size() * 2);
+	std::memcpy(im.data.data(), d.data(), im.data.size());
+	return im;
+}
+static std::vector<unsigned short> as16(const Image& im) {
+	std::vector<unsigned short> v(im.data.size() / 2);
+	std::memcpy(v.data(), im.data.data(), im.data.size());
+	return v;
+}
+template<class F>
+static std::string thrown(F f) {
+	try {
+		f();
+	} catch(const std::runtime_error& e) {
+		return e.what();
+	}
+	return "";
+}
+
+int main() {
+	static_assert(sizeof(Image) == 56, "Image layout must match the reference (libstdc++ x86-64)");
+	using L = Image::Layout;
+	// ---- ChangeChannelLayout, 8 bit
+	const Image g8 = make8(3, 1, L::Grayscale, {10, 20, 30});
+	EXPECT(ChangeChannelLayout(g8, L::RGB).data == (std::vector<unsigned char>{10, 10, 10, 20, 20, 20, 30, 30, 30}));
+	EXPECT(ChangeChannelLayout(g8, L::RGBA).data == (std::vector<unsigned char>{10, 10, 10, 255, 10, 10, 10, 255, 10, 10, 10, 255})); // pixel-0 quirk
+	const Image rgb8 = make8(3, 1, L::RGB, {255, 255, 255, 1, 2, 3, 200, 100, 50});
+	EXPECT(ChangeChannelLayout(rgb8, L::RGBA).data == (std::vector<unsigned char>{255, 255, 255, 255, 1, 2, 3, 255, 200, 100, 50, 255}));
+	EXPECT(ChangeChannelLayout(rgb8, L::Grayscale).data == (std::vector<unsigned char>{254, 1, 116}));
+	const Image rgba8 = make8(3, 1, L::RGBA, {255, 255, 255, 7, 1, 2, 3, 8, 200, 100, 50, 9});
+	const Image r = ChangeChannelLayout(rgba8, L::RGB);
+	EXPECT(r.data == (std::vector<unsigned char>{255, 255, 255, 1, 2, 3, 200, 100, 50}));
+	EXPECT(r.w == 3 && r.h == 1 && r.layout == L::RGB && r.bitsPerChannel == 8 && r.format == Image::Format::TIFF && r.quality == 42 && r.lossy);
+	EXPECT(rgba8.data.size() == 12 && rgba8.data[3] == 7); // source untouched
+	// ---- ChangeChannelLayout, 16 bit
+	const Image rgb16 = make16(3, 1, L::RGB, {65535, 65535, 65535, 100, 200, 300, 1000, 100, 50});
+	EXPECT(as16(ChangeChannelLayout(rgb16, L::RGBA)) == (std::vector<unsigned short>{65535, 65535, 65535, 65535, 100, 200, 300, 65535, 1000, 100, 50, 65535}));
+	EXPECT(as16(ChangeChannelLayout(rgb16, L::Grayscale)) == (std::vector<unsigned short>{255, 185, 255})); // clamp-255 quirk
+	const Image g16 = make16(3, 1, L::Grayscale, {1000, 20000, 65535});
+	EXPECT(as16(ChangeChannelLayout(g16, L::RGBA)) == (std::vector<unsigned short>{1000, 1000, 1000, 65535, 1000, 1000, 1000, 65535, 1000, 1000, 1000, 65535}));
+	// ---- Convert16To8BitColor
+	EXPECT(Convert16To8BitColor(rgb16).data == (std::vector<unsigned char>{254, 254, 254, 5, 10, 14, 33, 5, 2}));
+	const Image rgba16 = make16(2, 1, L::RGBA, {65535, 32768, 0, 65535, 100, 200, 300, 400});
+	const Image d8 = Convert16To8BitColor(rgba16);
+	EXPECT(d8.data == (std::vector<unsigned char>{254, 187, 0, 254, 5, 10, 14, 18}) && d8.bitsPerChannel == 8 && d8.layout == L::RGBA && d8.quality == 42);
+	// ---- the engine's per-face sequence (Cubemap.cpp:28-31) and its fused form
+	Image face = rgba16;
+	if(face.bitsPerChannel == 16) face = Convert16To8BitColor(face);
+	if(face.layout != L::RGB) face = ChangeChannelLayout(face, L::RGB);
+	EXPECT(face.data == (std::vector<unsigned char>{254, 187, 0, 5, 10, 14}));
+	EXPECT(ToRGB8(rgba16).data == face.data);
+	// ---- errors: the reference's texts (Layout.cpp:9, Colordepth.cpp:8, Flip.cpp:8-10)
+	EXPECT(thrown([&] { ChangeChannelLayout(rgb8, L::RGB); }) == "Cannot change an image's channel layout to its current layout!");
+	EXPECT(thrown([&] { Convert16To8BitColor(rgb8); }) == "Source image for 16 to 8-bit color conversion does not have a 16-bit color depth!");
+	EXPECT(thrown([&] { Flip(make8(0, 3, L::RGB, {})); }) == "Cannot flip an image with zeroed dimensions!");
+	Image bad = make8(1, 2, L::RGB, {1, 2, 3, 4, 5, 6});
+	bad.bitsPerChannel = 12;
+	EXPECT(thrown([&] { Flip(bad); }) == "Invalid color depth; only 8 and 16 are allowed.");
+	EXPECT(thrown([&] { Flip(make8(1, 2, L::RGB, {})); }) == "Cannot flip an image with a zero-sized data buffer!");
+	// ---- Flip: intended semantics, source untouched
+	const Image two = make8(2, 3, L::Grayscale, {1, 2, 3, 4, 5, 6});
+	EXPECT(Flip(two).data == (std::vector<unsigned char>{5, 6, 3, 4, 1, 2}) && two.data[0] == 1);
+	EXPECT(Flip(make8(3, 1, L::Grayscale, {7, 8, 9})).data == (std::vector<unsigned char>{7, 8, 9}));
+	// ---- extensions: float formats and the projection
+	ImageEx ex = FromImage(rgb8);
+	const ImageEx f32 = Convert(ex, L::RGBA, SampleFormat::F32);
+	const float* fp = reinterpret_cast<const float*>(f32.data.data());
+	EXPECT(f32.data.size() == 3 * 4 * 4 && fp[0] == 1.0f && fp[3] == 1.0f && fp[4] == 1.0f / 255.0f && fp[9] == 100.0f / 255.0f);
+	EXPECT(ToImage(Convert(f32, L::RGB, SampleFormat::U8)).data == rgb8.data); // round trip
+	ImageEx pano;
+	pano.w = 64;
+	pano.h = 32;
+	pano.layout = L::RGB;
+	pano.format = SampleFormat::U8;
+	pano.data.assign(64 * 32 * 3, 99);
+	const auto cube = EquirectToCubemap(pano, 8);
+	for(const auto& f : cube) EXPECT(f.w == 8 && f.h == 8 && f.data.size() == 8 * 8 * 3 && f.data[0] == 99 && f.data.back() == 99);
+	std::printf(failures ? "%d FAILURES\n" : "cpp api ok\n", failures);
+	return failures ? 1 : 0;
+}

@@ -1,0 +1,106 @@
+"""ce-cubetool: the reference tool's CLI contract (tools/cubetool/main.cpp:15-38, commands.hpp:9-11)
+plus the new `project` subcommand."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ERR = "\x1b[0m\x1b[1;91mERROR: \x1b[0m"
+
+
+@pytest.fixture(scope="module")
+def tool(built_lib):
+	from cacaoengine_b200 import build as b
+
+	assert os.path.exists(b.TOOL)
+	return b.TOOL
+
+
+def run(tool, *args):
+	return subprocess.run([tool, *args], capture_output=True, text=True)
+
+
+def test_version_and_help(tool):
+	r = run(tool, "--version")
+	assert r.returncode == 0 and r.stdout.startswith("CubeTool v") and "For Cacao Engine v" in r.stdout
+	assert run(tool, "-v").stdout == r.stdout
+	h = run(tool, "--help")
+	assert h.returncode == 0 and "SUBCOMMANDS:" in h.stdout and "create" in h.stdout and "extract" in h.stdout and "project" in h.stdout
+
+
+def test_subcommand_is_required(tool):
+	r = run(tool)
+	assert r.returncode != 0 and "subcommand is required" in r.stderr.lower()
+
+
+def test_reference_subcommands_answer_with_cube_error(tool):
+	for sub in ("create", "extract"):
+		r = run(tool, sub, "x", "-o", "y")
+		assert r.returncode == 1 and r.stderr.startswith(ERR) and r.stdout == ""
+
+
+def test_project_argument_validation(tool, tmp_path):
+	assert run(tool, "project").returncode != 0
+	assert "File does not exist" in run(tool, "project", str(tmp_path / "nope.png"), "-o", str(tmp_path)).stderr
+	np.save(tmp_path / "p.npy", np.zeros((4, 8, 3), np.uint8))
+	assert "-o is required" in run(tool, "project", str(tmp_path / "p.npy")).stderr
+	assert "Invalid face name" in run(tool, "project", str(tmp_path / "p.npy"), "-o", str(tmp_path), "-f", "sideways").stderr
+	bad = tmp_path / "bad.bin"
+	bad.write_bytes(b"not an image")
+	r = run(tool, "project", str(bad), "-o", str(tmp_path / "o"))
+	assert r.returncode == 1 and r.stderr.startswith(ERR) and "Unrecognised image format" in r.stderr
+
+
+def test_silent_by_default_verbose_on_request(tool, tmp_path):
+	np.save(tmp_path / "p.npy", np.zeros((4, 8, 3), np.uint8))
+	from cacaoengine_b200 import device
+
+	if device.device_count() == 0:
+		r = run(tool, "project", str(tmp_path / "p.npy"), "-o", str(tmp_path / "o"))
+		assert r.returncode == 1 and r.stderr.startswith(ERR) and r.stdout == ""  # loud failure, no CPU fallback
+		v = run(tool, "-V", "project", str(tmp_path / "p.npy"), "-o", str(tmp_path / "o"))
+		assert "Opening input file" in v.stdout
+
+
+@pytest.mark.gpu
+def test_project_png_end_to_end(tool, tmp_path, oracle):
+	import cv2
+
+	W, H, N = 256, 128, 48
+	pano = oracle.synth(W * H * 3, oracle.U8, 3, 31).reshape(H, W, 3)
+	cv2.imwrite(str(tmp_path / "sky.png"), pano[:, :, ::-1])  # cv2 wants BGR
+	r = run(tool, "project", str(tmp_path / "sky.png"), "-o", str(tmp_path / "out"), "--face-size", str(N))
+	assert r.returncode == 0 and r.stdout == "", r.stderr
+	want = oracle.equirect_to_cube(pano.reshape(-1), W, H, 3, oracle.U8, N).reshape(6, N, N, 3)
+	names = ["right", "left", "up", "down", "front", "back"]
+	for k, nm in enumerate(names):
+		face = cv2.imread(str(tmp_path / "out" / f"sky_{nm}.png"), cv2.IMREAD_UNCHANGED)[:, :, ::-1]
+		assert (face == want[k]).all(), nm
+	ajc = (tmp_path / "out" / "sky.ajc").read_text().splitlines()
+	assert ajc == [f"{key}: sky_{nm}.png" for key, nm in zip(["right", "left", "top", "bottom", "front", "back"], names)]
+
+
+@pytest.mark.gpu
+def test_project_float_npy_16bit_png_and_options(tool, tmp_path, oracle):
+	import cv2
+
+	W, H, N = 128, 64, 20
+	pano = oracle.synth(W * H * 4, oracle.F32, 4, 32).reshape(H, W, 4)
+	np.save(tmp_path / "hdr.npy", pano)
+	r = run(tool, "-V", "project", str(tmp_path / "hdr.npy"), "-o", str(tmp_path / "o1"), "-s", str(N), "--bench")
+	assert r.returncode == 0 and "Projecting onto 6 faces" in r.stdout and '"subcommand": "project"' in r.stdout
+	want = oracle.equirect_to_cube(pano.reshape(-1), W, H, 4, oracle.F32, N).reshape(6, N, N, 4)
+	got = np.load(tmp_path / "o1" / "hdr_front.npy")
+	assert got.dtype == np.float32 and (got.view(np.uint32) == want[4].view(np.uint32)).all()
+	# 16-bit PNG in, single face out, converted to 8-bit RGB and flipped
+	p16 = oracle.synth(W * H * 4, oracle.U16, 4, 33).reshape(H, W, 4)
+	cv2.imwrite(str(tmp_path / "deep.png"), p16[:, :, [2, 1, 0, 3]])
+	r = run(tool, "project", str(tmp_path / "deep.png"), "-o", str(tmp_path / "o2"), "-s", str(N), "-f", "up", "--layout", "rgb", "--depth", "8", "--flip")
+	assert r.returncode == 0, r.stderr
+	cube16 = oracle.equirect_to_cube(p16.reshape(-1), W, H, 4, oracle.U16, N).reshape(6, N * N * 4)
+	up8 = oracle.convert(cube16[2], 4, 3, oracle.U16, oracle.U8).reshape(N, N, 3)[::-1]
+	face = cv2.imread(str(tmp_path / "o2" / "deep_up.png"), cv2.IMREAD_UNCHANGED)[:, :, ::-1]
+	assert (face == up8).all()
+	assert sorted(os.listdir(tmp_path / "o2")) == ["deep_up.png"]  # no .ajc for a partial set
