@@ -268,7 +268,9 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 
 		ms = timed_region(torch, dist, world, fn, 3, 3 if world > 1 else 1)
 		alg = total * px * (3 + dbytes)
-		out[key] = {"value": total * px / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "logical_images": total, "images_per_rank": hi - lo, "resident_ring": ring, "roofline": roof(alg, ms, peak * world, traffic_for(key))}
+		per_launch = traffic_for(key.split("_")[0] + "_16x_4096sq_" + key.split("sq_")[1] + "_per_launch")  # ncu: one 16-image launch
+		launches = (total + ring - 1) // ring
+		out[key] = {"value": total * px / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "logical_images": total, "images_per_rank": hi - lo, "resident_ring": ring, "launches_per_step_all_ranks": launches, "roofline": roof(alg, ms, peak * world, per_launch * launches if per_launch else None)}
 		del dst
 	del src
 	torch.cuda.empty_cache()
