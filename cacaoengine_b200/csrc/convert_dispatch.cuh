@@ -5,6 +5,7 @@
 #pragma once
 
 #include "convert_tiles.cuh"
+#include "convert_wide.cuh"
 
 namespace cacao {
 
@@ -60,13 +61,34 @@ namespace cacao {
 		const bool quirk = FmtTraits<SF>::is_int && SC == 1 && DC == 4 && job.mode == CACAO_MODE_REF_EXACT;
 		const bool aligned = ((reinterpret_cast<uintptr_t>(job.src) | reinterpret_cast<uintptr_t>(job.dst)) & 15u) == 0;
 		const uint32_t gray16_cap = (job.mode == CACAO_MODE_REF_EXACT) ? 255u : 65535u;
-		uint64_t n_tiles = (quirk || !aligned) ? 0 : job.pixels / S::tile_pixels;
-		if(n_tiles > 0) {
-			cudaError_t e = launch_convert_tiles<SF, DF, SC, DC>(job.src, job.dst, n_tiles, job.lut2_dev, gray16_cap, job.dev, job.stream);
-			if(e != cudaSuccess) return e;
-			job.launches += 1;
+		// preferred: the 256-bit sector kernel (convert_wide.cuh) when the shape fits it and both
+		// buffers are 32-byte aligned; otherwise the 128-bit tile kernel (convert_tiles.cuh)
+		uint64_t done = 0;
+		bool wide = false;
+		if constexpr(WideShape<SF, DF, SC, DC>::ok) {
+			using WS = WideShape<SF, DF, SC, DC>;
+			const bool aligned32 = ((reinterpret_cast<uintptr_t>(job.src) | reinterpret_cast<uintptr_t>(job.dst)) & 31u) == 0;
+			const char* force = getenv("CACAO_FORCE_WIDE"); // dev/test switch: run every fitting shape on the sector kernel
+			wide = !quirk && aligned32 && !getenv("CACAO_NO_WIDE") && (WS::preferred || (force && force[0] == '1'));
+			if(wide) {
+				const uint64_t n_runs = job.pixels / WS::G;
+				if(n_runs > 0) {
+					cudaError_t e = launch_convert_wide<SF, DF, SC, DC>(job.src, job.dst, n_runs, job.lut_dev, job.lut2_dev, gray16_cap, job.stream);
+					if(e != cudaSuccess) return e;
+					job.launches += 1;
+				}
+				done = n_runs * WS::G;
+			}
 		}
-		const uint64_t done = n_tiles * S::tile_pixels;
+		if(!wide) {
+			const uint64_t n_tiles = (quirk || !aligned) ? 0 : job.pixels / S::tile_pixels;
+			if(n_tiles > 0) {
+				cudaError_t e = launch_convert_tiles<SF, DF, SC, DC>(job.src, job.dst, n_tiles, job.lut2_dev, gray16_cap, job.dev, job.stream);
+				if(e != cudaSuccess) return e;
+				job.launches += 1;
+			}
+			done = n_tiles * S::tile_pixels;
+		}
 		if(done < job.pixels) {
 			const uint64_t rest = job.pixels - done;
 			uint64_t blocks = (rest + 255) / 256;

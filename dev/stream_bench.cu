@@ -125,6 +125,40 @@ __global__ void __launch_bounds__(256) expand256_kernel(const uint4* __restrict_
 	}
 }
 
+// ---- E: lane-contiguous chunks: each lane owns KIN*32 contiguous bytes in and KOUT*32 out (no smem, no
+// warp-level coalescing beyond full 32-B sectors).  Does DRAM care?  KIN=KOUT: copy; 3->4: RGB8->RGBA8 math.
+template<int KIN, int KOUT>
+__global__ void __launch_bounds__(256) lane_chunk_kernel(const uint4* __restrict__ s, uint4* __restrict__ d, uint64_t n_lanes) {
+	const uint64_t lane = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(lane >= n_lanes) return;
+	uint4 v[KIN][2];
+	const uint4* sp = s + lane * (2 * KIN);
+#pragma unroll
+	for(int k = 0; k < KIN; ++k) ldg256(sp + 2 * k, v[k][0], v[k][1]);
+	uint4* dp = d + lane * (2 * KOUT);
+	if constexpr(KIN == KOUT) {
+#pragma unroll
+		for(int k = 0; k < KOUT; ++k) stg256(dp + 2 * k, v[k][0], v[k][1]);
+	} else {
+		// 96 B = 32 RGB8 px -> 128 B RGBA8: word j of the output = bytes 3j..3j+2 of the input | 0xFF000000
+		uint32_t w[KIN * 8 + 1];
+#pragma unroll
+		for(int k = 0; k < KIN; ++k) {
+			w[8 * k + 0] = v[k][0].x; w[8 * k + 1] = v[k][0].y; w[8 * k + 2] = v[k][0].z; w[8 * k + 3] = v[k][0].w;
+			w[8 * k + 4] = v[k][1].x; w[8 * k + 5] = v[k][1].y; w[8 * k + 6] = v[k][1].z; w[8 * k + 7] = v[k][1].w;
+		}
+		w[KIN * 8] = 0;
+		uint32_t o[KOUT * 8];
+#pragma unroll
+		for(int j = 0; j < KOUT * 8; ++j) {
+			const int byte = 3 * j, wi = byte >> 2, sh = (byte & 3) * 8;
+			o[j] = (__funnelshift_r(w[wi], w[wi + 1], sh) & 0x00FFFFFFu) | 0xFF000000u;
+		}
+#pragma unroll
+		for(int k = 0; k < KOUT; ++k) stg256(dp + 2 * k, make_uint4(o[8 * k], o[8 * k + 1], o[8 * k + 2], o[8 * k + 3]), make_uint4(o[8 * k + 4], o[8 * k + 5], o[8 * k + 6], o[8 * k + 7]));
+	}
+}
+
 struct Timer {
 	cudaEvent_t a, b;
 	Timer() {
@@ -217,6 +251,20 @@ int main() {
 		report(nm, b3, time_ms([&] { expand256_kernel<2><<<g2, 256>>>(src, dst, n); }));
 		snprintf(nm, sizeof nm, "convert LDG.256+2xSTG.256 U=1 grid=%u", g1);
 		report(nm, b3, time_ms([&] { expand256_kernel<1><<<g1, 256>>>(src, dst, n); }));
+	}
+	// E: lane-contiguous chunk access
+	{
+		auto run = [&](auto kern, int kin, int kout, const char* nm) {
+			const uint64_t lanes = in_bytes / (32ull * kin);
+			const unsigned grid = (unsigned)((lanes + 255) / 256);
+			report(nm, (double)lanes * 32.0 * (kin + kout), time_ms([&] { kern<<<grid, 256>>>(src, dst, lanes); }));
+		};
+		run(lane_chunk_kernel<1, 1>, 1, 1, "lane-chunk copy 32 B/lane");
+		run(lane_chunk_kernel<2, 2>, 2, 2, "lane-chunk copy 64 B/lane");
+		run(lane_chunk_kernel<3, 3>, 3, 3, "lane-chunk copy 96 B/lane");
+		run(lane_chunk_kernel<4, 4>, 4, 4, "lane-chunk copy 128 B/lane");
+		run(lane_chunk_kernel<8, 8>, 8, 8, "lane-chunk copy 256 B/lane");
+		run(lane_chunk_kernel<3, 4>, 3, 4, "lane-chunk RGB8->RGBA8 96->128 B/lane");
 	}
 	CK(cudaFree(src));
 	CK(cudaFree(dst));

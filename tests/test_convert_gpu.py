@@ -42,6 +42,27 @@ def test_every_shape_matches_oracle(oracle, sf, df, sc, dc):
 				assert same_bits(got_h, want), (mode, px, "host")
 
 
+@pytest.mark.parametrize("sf,df,sc,dc", SHAPES, ids=[f"{NAME[a]}x{c}-{NAME[b]}x{d}" for a, b, c, d in SHAPES])
+def test_every_shape_on_both_vector_kernels(oracle, monkeypatch, sf, df, sc, dc):
+	"""The 128-bit tile kernel (convert_tiles.cuh) serves shapes the 256-bit sector kernel does not fit
+	and buffers that are only 16-byte aligned; CACAO_NO_WIDE pins every shape onto it, and a
+	16-byte-offset destination reaches it the natural way."""
+	rng = np.random.default_rng(1 + (hash((sf, df, sc, dc)) & 0xFFFF))
+	px = 40961
+	src = random_samples(rng, px * sc, sf)
+	want = oracle.convert(src, sc, dc, sf, df, 1)
+	monkeypatch.setenv("CACAO_NO_WIDE", "1")
+	assert same_bits(convert_device(src, sc, dc, sf, df, 1), want)
+	monkeypatch.delenv("CACAO_NO_WIDE")
+	# ... and CACAO_FORCE_WIDE pins every shape that fits onto the 256-bit sector kernel
+	monkeypatch.setenv("CACAO_FORCE_WIDE", "1")
+	assert same_bits(convert_device(src, sc, dc, sf, df, 1), want)
+	assert same_bits(convert_device(src[: 1000 * sc], sc, dc, sf, df, 0), oracle.convert(src[: 1000 * sc], sc, dc, sf, df, 0))
+	monkeypatch.delenv("CACAO_FORCE_WIDE")
+	assert same_bits(convert_device(src, sc, dc, sf, df, 1, dst_off=16), want)
+	assert same_bits(convert_device(src, sc, dc, sf, df, 1, src_off=16), want)
+
+
 def test_golden_reference_vectors(golden):
 	"""Outputs of the UNMODIFIED reference (tests/golden/ref_golden.npz) reproduced on the GPU."""
 	from cacaoengine_b200 import _capi as c
