@@ -9,14 +9,30 @@ FMTS = (capi.FMT_U8, capi.FMT_U16, capi.FMT_F16, capi.FMT_F32)
 NAME = {capi.FMT_U8: "u8", capi.FMT_U16: "u16", capi.FMT_F16: "f16", capi.FMT_F32: "f32"}
 
 
+GUARD = 256  # bytes of canary on both sides of every test buffer
+
+
 class DevBuf:
+	"""Device buffer with canaries: compute-sanitizer is closed on this GPU pool, so every test buffer
+	carries 256 guard bytes before and after the payload and free() asserts no kernel touched them."""
+
 	def __init__(self, nbytes, offset=0):
-		self.base = device.malloc(nbytes + offset + 16)
-		self.ptr = self.base + offset
 		self.nbytes = nbytes
+		self.offset = offset
+		self.total = GUARD + offset + nbytes + GUARD
+		self.base = device.malloc(self.total)
+		self.ptr = self.base + GUARD + offset
+		self._lo = GUARD + offset
+		device.upload(self.base, np.full(self._lo, 0xA5, np.uint8))
+		device.upload(self.base + self._lo + nbytes, np.full(GUARD, 0xA5, np.uint8))
 
 	def free(self):
+		front, back = np.empty(self._lo, np.uint8), np.empty(GUARD, np.uint8)
+		device.download(front, self.base)
+		device.download(back, self.base + self._lo + self.nbytes)
 		device.free(self.base)
+		assert (front == 0xA5).all(), "kernel wrote BEFORE its buffer"
+		assert (back == 0xA5).all(), "kernel wrote PAST its buffer"
 
 
 def convert_host(src, sc, dc, sf, df, mode=capi.MODE_REF_EXACT, count=1):
