@@ -232,9 +232,10 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 		device.synth(src.data_ptr(), wn * W * ch, fmt, ch, 0xC0FFEE + 3, first_sample=w0 * W * ch, device=dev, stream=stream)
 
 		def fn():
-			for u in units:
-				mask = 0x3F if u.face < 0 else (1 << u.face)
-				device.equirect_to_cube(src.data_ptr(), W, H, ch, fmt, dst.data_ptr(), N, mask, u.row_begin, u.row_end, src_row0=w0, src_rows=wn, device=dev, stream=stream)
+			if world == 1:
+				device.equirect_to_cube(src.data_ptr(), W, H, ch, fmt, dst.data_ptr(), N, 0x3F, 0, N, device=dev, stream=stream)
+			else:  # all of this rank's (face, band) units in one launch
+				device.equirect_to_cube_units(src.data_ptr(), W, H, ch, fmt, dst.data_ptr(), N, units, src_row0=w0, src_rows=wn, device=dev, stream=stream)
 
 		ms = timed_region(torch, dist, world, fn, steps, 3)
 		alg = W * H * bpp + 6 * N * N * bpp
@@ -293,8 +294,21 @@ def run_gpu_arm(args):
 		builder.build()  # no-op when the in-tree library is current
 	torch.cuda.set_device(local)
 	if world > 1:
-		dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-		dist.barrier()
+		# NCCL announces its version on stdout at first use; stdout must carry exactly one JSON line,
+		# so fd 1 points at stderr until the communicator is up
+		sys.stdout.flush()
+		saved = os.dup(1)
+		os.dup2(2, 1)
+		try:
+			dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+			dist.barrier()
+			t = torch.zeros(1, device=f"cuda:{local}")
+			dist.all_reduce(t)
+			torch.cuda.synchronize()
+		finally:
+			sys.stdout.flush()
+			os.dup2(saved, 1)
+			os.close(saved)
 	device.init(local)
 	stream = torch.cuda.current_stream().cuda_stream
 	peak, peak_src = hbm_peak()

@@ -736,6 +736,28 @@ int cacao_img_equirect_to_cube(int device, const void* src, uint32_t W, uint32_t
 	return CACAO_OK;
 }
 
+int cacao_img_equirect_to_cube_units(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, const cacao_cube_unit* units, uint32_t n_units, void* stream) {
+	if(!ch_ok(ch) || !fmt_ok(fmt)) return fail(CACAO_E_BAD_ARG, "equirect: bad channel count %d or format %d", ch, fmt);
+	if(W == 0 || H == 0 || N == 0) return fail(CACAO_E_ZERO_DIM, "equirect: zero-sized image or face");
+	if(!src || !dst || (!units && n_units)) return fail(CACAO_E_BAD_ARG, "null pointer");
+	if(W > (1u << 24) || H > (1u << 24) || N > (1u << 23)) return fail(CACAO_E_BAD_ARG, "equirect: dimensions beyond exact float range");
+	if(src_rows == 0 || src_row0 + static_cast<uint64_t>(src_rows) > H) return fail(CACAO_E_BAD_ARG, "equirect: source window [%u,+%u) outside the image (H=%u)", src_row0, src_rows, H);
+	if(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) != 0) return fail(CACAO_E_BAD_ARG, "equirect: device buffers must be 16-byte aligned");
+	for(uint32_t u = 0; u < n_units; ++u)
+		if(units[u].face > 5) return fail(CACAO_E_BAD_ARG, "equirect: unit %u names face %u", u, units[u].face);
+	if(n_units == 0) return CACAO_OK;
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	static_assert(sizeof(cacao_cube_unit) == sizeof(CubeUnit), "unit layouts must match");
+	unsigned launches = 0;
+	cudaError_t e = equirect_launch_units(src, dst, ch, fmt, W, H, src_row0, src_rows, N, reinterpret_cast<const CubeUnit*>(units), n_units, static_cast<cudaStream_t>(stream), &launches);
+	g_launches.fetch_add(launches, std::memory_order_relaxed);
+	if(e != cudaSuccess) return fail_cuda(e, "equirect kernel launch");
+	return CACAO_OK;
+}
+
 int cacao_img_synth(int device, void* dst_dev, uint64_t first_sample, uint64_t samples, int fmt, int ch, uint32_t seed, void* stream) {
 	if(!fmt_ok(fmt) || !ch_ok(ch) || !dst_dev) return fail(CACAO_E_BAD_ARG, "synth: bad argument");
 	DeviceGuard g;

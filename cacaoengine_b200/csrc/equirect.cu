@@ -10,6 +10,8 @@
 // 0.54 GB source).
 #include "equirect.cuh"
 
+#include <algorithm>
+
 #include "cacao_device.cuh"
 #include "projection.cuh"
 
@@ -144,11 +146,12 @@ namespace cacao {
 		template<int F, int CH, typename IDX>
 		__global__ void __launch_bounds__(256) equirect_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, EquirectParams prm) {
 			constexpr int bpp = FmtTraits<F>::bytes * CH;
+			const CubeUnit unit = prm.units[blockIdx.z];
 			const uint32_t i = blockIdx.x * 32u + threadIdx.x;
-			const uint32_t j = prm.row_begin + blockIdx.y * 8u + threadIdx.y;
-			const uint32_t face = (prm.faces >> (4u * blockIdx.z)) & 7u;
+			const uint32_t j = unit.row_begin + blockIdx.y * 8u + threadIdx.y;
+			const uint32_t face = unit.face;
 			const uint32_t half = (prm.N + 1u) >> 1;
-			if(i >= half || j >= prm.row_end) return;
+			if(i >= half || j >= unit.row_end) return;
 			const uint32_t im = prm.N - 1u - i;
 
 			const float sc = face_coord(i, prm.pc);
@@ -186,10 +189,12 @@ namespace cacao {
 		}
 
 		template<int F, int CH>
-		cudaError_t launch(const void* src, void* dst, const EquirectParams& prm, unsigned nfaces, cudaStream_t stream) {
+		cudaError_t launch(const void* src, void* dst, const EquirectParams& prm, cudaStream_t stream) {
 			const dim3 block(32, 8, 1);
 			const uint32_t half = (prm.N + 1u) >> 1;
-			const dim3 grid((half + 31) / 32, (prm.row_end - prm.row_begin + 7) / 8, nfaces);
+			uint32_t max_rows = 0;
+			for(uint32_t u = 0; u < prm.n_units; ++u) max_rows = std::max(max_rows, prm.units[u].row_end - prm.units[u].row_begin);
+			const dim3 grid((half + 31) / 32, (max_rows + 7) / 8, prm.n_units);
 			const bool small = static_cast<uint64_t>(prm.src_rows) * prm.W < (1ull << 32);
 			if(small)
 				equirect_kernel<F, CH, uint32_t><<<grid, block, 0, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), prm);
@@ -199,38 +204,54 @@ namespace cacao {
 		}
 
 		template<int F>
-		cudaError_t launch_ch(const void* src, void* dst, int ch, const EquirectParams& prm, unsigned nfaces, cudaStream_t stream) {
+		cudaError_t launch_ch(const void* src, void* dst, int ch, const EquirectParams& prm, cudaStream_t stream) {
 			switch(ch) {
-				case 1: return launch<F, 1>(src, dst, prm, nfaces, stream);
-				case 3: return launch<F, 3>(src, dst, prm, nfaces, stream);
-				case 4: return launch<F, 4>(src, dst, prm, nfaces, stream);
+				case 1: return launch<F, 1>(src, dst, prm, stream);
+				case 3: return launch<F, 3>(src, dst, prm, stream);
+				case 4: return launch<F, 4>(src, dst, prm, stream);
 			}
 			return cudaErrorInvalidValue;
 		}
 	}
 
-	cudaError_t equirect_launch(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, uint32_t face_mask, uint32_t row_begin, uint32_t row_end, cudaStream_t stream) {
+	cudaError_t equirect_launch_units(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, const CubeUnit* units, uint32_t n_units, cudaStream_t stream, unsigned* launches) {
+		if(launches) *launches = 0;
 		EquirectParams prm;
 		prm.W = W;
 		prm.H = H;
 		prm.N = N;
 		prm.src_row0 = src_row0;
 		prm.src_rows = src_rows;
-		prm.row_begin = row_begin;
-		prm.row_end = row_end;
 		prm.pc = make_proj_const(N, W, H);
-		prm.faces = 0;
-		unsigned nfaces = 0;
-		for(uint32_t f = 0; f < 6; ++f)
-			if(face_mask & (1u << f)) prm.faces |= f << (4u * nfaces++);
-		if(nfaces == 0 || row_begin >= row_end) return cudaSuccess;
-		switch(fmt) {
-			case CACAO_FMT_U8: return launch_ch<CACAO_FMT_U8>(src, dst, ch, prm, nfaces, stream);
-			case CACAO_FMT_U16: return launch_ch<CACAO_FMT_U16>(src, dst, ch, prm, nfaces, stream);
-			case CACAO_FMT_F16: return launch_ch<CACAO_FMT_F16>(src, dst, ch, prm, nfaces, stream);
-			case CACAO_FMT_F32: return launch_ch<CACAO_FMT_F32>(src, dst, ch, prm, nfaces, stream);
+		uint32_t next = 0;
+		while(next < n_units) {
+			prm.n_units = 0;
+			while(next < n_units && prm.n_units < kMaxUnitsPerLaunch) {
+				CubeUnit u = units[next++];
+				if(u.row_end > N) u.row_end = N;
+				if(u.face < 6 && u.row_begin < u.row_end) prm.units[prm.n_units++] = u;
+			}
+			if(prm.n_units == 0) continue;
+			cudaError_t e;
+			switch(fmt) {
+				case CACAO_FMT_U8: e = launch_ch<CACAO_FMT_U8>(src, dst, ch, prm, stream); break;
+				case CACAO_FMT_U16: e = launch_ch<CACAO_FMT_U16>(src, dst, ch, prm, stream); break;
+				case CACAO_FMT_F16: e = launch_ch<CACAO_FMT_F16>(src, dst, ch, prm, stream); break;
+				case CACAO_FMT_F32: e = launch_ch<CACAO_FMT_F32>(src, dst, ch, prm, stream); break;
+				default: return cudaErrorInvalidValue;
+			}
+			if(e != cudaSuccess) return e;
+			if(launches) *launches += 1;
 		}
-		return cudaErrorInvalidValue;
+		return cudaSuccess;
+	}
+
+	cudaError_t equirect_launch(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, uint32_t face_mask, uint32_t row_begin, uint32_t row_end, cudaStream_t stream) {
+		CubeUnit units[6];
+		uint32_t n = 0;
+		for(uint32_t f = 0; f < 6; ++f)
+			if(face_mask & (1u << f)) units[n++] = {f, row_begin, row_end};
+		return equirect_launch_units(src, dst, ch, fmt, W, H, src_row0, src_rows, N, units, n, stream, nullptr);
 	}
 
 	// Host-side planning with the same arithmetic as the kernel.  theta (hence ys) is monotone in tc

@@ -9,16 +9,26 @@
 
 namespace cacao {
 
+	constexpr int kMaxUnitsPerLaunch = 8;
+
+	// one work unit = rows [row_begin,row_end) of one face
+	struct CubeUnit {
+		uint32_t face, row_begin, row_end;
+	};
+
 	struct EquirectParams {
 		uint32_t W, H;               // source size in pixels
 		uint32_t N;                  // face edge in pixels
 		uint32_t src_row0, src_rows; // window of source rows present in `src`
-		uint32_t row_begin, row_end; // face rows to produce
-		uint32_t faces;              // packed list: nibble k = k-th selected face
+		uint32_t n_units;            // blockIdx.z selects the unit
+		CubeUnit units[kMaxUnitsPerLaunch];
 		ProjConst pc;
 	};
 
-	// Enqueue the resampling of rows [row_begin,row_end) of every face in face_mask.
+	// Enqueue the resampling of a list of (face, row band) units: ceil(n/8) launches, *launches gets the count.
+	cudaError_t equirect_launch_units(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, const CubeUnit* units, uint32_t n_units, cudaStream_t stream, unsigned* launches);
+
+	// Enqueue the resampling of rows [row_begin,row_end) of every face in face_mask (one launch).
 	cudaError_t equirect_launch(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, uint32_t face_mask, uint32_t row_begin, uint32_t row_end, cudaStream_t stream);
 
 	// Which source rows that work unit reads (host arithmetic identical to the kernel's).

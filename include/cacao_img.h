@@ -125,6 +125,20 @@ int cacao_img_equirect_to_cube(int device, const void* src, uint32_t W, uint32_t
 							   uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, uint32_t face_mask,
 							   uint32_t row_begin, uint32_t row_end, int mem, void* stream);
 
+/* One (face, row band) work unit of a cubemap: rows [row_begin,row_end) of face `face` (0..5). */
+typedef struct cacao_cube_unit {
+	uint32_t face;
+	uint32_t row_begin;
+	uint32_t row_end;
+} cacao_cube_unit;
+
+/* The same resampling for an explicit list of work units -- what one GPU of a sharded job owns
+ * (cacaoengine_b200/sharding.py deals units out) -- in ceil(n_units/8) kernel launches instead of
+ * one per unit.  src/dst/window arguments as above; device memory only. */
+int cacao_img_equirect_to_cube_units(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0,
+									 uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N,
+									 const cacao_cube_unit* units, uint32_t n_units, void* stream);
+
 /* Host-side planning: the inclusive-exclusive window of source rows that the work unit
  * (face_mask, [row_begin,row_end)) reads, so a shard can upload just that band. */
 int cacao_img_equirect_src_window(uint32_t W, uint32_t H, uint32_t N, uint32_t face_mask, uint32_t row_begin,

@@ -109,6 +109,32 @@ def test_face_masks_row_bands_and_source_windows(oracle):
 	assert same_bits(acc, full)
 
 
+def test_unit_list_launch_matches_per_unit_calls(oracle):
+	"""cacao_img_equirect_to_cube_units: a rank's whole unit list (more than 8 -> two launches) in one
+	call equals the oracle on exactly those rows and writes nothing else."""
+	from cacaoengine_b200 import _capi as c, device, sharding
+
+	W, H, N, ch, fmt = 300, 150, 70, 3, c.FMT_U16
+	src = oracle.synth(W * H * ch, fmt, ch, 6)
+	units = sharding.cube_units(N, 5)[::3]  # 10 units, mixed faces and bands
+	assert len(units) == 10
+	want = np.zeros(6 * N * N * ch, np.uint16)
+	for u in units:
+		oracle.equirect_to_cube(src, W, H, ch, fmt, N, face_mask=1 << u.face, row_begin=u.row_begin, row_end=u.row_end, out=want)
+	a, b = DevBuf(src.nbytes), DevBuf(want.nbytes)
+	device.upload(a.ptr, src)
+	device.upload(b.ptr, np.zeros_like(want))
+	before = device.launch_count()
+	device.equirect_to_cube_units(a.ptr, W, H, ch, fmt, b.ptr, N, units)
+	assert device.launch_count() - before == 2
+	got = np.empty_like(want)
+	device.download(got, b.ptr)
+	a.free(), b.free()
+	assert same_bits(got, want)
+	with pytest.raises(c.CacaoError):
+		device.equirect_to_cube_units(1, W, H, ch, fmt, 1, N, [(7, 0, 1)])
+
+
 def test_seam_and_poles(oracle):
 	"""One-hot panoramas: a texel on the u=0/1 seam and texels in the pole rows land identically."""
 	from cacaoengine_b200 import _capi as c
