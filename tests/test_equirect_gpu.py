@@ -135,6 +135,28 @@ def test_unit_list_launch_matches_per_unit_calls(oracle):
 		device.equirect_to_cube_units(1, W, H, ch, fmt, 1, N, [(7, 0, 1)])
 
 
+@pytest.mark.parametrize("fmt,ch", [(3, 4), (2, 4), (0, 4), (3, 1), (1, 4)], ids=["f32x4", "f16x4", "u8x4", "f32x1", "u16x4"])
+def test_tma_staged_variant_is_bit_identical(oracle, monkeypatch, fmt, ch):
+	"""The experimental TMA-staged kernel (CACAO_EQUIRECT_STAGED=1; cp.async.bulk row segments into
+	shared memory, LDS taps, per-side fallback to global gathers) must give exactly the gather kernel's
+	result: boxes that fit, boxes that do not (polar caps), the seam, odd sizes and row windows."""
+	from cacaoengine_b200 import device
+
+	monkeypatch.setenv("CACAO_EQUIRECT_STAGED", "1")
+	for (W, H, N) in ((512, 256, 128), (1000, 500, 333), (256, 128, 400)):
+		src = oracle.synth(W * H * ch, fmt, ch, 17)
+		want = oracle.equirect_to_cube(src, W, H, ch, fmt, N)
+		assert same_bits(gpu_equirect_device(src, W, H, ch, fmt, N), want), (W, H, N)
+	W, H, N = 512, 256, 96
+	src = oracle.synth(W * H * ch, fmt, ch, 18)
+	full = oracle.equirect_to_cube(src, W, H, ch, fmt, N)
+	for f in (0, 2, 5):
+		win = device.equirect_src_window(W, H, N, 1 << f, 24, 72)
+		part = gpu_equirect_device(src, W, H, ch, fmt, N, 1 << f, 24, 72, window=win)
+		sl = slice((f * N + 24) * N * ch, (f * N + 72) * N * ch)
+		assert same_bits(part[sl], full[sl]), f
+
+
 def test_seam_and_poles(oracle):
 	"""One-hot panoramas: a texel on the u=0/1 seam and texels in the pole rows land identically."""
 	from cacaoengine_b200 import _capi as c
