@@ -5,6 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 from cacaoengine_b200 import FMT_F16, FMT_F32, FMT_U8, FMT_U16, device
 device.init(0)
+KEY = sys.argv[1] if len(sys.argv) > 1 else "CACAO_EQUIRECT_STAGED"
 stream = torch.cuda.current_stream().cuda_stream
 def timeit(fn, reps=20):
 	for _ in range(3): fn()
@@ -23,11 +24,11 @@ for name, W, H, N, ch, fmt in [("cfg3 rgba32f 8192x4096->2048", 8192, 4096, 2048
 	d0 = torch.zeros(6 * N * N * bpp, dtype=torch.uint8, device="cuda")
 	d1 = torch.zeros(6 * N * N * bpp, dtype=torch.uint8, device="cuda")
 	device.synth(src.data_ptr(), W * H * ch, fmt, ch, 3, stream=stream)
-	os.environ["CACAO_EQUIRECT_STAGED"] = "0"
+	os.environ[KEY] = "0"
 	t0 = timeit(lambda: device.equirect_to_cube(src.data_ptr(), W, H, ch, fmt, d0.data_ptr(), N, stream=stream))
-	os.environ["CACAO_EQUIRECT_STAGED"] = "1"
+	os.environ[KEY] = "1"
 	t1 = timeit(lambda: device.equirect_to_cube(src.data_ptr(), W, H, ch, fmt, d1.data_ptr(), N, stream=stream))
 	same = bool(torch.equal(d0, d1))
 	alg = W * H * bpp + 6 * N * N * bpp
-	print(f"{name:36s} gather {t0:8.4f} ms ({alg/t0/1e6/6551.7:.3f})   staged {t1:8.4f} ms ({alg/t1/1e6/6551.7:.3f})   identical={same}", flush=True)
+	print(f"{name:36s} off {t0:8.4f} ms ({alg/t0/1e6/6551.7:.3f})   on {t1:8.4f} ms ({alg/t1/1e6/6551.7:.3f})   identical={same}", flush=True)
 	del src, d0, d1
