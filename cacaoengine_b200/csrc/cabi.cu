@@ -682,6 +682,33 @@ int cacao_img_flip_rows(int device, const void* src, void* dst, uint32_t w, uint
 	return download_any(c, static_cast<uint8_t*>(dst), c->stage_out[0], bytes, c->s_run);
 }
 
+int cacao_img_shift_left_u16(int device, const void* src, void* dst, uint64_t samples, uint32_t shift, int mem, void* stream) {
+	if(!src || !dst) return fail(CACAO_E_BAD_ARG, "null image pointer");
+	if(shift > 15) return fail(CACAO_E_BAD_ARG, "shift %u out of range for 16-bit samples", shift);
+	if(mem != CACAO_MEM_HOST && mem != CACAO_MEM_DEVICE) return fail(CACAO_E_BAD_ARG, "unknown memory kind %d", mem);
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	if(samples == 0) return CACAO_OK;
+	const unsigned n_launch = 1u + ((samples % 8) ? 1u : 0u);
+	if(mem == CACAO_MEM_DEVICE) {
+		cudaError_t e = shift_left_u16_launch(src, dst, samples, shift, static_cast<cudaStream_t>(stream));
+		if(e != cudaSuccess) return fail_cuda(e, "shift kernel launch");
+		g_launches.fetch_add(n_launch, std::memory_order_relaxed);
+		return CACAO_OK;
+	}
+	std::lock_guard<std::mutex> lock(c->pipe_mutex);
+	rc = ensure_stage(c, samples * 2, 0);
+	if(rc) return rc;
+	rc = upload_any(c, c->stage_in[0], static_cast<const uint8_t*>(src), samples * 2, c->s_run);
+	if(rc) return rc;
+	cudaError_t e = shift_left_u16_launch(c->stage_in[0], c->stage_in[0], samples, shift, c->s_run);
+	if(e != cudaSuccess) return fail_cuda(e, "shift kernel launch");
+	g_launches.fetch_add(n_launch, std::memory_order_relaxed);
+	return download_any(c, static_cast<uint8_t*>(dst), c->stage_in[0], samples * 2, c->s_run);
+}
+
 int cacao_img_equirect_src_window(uint32_t W, uint32_t H, uint32_t N, uint32_t face_mask, uint32_t row_begin, uint32_t row_end, uint32_t* src_row0, uint32_t* src_rows) {
 	if(!src_row0 || !src_rows) return fail(CACAO_E_BAD_ARG, "null out-pointer");
 	if(W == 0 || H == 0 || N == 0) return fail(CACAO_E_ZERO_DIM, "equirect: zero-sized image or face");

@@ -26,6 +26,22 @@ namespace cacao {
 			}
 		}
 
+		// 16-bit left shift on packed pairs: (w << s) with the bits that crossed the half-word border masked off
+		__global__ void __launch_bounds__(256) shl16_vec_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t units, uint32_t shift, uint32_t mask) {
+			const uint64_t u = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+			if(u >= units) return;
+			uint4 v = ldg_stream(src + u);
+			v.x = (v.x << shift) & mask;
+			v.y = (v.y << shift) & mask;
+			v.z = (v.z << shift) & mask;
+			v.w = (v.w << shift) & mask;
+			stg_stream(dst + u, v);
+		}
+		__global__ void __launch_bounds__(256) shl16_scalar_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, uint64_t begin, uint64_t end, uint32_t shift) {
+			const uint64_t k = begin + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+			if(k < end) dst[k] = static_cast<uint16_t>(static_cast<uint32_t>(src[k]) << shift);
+		}
+
 		__device__ __forceinline__ float synth_float(uint32_t hsh) {
 			// (1 + m/65536) * 2^(e-8), e in [0,16): assembled from bits so host and device agree exactly
 			const uint32_t e = (hsh >> 24) & 15u, m = (hsh >> 8) & 0xFFFFu;
@@ -75,6 +91,23 @@ namespace cacao {
 		else
 			flip_rows_byte_kernel<<<grid_for(pitch * h, sm_count), 256, 0, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), pitch, h);
 		return cudaGetLastError();
+	}
+
+	cudaError_t shift_left_u16_launch(const void* src, void* dst, uint64_t samples, uint32_t shift, cudaStream_t stream) {
+		const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+		const uint64_t units = vec ? samples / 8 : 0;
+		if(units) {
+			const uint32_t half = (0xFFFFu << shift) & 0xFFFFu;
+			shl16_vec_kernel<<<static_cast<unsigned>((units + 255) / 256), 256, 0, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), units, shift, half | (half << 16));
+			cudaError_t e = cudaGetLastError();
+			if(e != cudaSuccess) return e;
+		}
+		if(units * 8 < samples) {
+			const uint64_t rest = samples - units * 8;
+			shl16_scalar_kernel<<<static_cast<unsigned>((rest + 255) / 256), 256, 0, stream>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), units * 8, samples, shift);
+			return cudaGetLastError();
+		}
+		return cudaSuccess;
 	}
 
 	cudaError_t synth_launch(void* dst, uint64_t first_sample, uint64_t samples, int fmt, int ch, uint32_t seed, int sm_count, cudaStream_t stream) {

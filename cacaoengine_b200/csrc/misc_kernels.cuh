@@ -10,6 +10,9 @@ namespace cacao {
 	// out.row[y] = src.row[h-1-y]; pitch in bytes (the semantics libs/image/src/Flip.cpp:6-42 intends)
 	cudaError_t flip_rows_launch(const void* src, void* dst, uint64_t pitch, uint32_t h, int sm_count, cudaStream_t stream);
 
+	// dst[k] = uint16(src[k] << shift) (libs/image/src/JPEG.cpp:79-82 uses shift 4)
+	cudaError_t shift_left_u16_launch(const void* src, void* dst, uint64_t samples, uint32_t shift, cudaStream_t stream);
+
 	// counter-hash synthetic samples (DESIGN.md "Synthetic inputs")
 	cudaError_t synth_launch(void* dst, uint64_t first_sample, uint64_t samples, int fmt, int ch, uint32_t seed, int sm_count, cudaStream_t stream);
 

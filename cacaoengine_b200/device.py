@@ -71,6 +71,11 @@ def convert_batch(src: int, dst: int, pixels_per_image: int, count: int, src_ch:
 	capi.check(capi.lib().cacao_img_convert_batch(device, src, dst, pixels_per_image, count, src_ch, dst_ch, src_fmt, dst_fmt, mode, mem, stream))
 
 
+def shift_left_u16(src: int, dst: int, samples: int, shift: int, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> None:
+	"""dst[k] = uint16(src[k] << shift): the JPEG decoder's 12 -> 16 bit widening (JPEG.cpp:79-82, shift 4)."""
+	capi.check(capi.lib().cacao_img_shift_left_u16(device, src, dst, samples, shift, mem, stream))
+
+
 def flip_rows(src: int, dst: int, w: int, h: int, bytes_per_pixel: int, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> None:
 	capi.check(capi.lib().cacao_img_flip_rows(device, src, dst, w, h, bytes_per_pixel, mem, stream))
 

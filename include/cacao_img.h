@@ -103,6 +103,15 @@ int cacao_img_convert_batch(int device, const void* src, void* dst, uint64_t pix
 							int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, int mem, void* stream);
 
 /*
+ * dst[k] = (uint16_t)(src[k] << shift) over `samples` 16-bit samples, shift in [0,15].
+ *   replaces the 12 -> 16 bit widening loop of the JPEG decoder, libs/image/src/JPEG.cpp:79-82
+ *   (`imgDataSixteen[i] = uint16_t(twelveBit[i]) << 4`), one of the per-pixel loops next to the
+ *   hot path.  In place (src == dst) is allowed.
+ */
+int cacao_img_shift_left_u16(int device, const void* src, void* dst, uint64_t samples, uint32_t shift, int mem,
+							 void* stream);
+
+/*
  * Vertical mirror, out.row[y] = src.row[h-1-y], src untouched: the semantics
  * libs/image/src/Flip.cpp:6-42 intends (the reference itself overruns its buffer for h >= 2).
  */

@@ -208,6 +208,30 @@ def test_flip_rows(oracle, w, h, bpp):
 	assert (oracle.flip_rows(out2, w, h, bpp) == src).all()
 
 
+def test_jpeg_12_to_16_bit_widening():
+	"""libs/image/src/JPEG.cpp:79-82: `uint16_t(twelveBit[i]) << 4` over int16 samples -- restated in
+	numpy (the reference loop needs libjpeg-turbo to build, so this row is parity-unpinned)."""
+	from cacaoengine_b200 import _capi as c, device
+	from gpu_util import DevBuf
+
+	rng = np.random.default_rng(44)
+	for n in (1, 7, 8, 1000, 40963):
+		src = rng.integers(0, 4096, n).astype(np.int16)
+		src[:1] = -1  # the cast to uint16_t wraps negatives before shifting
+		want = (src.astype(np.uint16).astype(np.uint32) << 4).astype(np.uint16)
+		out = np.empty(n, np.uint16)
+		c.check(c.lib().cacao_img_shift_left_u16(-1, src.ctypes.data, out.ctypes.data, n, 4, c.MEM_HOST, None))
+		assert (out == want).all()
+		a = DevBuf(n * 2)
+		device.upload(a.ptr, src)
+		device.shift_left_u16(a.ptr, a.ptr, n, 4)  # in place
+		got = np.empty(n, np.uint16)
+		device.download(got, a.ptr)
+		a.free()
+		assert (got == want).all()
+	assert c.lib().cacao_img_shift_left_u16(-1, src.ctypes.data, out.ctypes.data, 4, 16, c.MEM_HOST, None) == c.E_BAD_ARG
+
+
 def test_device_synth_and_checksum_match_host(oracle):
 	from cacaoengine_b200 import _capi as c, device
 	from gpu_util import DevBuf
