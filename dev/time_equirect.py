@@ -8,14 +8,14 @@ from cacaoengine_b200 import FMT_F16, FMT_F32, FMT_U8, FMT_U16, device
 device.init(0)
 stream = torch.cuda.current_stream().cuda_stream
 def timeit(fn, reps=20):
+	"""back-to-back launches between two events (what bench.py measures)"""
 	for _ in range(3): fn()
 	torch.cuda.synchronize()
-	ts = []
-	for _ in range(reps):
-		a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-		a.record(); fn(); b.record(); torch.cuda.synchronize()
-		ts.append(a.elapsed_time(b))
-	return sum(ts) / len(ts)
+	a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	a.record()
+	for _ in range(reps): fn()
+	b.record(); torch.cuda.synchronize()
+	return a.elapsed_time(b) / reps
 
 B = {FMT_U8: 1, FMT_U16: 2, FMT_F16: 2, FMT_F32: 4}
 for name, W, H, N, ch, fmt in [("cfg3 rgba32f 8192x4096->2048", 8192, 4096, 2048, 4, FMT_F32), ("cfg5 rgba32f 16384x8192->4096", 16384, 8192, 4096, 4, FMT_F32),
