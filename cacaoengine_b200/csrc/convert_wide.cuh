@@ -118,9 +118,11 @@ namespace cacao {
 	template<int SF, int DF, int SC, int DC>
 	cudaError_t launch_convert_wide(const void* src, void* dst, uint64_t n_runs, const uint8_t* lut_global, const uint16_t* lut2_global, uint32_t gray16_cap, cudaStream_t stream) {
 		using S = WideShape<SF, DF, SC, DC>;
-		// table shapes: the full table in shared memory needs the fewest instructions per sample but
-		// 64 KiB per block, so it runs 1024-thread blocks over long contiguous ranges
-		bool direct = S::needs_lut;
+		// table shapes: the 8 KiB two-level form is the default.  The full 64 KiB table (fewest
+		// instructions per sample, but 1024-thread blocks and 3 blocks/SM) is kept selectable: on
+		// uniform-random samples it is 2-15 % behind (RGBA16->RGBA8 5.84 vs 5.93 TB/s, Gray16->Gray8
+		// 4.47 vs 5.23), on smooth images about level (dev/sweep_lut.py).
+		bool direct = false;
 		if(const char* e = getenv("CACAO_LUT_DIRECT")) direct = S::needs_lut && atoi(e) != 0;
 		uint32_t iters = S::needs_lut ? (direct ? 16u : 4u) : 1u;
 		if(const char* e = getenv("CACAO_TILE_ITERS")) iters = static_cast<uint32_t>(atoi(e) > 0 ? atoi(e) : 1);

@@ -28,6 +28,7 @@ TRAFFIC_KEYS = {
 	"convert_tiles_kernel<0, 0, 3, 4": "cfg4a_16x_4096sq_rgb8_to_rgba8_per_launch",
 	"convert_tiles_kernel<0, 3, 3, 4": "cfg4b_16x_4096sq_rgb8_to_rgba32f_per_launch",
 	"convert_tiles_kernel<1, 0, 4, 3": "lut_64x_2048sq_rgba16_to_rgb8",
+	"convert_wide_kernel<1, 0, 4, 3": "lut_64x_2048sq_rgba16_to_rgb8",
 	"equirect_kernel<3, 4": "cfg3_equirect_8192x4096_rgba32f_to_6x2048",
 }
 UNIT_SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0, "msecond": 1e-3, "usecond": 1e-6, "nsecond": 1e-9, "second": 1.0}
