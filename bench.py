@@ -138,6 +138,29 @@ def cpu_baseline_block():
 	return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{frames} of 256 frames (1920x1080 RGBA8 -> RGBA16F), oracle/cacao_oracle.c orc_convert_mt, OpenMP x{threads}, {secs:.2f} s; single-thread {rate1:.4f} {UNIT}", "single_thread_value": rate1}
 
 
+def cpu_reference_cfg4a():
+	"""BASELINE config 4a is the one headline conversion the reference itself implements
+	(ChangeChannelLayout RGB8 -> RGBA8, libs/image/src/Layout.cpp:8-103): time the UNMODIFIED reference
+	sources (oracle/_ref, compiled by path in the build container) on this box's host cores."""
+	import ctypes as C
+
+	from oracle import pyoracle as po
+
+	if not po.have_ref():
+		return {"unavailable": "oracle/_ref/libcacaoimage_ref.so was not built (no /root/reference at build time)"}
+	lib = po.ref()
+	threads = lib.ref_max_threads()
+	w = h = 4096
+	images = max(4, min(16, threads))
+	src = po.synth(images * w * h * 3, po.U8, 3, 0xC0FFEE + 4)
+	secs = C.c_double()
+	lib.ref_batch_change_layout(src.ctypes.data, None, w, h, 3, 4, 8, 1, 1, C.byref(secs))
+	single = w * h / secs.value / 1e9
+	lib.ref_batch_change_layout(src.ctypes.data, None, w, h, 3, 4, 8, images, threads, C.byref(secs))
+	return {"value": images * w * h / secs.value / 1e9, "unit": UNIT, "cores": threads, "kind": "reference", "single_thread_value": single,
+			"sample": f"{images} of 4096 images (4096x4096 RGB8 -> RGBA8), libcacaoimage::ChangeChannelLayout as shipped, one call per image, OpenMP x{threads} over images, {secs.value:.2f} s"}
+
+
 def run_reference_arm(args):
 	"""--impl reference: the CPU implementation of the same config on the host cores."""
 	rank = int(os.environ.get("RANK", "0"))
@@ -383,6 +406,11 @@ def run_gpu_arm(args):
 			extra = {"error": repr(e)}
 	if rank == 0:
 		if extra is not None:
+			if world == 1 and "error" not in extra:
+				try:
+					extra["cfg4a_4096x_4096sq_rgb8_to_rgba8"]["cpu_baseline"] = cpu_reference_cfg4a()
+				except Exception as e:
+					extra["cfg4a_4096x_4096sq_rgb8_to_rgba8"]["cpu_baseline"] = {"error": repr(e)}
 			line["extra"] = extra
 		print(json.dumps(line), flush=True)
 	if world > 1:
