@@ -20,12 +20,11 @@ namespace cacao {
 
 	namespace {
 
-		// ---- one texel as CH floats -------------------------------------------------------------
+		// ---- one texel: raw words from global memory, then CH floats -------------------------------
 		template<int F, int CH>
-		__device__ __forceinline__ void load_texel(const uint8_t* __restrict__ p, float (&v)[CH]) {
+		__device__ __forceinline__ void load_words(const uint8_t* __restrict__ p, uint32_t (&w)[4]) {
 			constexpr int sb = FmtTraits<F>::bytes;
 			constexpr int bpp = sb * CH;
-			uint32_t w[4] = {0, 0, 0, 0};
 			if constexpr(bpp == 16) {
 				const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
 				w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
@@ -48,6 +47,10 @@ namespace cacao {
 			} else {
 				w[0] = __ldg(p);
 			}
+		}
+
+		template<int F, int CH>
+		__device__ __forceinline__ void words_to_floats(const uint32_t (&w)[4], float (&v)[CH]) {
 #pragma unroll
 			for(int c = 0; c < CH; ++c) {
 				if constexpr(F == CACAO_FMT_U8)
@@ -59,6 +62,13 @@ namespace cacao {
 				else
 					v[c] = __uint_as_float(w[c]);
 			}
+		}
+
+		template<int F, int CH>
+		__device__ __forceinline__ void load_texel(const uint8_t* __restrict__ p, float (&v)[CH]) {
+			uint32_t w[4] = {0, 0, 0, 0};
+			load_words<F, CH>(p, w);
+			words_to_floats<F, CH>(w, v);
 		}
 
 		template<int F, int CH>
@@ -215,21 +225,6 @@ namespace cacao {
 				asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(saddr));
 			else
 				asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[0]) : "r"(saddr));
-		}
-
-		template<int F, int CH>
-		__device__ __forceinline__ void words_to_floats(const uint32_t (&w)[4], float (&v)[CH]) {
-#pragma unroll
-			for(int c = 0; c < CH; ++c) {
-				if constexpr(F == CACAO_FMT_U8)
-					v[c] = static_cast<float>((w[c >> 2] >> ((c & 3) * 8)) & 0xFFu);
-				else if constexpr(F == CACAO_FMT_U16)
-					v[c] = static_cast<float>((w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu);
-				else if constexpr(F == CACAO_FMT_F16)
-					v[c] = f16_bits_to_f32(static_cast<uint16_t>((w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu));
-				else
-					v[c] = __uint_as_float(w[c]);
-			}
 		}
 
 		template<int F, int CH>
