@@ -194,7 +194,7 @@ namespace {
 		cudaEvent_t ev_in[kSlots] = {}, ev_run[kSlots] = {}, ev_out[kSlots] = {};
 		uint8_t* stage_in[kSlots] = {};
 		uint8_t* stage_out[kSlots] = {};
-		size_t stage_in_cap = 0, stage_out_cap = 0;
+		size_t stage_in_cap[kSlots] = {}, stage_out_cap[kSlots] = {};
 		uint8_t* pin_in[kSlots] = {}; // pinned ring for pageable host buffers
 		uint8_t* pin_out[kSlots] = {};
 		size_t pin_in_cap = 0, pin_out_cap = 0;
@@ -301,30 +301,27 @@ namespace {
 		delete c;
 	}
 
-	int ensure_stage(DeviceCtx* c, size_t in_bytes, size_t out_bytes) {
-		if(in_bytes > c->stage_in_cap) {
-			for(int s = 0; s < kSlots; ++s) {
-				if(c->stage_in[s]) cudaFree(c->stage_in[s]);
-				c->stage_in[s] = nullptr;
+	// Device staging buffers of the host-memory paths.  The chunked conversion pipeline uses all kSlots
+	// slots; the single-shot paths (equirect, flip, shift) use slot 0 only, so only it grows for them.
+	int ensure_stage(DeviceCtx* c, size_t in_bytes, size_t out_bytes, int slots = kSlots) {
+		auto grow = [](uint8_t*& buf, size_t& cap, size_t need, const char* what) -> int {
+			if(need <= cap) return CACAO_OK;
+			if(buf) cudaFree(buf);
+			buf = nullptr;
+			cap = 0;
+			cudaError_t e = cudaMalloc(&buf, need);
+			if(e != cudaSuccess) {
+				cudaGetLastError();
+				return fail(CACAO_E_NO_MEMORY, "cudaMalloc(%zu) for the %s ring failed: %s", need, what, cudaGetErrorString(e));
 			}
-			c->stage_in_cap = 0;
-			for(int s = 0; s < kSlots; ++s) {
-				cudaError_t e = cudaMalloc(&c->stage_in[s], in_bytes);
-				if(e != cudaSuccess) return fail(CACAO_E_NO_MEMORY, "cudaMalloc(%zu) for the upload ring failed: %s", in_bytes, cudaGetErrorString(e));
-			}
-			c->stage_in_cap = in_bytes;
-		}
-		if(out_bytes > c->stage_out_cap) {
-			for(int s = 0; s < kSlots; ++s) {
-				if(c->stage_out[s]) cudaFree(c->stage_out[s]);
-				c->stage_out[s] = nullptr;
-			}
-			c->stage_out_cap = 0;
-			for(int s = 0; s < kSlots; ++s) {
-				cudaError_t e = cudaMalloc(&c->stage_out[s], out_bytes);
-				if(e != cudaSuccess) return fail(CACAO_E_NO_MEMORY, "cudaMalloc(%zu) for the readback ring failed: %s", out_bytes, cudaGetErrorString(e));
-			}
-			c->stage_out_cap = out_bytes;
+			cap = need;
+			return CACAO_OK;
+		};
+		for(int s = 0; s < slots; ++s) {
+			int rc = grow(c->stage_in[s], c->stage_in_cap[s], in_bytes, "upload");
+			if(rc) return rc;
+			rc = grow(c->stage_out[s], c->stage_out_cap[s], out_bytes, "readback");
+			if(rc) return rc;
 		}
 		return CACAO_OK;
 	}
@@ -612,6 +609,12 @@ int cacao_img_upload(int device, void* dst_dev, const void* src_host, uint64_t b
 	DeviceCtx* c = nullptr;
 	int rc = get_ctx(device, &c, g);
 	if(rc) return rc;
+	if(bytes >= (1u << 20) && is_pageable(src_host)) {
+		// pageable memory cannot be DMA'd asynchronously anyway: stage it through the pinned ring with the
+		// host copy pool (3x the driver's own pageable path) and return when it has landed
+		std::lock_guard<std::mutex> lock(c->pipe_mutex);
+		return upload_any(c, static_cast<uint8_t*>(dst_dev), static_cast<const uint8_t*>(src_host), bytes, static_cast<cudaStream_t>(stream));
+	}
 	CU_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
 	return CACAO_OK;
 }
@@ -621,6 +624,10 @@ int cacao_img_download(int device, void* dst_host, const void* src_dev, uint64_t
 	DeviceCtx* c = nullptr;
 	int rc = get_ctx(device, &c, g);
 	if(rc) return rc;
+	if(bytes >= (1u << 20) && is_pageable(dst_host)) {
+		std::lock_guard<std::mutex> lock(c->pipe_mutex);
+		return download_any(c, static_cast<uint8_t*>(dst_host), static_cast<const uint8_t*>(src_dev), bytes, static_cast<cudaStream_t>(stream));
+	}
 	CU_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
 	return CACAO_OK;
 }
@@ -672,7 +679,7 @@ int cacao_img_flip_rows(int device, const void* src, void* dst, uint32_t w, uint
 	}
 	std::lock_guard<std::mutex> lock(c->pipe_mutex);
 	const uint64_t bytes = pitch * h;
-	rc = ensure_stage(c, bytes, bytes);
+	rc = ensure_stage(c, bytes, bytes, 1);
 	if(rc) return rc;
 	rc = upload_any(c, c->stage_in[0], static_cast<const uint8_t*>(src), bytes, c->s_run);
 	if(rc) return rc;
@@ -699,7 +706,7 @@ int cacao_img_shift_left_u16(int device, const void* src, void* dst, uint64_t sa
 		return CACAO_OK;
 	}
 	std::lock_guard<std::mutex> lock(c->pipe_mutex);
-	rc = ensure_stage(c, samples * 2, 0);
+	rc = ensure_stage(c, samples * 2, 0, 1);
 	if(rc) return rc;
 	rc = upload_any(c, c->stage_in[0], static_cast<const uint8_t*>(src), samples * 2, c->s_run);
 	if(rc) return rc;
@@ -746,7 +753,7 @@ int cacao_img_equirect_to_cube(int device, const void* src, uint32_t W, uint32_t
 	const uint64_t pitch = static_cast<uint64_t>(W) * bpp;
 	const uint64_t cube_bytes = 6ull * N * N * bpp;
 	std::lock_guard<std::mutex> lock(c->pipe_mutex);
-	rc = ensure_stage(c, need_rows * pitch, cube_bytes);
+	rc = ensure_stage(c, need_rows * pitch, cube_bytes, 1);
 	if(rc) return rc;
 	const uint8_t* hsrc = static_cast<const uint8_t*>(src) + static_cast<uint64_t>(need0 - src_row0) * pitch;
 	rc = upload_any(c, c->stage_in[0], hsrc, need_rows * pitch, c->s_run);

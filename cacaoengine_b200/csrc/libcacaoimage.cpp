@@ -5,6 +5,7 @@
 // std::vector, metadata copied through (libs/image/src/Layout.cpp:12-13, Colordepth.cpp:11-18),
 // failures as std::runtime_error carrying the reference's message texts
 // (libs/common/include/libcacaocommon.hpp:20-25).
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -167,49 +168,69 @@ namespace libcacaoimage {
 		const std::size_t bpp = BytesPerPixel(src.layout, src.format);
 		if(src.data.size() < static_cast<std::size_t>(src.w) * src.h * bpp) throw std::runtime_error("equirect source buffer is smaller than w*h*bytes-per-pixel");
 		const std::size_t face_bytes = static_cast<std::size_t>(faceSize) * faceSize * bpp;
-		std::vector<unsigned char> cube(6 * face_bytes);
+		// the six results are allocated up front and every device reads its rows back straight into them
+		std::array<ImageEx, 6> faces;
+		for(unsigned f = 0; f < 6; ++f) {
+			faces[f].w = faces[f].h = faceSize;
+			faces[f].layout = src.layout;
+			faces[f].format = src.format;
+			faces[f].data.resize(face_bytes);
+		}
 
-		// work units: (face, row band); bands sized so every device gets several units
-		std::vector<int> devs = devices.empty() ? std::vector<int>{-1} : devices;
-		const unsigned bands = devs.size() > 1 ? 4u : 1u;
-		struct Unit {
-			unsigned face, r0, r1;
-		};
-		std::vector<Unit> units;
-		for(unsigned f = 0; f < 6; ++f)
-			for(unsigned b = 0; b < bands; ++b) {
+		// (face, row band) work units dealt round-robin, band-major, so with several devices each one gets
+		// a mix of polar and side faces.  Each device thread uploads the union of the source-row windows
+		// its units read ONCE, resamples all its units in one launch, and reads back only its own rows.
+		const std::vector<int> devs = devices.empty() ? std::vector<int>{-1} : devices;
+		unsigned bands = 1;
+		while((6 * bands) % devs.size() != 0 && bands < 64) ++bands;
+		std::vector<cacao_cube_unit> units;
+		for(unsigned b = 0; b < bands; ++b)
+			for(unsigned f = 0; f < 6; ++f) {
 				const unsigned r0 = static_cast<unsigned>(static_cast<uint64_t>(faceSize) * b / bands);
 				const unsigned r1 = static_cast<unsigned>(static_cast<uint64_t>(faceSize) * (b + 1) / bands);
 				if(r1 > r0) units.push_back({f, r0, r1});
 			}
 		std::vector<std::string> errors(devs.size());
 		auto worker = [&](std::size_t k) {
-			for(std::size_t u = k; u < units.size(); u += devs.size()) {
-				const Unit& un = units[u];
-				const int rc = cacao_img_equirect_to_cube(devs[k], src.data.data(), src.w, src.h, 0, src.h, static_cast<int>(src.layout), static_cast<int>(src.format), cube.data(), faceSize, 1u << un.face, un.r0, un.r1, CACAO_MEM_HOST, nullptr);
-				if(rc != CACAO_OK) {
-					errors[k] = cacao_img_last_error();
-					return;
-				}
+			auto fail_if = [&](int rc) {
+				if(rc != CACAO_OK && errors[k].empty()) errors[k] = cacao_img_last_error();
+				return rc != CACAO_OK;
+			};
+			std::vector<cacao_cube_unit> mine;
+			for(std::size_t u = k; u < units.size(); u += devs.size()) mine.push_back(units[u]);
+			if(mine.empty()) return;
+			uint32_t lo = UINT32_MAX, hi = 0;
+			for(const auto& un : mine) {
+				uint32_t w0 = 0, wn = 0;
+				if(fail_if(cacao_img_equirect_src_window(src.w, src.h, faceSize, 1u << un.face, un.row_begin, un.row_end, &w0, &wn))) return;
+				lo = std::min(lo, w0);
+				hi = std::max(hi, w0 + wn);
 			}
+			const std::size_t pitch = static_cast<std::size_t>(src.w) * bpp;
+			void *dsrc = nullptr, *dcube = nullptr;
+			if(fail_if(cacao_img_malloc(devs[k], &dsrc, static_cast<uint64_t>(hi - lo) * pitch))) return;
+			if(!fail_if(cacao_img_malloc(devs[k], &dcube, 6 * face_bytes))) {
+				bool bad = fail_if(cacao_img_upload(devs[k], dsrc, src.data.data() + static_cast<std::size_t>(lo) * pitch, static_cast<uint64_t>(hi - lo) * pitch, nullptr));
+				bad = bad || fail_if(cacao_img_equirect_to_cube_units(devs[k], dsrc, src.w, src.h, lo, hi - lo, static_cast<int>(src.layout), static_cast<int>(src.format), dcube, faceSize, mine.data(), static_cast<uint32_t>(mine.size()), nullptr));
+				for(const auto& un : mine) {
+					if(bad) break;
+					const std::size_t in_face = static_cast<std::size_t>(un.row_begin) * faceSize * bpp;
+					bad = fail_if(cacao_img_download(devs[k], faces[un.face].data.data() + in_face, static_cast<unsigned char*>(dcube) + un.face * face_bytes + in_face, static_cast<uint64_t>(un.row_end - un.row_begin) * faceSize * bpp, nullptr));
+				}
+				if(!bad) fail_if(cacao_img_sync(devs[k], nullptr));
+				cacao_img_free(devs[k], dcube);
+			}
+			cacao_img_free(devs[k], dsrc);
 		};
 		if(devs.size() == 1) {
-			// single device: all six faces in one launch
-			check(cacao_img_equirect_to_cube(devs[0], src.data.data(), src.w, src.h, 0, src.h, static_cast<int>(src.layout), static_cast<int>(src.format), cube.data(), faceSize, 0x3F, 0, faceSize, CACAO_MEM_HOST, nullptr));
+			worker(0);
 		} else {
 			std::vector<std::thread> pool;
 			for(std::size_t k = 0; k < devs.size(); ++k) pool.emplace_back(worker, k);
 			for(auto& t : pool) t.join();
-			for(const auto& e : errors)
-				if(!e.empty()) throw std::runtime_error("libcacaoimage-b200: " + e);
 		}
-		std::array<ImageEx, 6> faces;
-		for(unsigned f = 0; f < 6; ++f) {
-			faces[f].w = faces[f].h = faceSize;
-			faces[f].layout = src.layout;
-			faces[f].format = src.format;
-			faces[f].data.assign(cube.begin() + f * face_bytes, cube.begin() + (f + 1) * face_bytes);
-		}
+		for(const auto& e : errors)
+			if(!e.empty()) throw std::runtime_error("libcacaoimage-b200: " + e);
 		return faces;
 	}
 }

@@ -76,6 +76,9 @@ int cacao_img_malloc(int device, void** dev_ptr, uint64_t bytes);
 int cacao_img_free(int device, void* dev_ptr);
 int cacao_img_host_alloc(void** host_ptr, uint64_t bytes); /* pinned, portable across devices */
 int cacao_img_host_free(void* host_ptr);
+/* Copies are enqueued on `stream` and asynchronous for pinned host memory.  Pageable host memory
+ * (>= 1 MiB) is staged through the library's pinned ring by its host copy threads and the call
+ * returns when the bytes have landed. */
 int cacao_img_upload(int device, void* dst_dev, const void* src_host, uint64_t bytes, void* stream);
 int cacao_img_download(int device, void* dst_host, const void* src_dev, uint64_t bytes, void* stream);
 int cacao_img_sync(int device, void* stream); /* stream == NULL: whole device */
