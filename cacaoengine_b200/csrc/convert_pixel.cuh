@@ -1,7 +1,7 @@
 // convert_pixel.cuh -- the per-pixel arithmetic of the fused layout + sample-format conversion.
 //
-// One place defines what a converted pixel is; the tiled vector kernel (convert_tiles.cuh) and the
-// scalar edge kernel (convert_scalar.cu) both call it.
+// One place defines what a converted pixel is; the two vector kernels (convert_tiles.cuh,
+// convert_wide.cuh) and the byte-wise edge kernel (convert_dispatch.cuh) all call it.
 //
 // Reference semantics reproduced here (paths relative to /root/reference/):
 //   ->Gray (int)   trunc(0.2126*r)+trunc(0.7152*g)+trunc(0.0722*b), double products truncated

@@ -27,3 +27,17 @@ w = h = 4096
 img = ce.Image(w, h, ce.Layout.RGBA, 16, np.random.default_rng(0).integers(0, 256, w * h * 8).astype(np.uint8))
 bench("Image API: 4096^2 RGBA16 -> Convert16To8BitColor", lambda: ce.Convert16To8BitColor(img), w * h)
 bench("Image API: 4096^2 RGBA16 -> ToRGB8 (fused)", lambda: ce.ToRGB8(img), w * h)
+# flip throughput, device resident
+import torch
+for (w, h, bpp) in ((4096, 4096, 4), (8192, 8192, 16)):
+	n = w * h * bpp
+	a = torch.empty(n, dtype=torch.uint8, device="cuda"); b = torch.empty(n, dtype=torch.uint8, device="cuda")
+	s = torch.cuda.current_stream().cuda_stream
+	for _ in range(3): device.flip_rows(a.data_ptr(), b.data_ptr(), w, h, bpp, stream=s)
+	torch.cuda.synchronize()
+	e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	e0.record()
+	for _ in range(10): device.flip_rows(a.data_ptr(), b.data_ptr(), w, h, bpp, stream=s)
+	e1.record(); torch.cuda.synchronize()
+	ms = e0.elapsed_time(e1) / 10
+	print(f"flip {w}x{h}x{bpp}B: {ms:.4f} ms  {2*n/ms/1e6:.0f} GB/s", flush=True)
