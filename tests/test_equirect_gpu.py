@@ -206,3 +206,26 @@ def test_cfg3_shape_band_sample(oracle):
 	assert device.checksum(cube2.ptr, 6 * N * N * 16) == whole
 	for x in (src, cube, cube2):
 		x.free()
+
+
+def test_source_beyond_4_gib_matches_windowed_run():
+	"""A 32768x16384 RGBA32F panorama is 8 GiB: byte offsets exceed 2^32 while pixel indices still fit
+	32 bits.  A band resampled from the full buffer must equal the same band resampled from just its
+	planned source-row window (different base addresses, same pixels)."""
+	from cacaoengine_b200 import _capi as c, device
+
+	W, H, N, ch, fmt = 32768, 16384, 1024, 4, c.FMT_F32
+	full = DevBuf(W * H * 16)
+	device.synth(full.ptr, W * H * 4, fmt, 4, 77)
+	cube_a, cube_b = DevBuf(6 * N * N * 16), DevBuf(6 * N * N * 16)
+	for f, (r0, r1) in ((3, (0, 256)), (0, (700, 1024)), (5, (512, 640))):  # -Y reaches the last source rows
+		w0, wn = device.equirect_src_window(W, H, N, 1 << f, r0, r1)
+		device.equirect_to_cube(full.ptr, W, H, ch, fmt, cube_a.ptr, N, 1 << f, r0, r1)
+		win = DevBuf(wn * W * 16)
+		device.synth(win.ptr, wn * W * 4, fmt, 4, 77, first_sample=w0 * W * 4)
+		device.equirect_to_cube(win.ptr, W, H, ch, fmt, cube_b.ptr, N, 1 << f, r0, r1, src_row0=w0, src_rows=wn)
+		off, n = (f * N + r0) * N * 16, (r1 - r0) * N * 16
+		assert device.checksum(cube_a.ptr + off, n) == device.checksum(cube_b.ptr + off, n), (f, r0, r1)
+		win.free()
+	for b in (full, cube_a, cube_b):
+		b.free()
