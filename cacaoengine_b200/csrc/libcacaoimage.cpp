@@ -138,6 +138,44 @@ namespace libcacaoimage {
 		return out;
 	}
 
+	std::vector<ImageEx> ConvertBatch(const std::vector<ImageEx>& srcs, Image::Layout layout, SampleFormat format, ConvertMode mode, const std::vector<int>& devices) {
+		std::vector<ImageEx> out(srcs.size());
+		for(std::size_t i = 0; i < srcs.size(); ++i) {
+			if(srcs[i].layout == layout && srcs[i].format == format) check(CACAO_E_SAME_LAYOUT);
+			out[i].w = srcs[i].w;
+			out[i].h = srcs[i].h;
+			out[i].layout = layout;
+			out[i].format = format;
+			out[i].data.resize(static_cast<std::size_t>(srcs[i].w) * srcs[i].h * BytesPerPixel(layout, format));
+		}
+		const std::vector<int> devs = devices.empty() ? std::vector<int>{-1} : devices;
+		std::vector<std::string> errors(devs.size());
+		auto worker = [&](std::size_t k) {
+			// contiguous, balanced index range of device k
+			const std::size_t base = srcs.size() / devs.size(), extra = srcs.size() % devs.size();
+			const std::size_t lo = k * base + std::min(k, extra), hi = lo + base + (k < extra ? 1 : 0);
+			for(std::size_t i = lo; i < hi; ++i) {
+				const uint64_t pixels = static_cast<uint64_t>(srcs[i].w) * srcs[i].h;
+				if(pixels == 0) continue;
+				const int rc = cacao_img_convert(devs[k], srcs[i].data.data(), out[i].data.data(), pixels, static_cast<int>(srcs[i].layout), static_cast<int>(layout), static_cast<int>(srcs[i].format), static_cast<int>(format), static_cast<int>(mode), CACAO_MEM_HOST, nullptr);
+				if(rc != CACAO_OK) {
+					errors[k] = cacao_img_last_error();
+					return;
+				}
+			}
+		};
+		if(devs.size() == 1) {
+			worker(0);
+		} else {
+			std::vector<std::thread> pool;
+			for(std::size_t k = 0; k < devs.size(); ++k) pool.emplace_back(worker, k);
+			for(auto& t : pool) t.join();
+		}
+		for(const auto& e : errors)
+			if(!e.empty()) throw std::runtime_error("libcacaoimage-b200: " + e);
+		return out;
+	}
+
 	Image ToRGB8(const Image& src) {
 		if(src.bitsPerChannel == 8 && src.layout == Image::Layout::RGB) return src;
 		Image out = {};

@@ -32,6 +32,11 @@ namespace libcacaoimage {
 	// Fused layout + format conversion in one pass over the pixels (one upload, one kernel, one readback).
 	ImageEx Convert(const ImageEx& src, Image::Layout layout, SampleFormat format, ConvertMode mode = ConvertMode::ReferenceExact);
 
+	// The same conversion for a batch of images, sharded by contiguous image-index range over `devices`
+	// (CUDA ordinals; empty = current device), one host thread per device, no cross-device traffic.
+	// Images may differ in size and source layout/format.
+	std::vector<ImageEx> ConvertBatch(const std::vector<ImageEx>& srcs, Image::Layout layout, SampleFormat format, ConvertMode mode = ConvertMode::ReferenceExact, const std::vector<int>& devices = {});
+
 	// What engine/src/core/Cubemap.cpp:28-31 does per face in two passes and two allocations
 	// (Convert16To8BitColor, then ChangeChannelLayout to RGB), as one kernel.
 	Image ToRGB8(const Image& src);

@@ -2,6 +2,7 @@
 // engine/src/core/Cubemap.cpp:20-32 and Tex2D.cpp:18 use it, against the known-answer vectors
 // extracted from the compiled reference.  Built and run by tests/test_cpp_api.py.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -55,7 +56,8 @@ static std::string thrown(F f) {
 	return "";
 }
 
-int main() {
+int main(int argc, char** argv) {
+	const int n_devices = argc > 1 ? std::atoi(argv[1]) : 1;
 	static_assert(sizeof(Image) == 56, "Image layout must match the reference (libstdc++ x86-64)");
 	using L = Image::Layout;
 	// ---- ChangeChannelLayout, 8 bit
@@ -105,6 +107,26 @@ int main() {
 	const float* fp = reinterpret_cast<const float*>(f32.data.data());
 	EXPECT(f32.data.size() == 3 * 4 * 4 && fp[0] == 1.0f && fp[3] == 1.0f && fp[4] == 1.0f / 255.0f && fp[9] == 100.0f / 255.0f);
 	EXPECT(ToImage(Convert(f32, L::RGB, SampleFormat::U8)).data == rgb8.data); // round trip
+	// batch conversion over however many devices argv says (default 1): results independent of the split
+	{
+		std::vector<ImageEx> batch(5);
+		for(std::size_t k = 0; k < batch.size(); ++k) {
+			batch[k].w = 64 + 3 * static_cast<unsigned>(k);
+			batch[k].h = 17;
+			batch[k].layout = L::RGB;
+			batch[k].format = SampleFormat::U8;
+			batch[k].data.resize(static_cast<std::size_t>(batch[k].w) * 17 * 3);
+			for(std::size_t b = 0; b < batch[k].data.size(); ++b) batch[k].data[b] = static_cast<unsigned char>((b * 7 + k * 13) & 0xFF);
+		}
+		std::vector<int> devs;
+		for(int d = 0; d < n_devices; ++d) devs.push_back(d);
+		const auto one = ConvertBatch(batch, L::RGBA, SampleFormat::U8);
+		const auto many = ConvertBatch(batch, L::RGBA, SampleFormat::U8, ConvertMode::ReferenceExact, devs);
+		for(std::size_t k = 0; k < batch.size(); ++k) {
+			EXPECT(one[k].data == many[k].data && one[k].data.size() == static_cast<std::size_t>(batch[k].w) * 17 * 4);
+			EXPECT(one[k].data[0] == batch[k].data[0] && one[k].data[3] == 255 && one[k].data[4] == batch[k].data[3]);
+		}
+	}
 	ImageEx pano;
 	pano.w = 64;
 	pano.h = 32;

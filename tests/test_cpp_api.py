@@ -30,6 +30,8 @@ def test_cpp_api_compiles_and_links(tmp_path, built_lib):
 @pytest.mark.gpu
 def test_cpp_api_known_answers(tmp_path, built_lib):
 	exe = _compile(tmp_path, built_lib)
-	r = subprocess.run([str(exe)], capture_output=True, text=True)
+	from cacaoengine_b200 import device
+
+	r = subprocess.run([str(exe), str(min(device.device_count(), 8))], capture_output=True, text=True)
 	assert r.returncode == 0, r.stdout + r.stderr
 	assert "cpp api ok" in r.stdout
