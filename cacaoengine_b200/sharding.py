@@ -53,18 +53,46 @@ def cube_units(face_size: int, bands_per_face: int) -> list[CubeUnit]:
 
 
 def bands_for_world(world: int) -> int:
-	"""Smallest band count whose 6*bands units deal out evenly over `world` ranks."""
-	for bands in range(1, 65):
-		if (6 * bands) % world == 0:
-			return bands
-	return world
+	"""Bands per face: at least 8 units per rank's worth of granularity so the cost-aware dealing
+	below can even out the polar faces (48 units for 8 ranks), never fewer than 1."""
+	if world <= 1:
+		return 1
+	bands = 1
+	while 6 * bands < 6 * world:
+		bands *= 2
+	return bands
+
+
+def unit_cost(u: CubeUnit, face_size: int) -> float:
+	"""Relative cost of a unit.  Measured on B200 (dev/unit_costs.py, 16384x8192 -> 4096^2): every
+	side-face row costs the same; rows of the +-Y faces cost 1.1x at the face edge rising to 2.2x at the
+	centre, where neighbouring pixels fan out over all longitudes and taps stop coalescing."""
+	if u.face not in (2, 3):
+		return float(u.rows)
+	total = 0.0
+	for r in range(u.row_begin, u.row_end):
+		d = abs((2 * r + 1) / face_size - 1.0)  # 0 at the centre row, 1 at the edge
+		total += 1.1 + 1.1 * (1.0 - d) ** 2
+	return total
 
 
 def units_for_rank(rank: int, world: int, face_size: int, bands_per_face: int | None = None) -> list[CubeUnit]:
+	"""Cost-balanced dealing (longest-processing-time first): units sorted by estimated cost, each
+	handed to the currently least-loaded rank.  Deterministic, so every rank computes the same plan
+	without talking to the others."""
 	if not (0 <= rank < world):
 		raise ValueError(f"rank {rank} outside world of {world}")
 	bands = bands_for_world(world) if bands_per_face is None else bands_per_face
-	return cube_units(face_size, bands)[rank::world]
+	units = cube_units(face_size, bands)
+	order = sorted(range(len(units)), key=lambda k: (-unit_cost(units[k], face_size), k))
+	load = [0.0] * world
+	mine = []
+	for k in order:
+		r = min(range(world), key=lambda q: (load[q], q))
+		load[r] += unit_cost(units[k], face_size)
+		if r == rank:
+			mine.append(units[k])
+	return sorted(mine, key=lambda u: (u.face, u.row_begin))
 
 
 def source_window(units: list[CubeUnit], W: int, H: int, face_size: int) -> tuple[int, int]:
