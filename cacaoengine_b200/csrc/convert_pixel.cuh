@@ -17,19 +17,22 @@
 namespace cacao {
 
 	// trunc(c * (double)x) for the three BT.709 weights, x <= 65535, without touching the FP64 pipe
-	// on the common path.  (x*num)/10000 equals the reference's double product truncated for every
+	// on the common path.  floor(x*num/10000) equals the reference's truncated double product for every
 	// x in [0,65535] for 0.2126 and 0.0722; for 0.7152 = 447/625 the double product of a multiple of
 	// 625 can land one ulp under the exact integer, so those inputs (1 in 625) take the reference's
-	// own double multiply.  tests/test_convert_gpu.py checks all 3 x 65536 inputs against the oracle.
+	// own double multiply.  floor(x*num/10000) itself is one IMAD.HI: mulhi(x, ceil(num*2^32/10000))
+	// is exact for x < 2^16 (the rounding-up of the constant adds < 2^-16, the nearest miss is 10^-4).
+	// tests/test_convert_gpu.py checks all 3 x 65536 inputs on the device against the compiled
+	// reference's outputs; tests/test_oracle.py checks the constants on the host.
 	__device__ __forceinline__ uint32_t trunc_2126(uint32_t x) {
-		return (x * 2126u) / 10000u;
+		return __umulhi(x, 913110048u); // ceil(2126 * 2^32 / 10000)
 	}
 	__device__ __forceinline__ uint32_t trunc_0722(uint32_t x) {
-		return (x * 722u) / 10000u;
+		return __umulhi(x, 310096639u); // ceil(722 * 2^32 / 10000)
 	}
 	template<bool Wide>
 	__device__ __forceinline__ uint32_t trunc_7152(uint32_t x) {
-		uint32_t t = (x * 7152u) / 10000u;
+		uint32_t t = __umulhi(x, 3071760611u); // ceil(7152 * 2^32 / 10000)
 		if constexpr(Wide) {
 			if(x % 625u == 0u) t = static_cast<uint32_t>(0.7152 * static_cast<double>(x));
 		}
