@@ -470,6 +470,9 @@ namespace {
 			if(rc) return rc;
 		}
 		const uint64_t chunks = (pixels + chunk_px - 1) / chunk_px;
+		// a single chunk has nothing to overlap with: keep its three steps on one stream and save the
+		// cross-stream event hops (tens of microseconds matter for a 64x64 texture)
+		cudaStream_t q_in = chunks == 1 ? c->s_run : c->s_in, q_out = chunks == 1 ? c->s_run : c->s_out;
 		for(uint64_t k = 0; k < chunks + (kSlots - 1); ++k) {
 			if(k < chunks) {
 				const int s = static_cast<int>(k % kSlots);
@@ -482,17 +485,17 @@ namespace {
 					up_from = c->pin_in[s];
 				}
 				// the device slot is free once its previous readback has finished
-				if(k >= kSlots) CU_TRY(cudaStreamWaitEvent(c->s_in, c->ev_out[s], 0));
-				CU_TRY(cudaMemcpyAsync(c->stage_in[s], up_from, n * sbpp, cudaMemcpyHostToDevice, c->s_in));
-				CU_TRY(cudaEventRecord(c->ev_in[s], c->s_in));
-				CU_TRY(cudaStreamWaitEvent(c->s_run, c->ev_in[s], 0));
+				if(k >= kSlots) CU_TRY(cudaStreamWaitEvent(q_in, c->ev_out[s], 0));
+				CU_TRY(cudaMemcpyAsync(c->stage_in[s], up_from, n * sbpp, cudaMemcpyHostToDevice, q_in));
+				CU_TRY(cudaEventRecord(c->ev_in[s], q_in));
+				if(chunks > 1) CU_TRY(cudaStreamWaitEvent(c->s_run, c->ev_in[s], 0));
 				if(k >= kSlots) CU_TRY(cudaStreamWaitEvent(c->s_run, c->ev_out[s], 0));
 				rc = enqueue_convert(c, c->stage_in[s], c->stage_out[s], n, quirk ? ppi : n, src_ch, dst_ch, src_fmt, dst_fmt, mode, c->s_run);
 				if(rc) return rc;
 				CU_TRY(cudaEventRecord(c->ev_run[s], c->s_run));
-				CU_TRY(cudaStreamWaitEvent(c->s_out, c->ev_run[s], 0));
-				CU_TRY(cudaMemcpyAsync(dst_pg ? c->pin_out[s] : dst + off * dbpp, c->stage_out[s], n * dbpp, cudaMemcpyDeviceToHost, c->s_out));
-				CU_TRY(cudaEventRecord(c->ev_out[s], c->s_out));
+				if(chunks > 1) CU_TRY(cudaStreamWaitEvent(c->s_out, c->ev_run[s], 0));
+				CU_TRY(cudaMemcpyAsync(dst_pg ? c->pin_out[s] : dst + off * dbpp, c->stage_out[s], n * dbpp, cudaMemcpyDeviceToHost, q_out));
+				CU_TRY(cudaEventRecord(c->ev_out[s], q_out));
 			}
 			// drain the chunk issued kSlots-1 iterations ago (its slot is the next one to be reused)
 			if(dst_pg && k >= static_cast<uint64_t>(kSlots - 1)) {
@@ -506,7 +509,7 @@ namespace {
 				}
 			}
 		}
-		CU_TRY(cudaStreamSynchronize(c->s_out));
+		CU_TRY(cudaStreamSynchronize(q_out));
 		return CACAO_OK;
 	}
 
