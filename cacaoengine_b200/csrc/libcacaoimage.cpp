@@ -70,6 +70,9 @@ namespace libcacaoimage {
 		out.lossy = src.lossy;
 		const int fmt = fmt_of_bits(src.bitsPerChannel);
 		const uint64_t pixels = static_cast<uint64_t>(src.w) * src.h;
+		// the reference walks w*h pixels whatever the buffer holds (Layout.cpp:20,31) and would read past
+		// a short one; that is the one place this wrapper is stricter
+		if(src.data.size() < pixels * static_cast<int>(src.layout) * bytes_of(fmt)) throw std::runtime_error("Image data buffer is smaller than w * h * channels * bytes per channel!");
 		out.data.resize(pixels * static_cast<int>(layout) * bytes_of(fmt));
 		if(pixels) check(cacao_img_convert(-1, src.data.data(), out.data.data(), pixels, static_cast<int>(src.layout), static_cast<int>(layout), fmt, fmt, CACAO_MODE_REF_EXACT, CACAO_MEM_HOST, nullptr));
 		return out;
@@ -91,6 +94,7 @@ namespace libcacaoimage {
 		out.lossy = src.lossy;
 		out.data.resize(src.data.size());
 		const uint32_t bpp = static_cast<uint32_t>(src.layout) * (src.bitsPerChannel / 8);
+		if(src.data.size() < static_cast<std::size_t>(src.w) * src.h * bpp) throw std::runtime_error("Image data buffer is smaller than w * h * channels * bytes per channel!");
 		check(cacao_img_flip_rows(-1, src.data.data(), out.data.data(), src.w, src.h, bpp, CACAO_MEM_HOST, nullptr));
 		return out;
 	}
@@ -132,8 +136,9 @@ namespace libcacaoimage {
 		out.layout = layout;
 		out.format = format;
 		const uint64_t pixels = static_cast<uint64_t>(src.w) * src.h;
-		out.data.resize(pixels * BytesPerPixel(layout, format));
 		if(src.layout == layout && src.format == format) check(CACAO_E_SAME_LAYOUT);
+		if(src.data.size() < pixels * BytesPerPixel(src.layout, src.format)) throw std::runtime_error("Image data buffer is smaller than w * h * channels * bytes per channel!");
+		out.data.resize(pixels * BytesPerPixel(layout, format));
 		if(pixels) check(cacao_img_convert(-1, src.data.data(), out.data.data(), pixels, static_cast<int>(src.layout), static_cast<int>(layout), static_cast<int>(src.format), static_cast<int>(format), static_cast<int>(mode), CACAO_MEM_HOST, nullptr));
 		return out;
 	}
@@ -142,6 +147,7 @@ namespace libcacaoimage {
 		std::vector<ImageEx> out(srcs.size());
 		for(std::size_t i = 0; i < srcs.size(); ++i) {
 			if(srcs[i].layout == layout && srcs[i].format == format) check(CACAO_E_SAME_LAYOUT);
+			if(srcs[i].data.size() < static_cast<std::size_t>(srcs[i].w) * srcs[i].h * BytesPerPixel(srcs[i].layout, srcs[i].format)) throw std::runtime_error("Image data buffer is smaller than w * h * channels * bytes per channel!");
 			out[i].w = srcs[i].w;
 			out[i].h = srcs[i].h;
 			out[i].layout = layout;
@@ -187,6 +193,7 @@ namespace libcacaoimage {
 		out.quality = src.quality;
 		out.lossy = src.lossy;
 		const uint64_t pixels = static_cast<uint64_t>(src.w) * src.h;
+		if(src.data.size() < pixels * static_cast<int>(src.layout) * (src.bitsPerChannel / 8)) throw std::runtime_error("Image data buffer is smaller than w * h * channels * bytes per channel!");
 		out.data.resize(pixels * 3);
 		if(pixels) check(cacao_img_convert(-1, src.data.data(), out.data.data(), pixels, static_cast<int>(src.layout), 3, fmt_of_bits(src.bitsPerChannel), CACAO_FMT_U8, CACAO_MODE_REF_EXACT, CACAO_MEM_HOST, nullptr));
 		return out;

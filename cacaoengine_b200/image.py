@@ -50,6 +50,16 @@ def _bytes(a: np.ndarray) -> np.ndarray:
 	return np.ascontiguousarray(a).view(np.uint8).reshape(-1)
 
 
+SHORT_BUFFER = "Image data buffer is smaller than w * h * channels * bytes per channel!"
+
+
+def _need(buf: np.ndarray, nbytes: int) -> None:
+	# the reference walks w*h pixels whatever the buffer holds (Layout.cpp:20,31); a short buffer is an
+	# error here instead of an out-of-bounds read
+	if buf.size < nbytes:
+		raise RuntimeError(SHORT_BUFFER)
+
+
 def _raise_ref(status: int) -> None:
 	# the reference's std::runtime_error texts (cacao_img_status_string carries them verbatim)
 	raise RuntimeError(capi.lib().cacao_img_status_string(status).decode())
@@ -73,6 +83,7 @@ def ChangeChannelLayout(src: Image, layout: Layout) -> Image:
 	fmt = capi.FMT_U16 if src.bitsPerChannel == 16 else capi.FMT_U8
 	s = _bytes(src.data)
 	pixels = src.w * src.h
+	_need(s, pixels * int(src.layout) * capi.FMT_BYTES[fmt])
 	out = np.empty(pixels * int(layout) * capi.FMT_BYTES[fmt], np.uint8)
 	if pixels:
 		capi.check(capi.lib().cacao_img_convert(-1, s.ctypes.data, out.ctypes.data, pixels, int(src.layout), int(layout), fmt, fmt, capi.MODE_REF_EXACT, capi.MEM_HOST, None))
@@ -94,6 +105,7 @@ def Flip(src):
 		_raise_ref(capi.E_EMPTY)
 	if src.h == 1:  # Flip.cpp:13
 		return replace(src, data=s.copy())
+	_need(s, src.w * src.h * bpp)
 	out = np.empty_like(s)
 	capi.check(capi.lib().cacao_img_flip_rows(-1, s.ctypes.data, out.ctypes.data, src.w, src.h, bpp, capi.MEM_HOST, None))
 	return replace(src, data=out)
@@ -103,6 +115,7 @@ def Convert(src: ImageEx, layout: Layout, fmt: int, mode: int = capi.MODE_REF_EX
 	"""Fused layout + sample-format conversion (DESIGN.md Spec B.1)."""
 	s = _bytes(src.data)
 	pixels = src.w * src.h
+	_need(s, pixels * int(src.layout) * capi.FMT_BYTES[src.format])
 	out = np.empty(pixels * int(layout) * capi.FMT_BYTES[fmt], np.uint8)
 	capi.check(capi.lib().cacao_img_convert(-1, s.ctypes.data, out.ctypes.data, pixels, int(src.layout), int(layout), src.format, fmt, mode, capi.MEM_HOST, None))
 	return ImageEx(src.w, src.h, Layout(layout), fmt, out)
@@ -115,6 +128,7 @@ def ToRGB8(src: Image) -> Image:
 	fmt = capi.FMT_U16 if src.bitsPerChannel == 16 else capi.FMT_U8
 	s = _bytes(src.data)
 	pixels = src.w * src.h
+	_need(s, pixels * int(src.layout) * capi.FMT_BYTES[fmt])
 	out = np.empty(pixels * 3, np.uint8)
 	if pixels:
 		capi.check(capi.lib().cacao_img_convert(-1, s.ctypes.data, out.ctypes.data, pixels, int(src.layout), 3, fmt, capi.FMT_U8, capi.MODE_REF_EXACT, capi.MEM_HOST, None))
@@ -125,6 +139,7 @@ def EquirectToCubemap(src: ImageEx, face_size: int, face_mask: int = 0x3F, row_b
 	"""Equirect -> cube buffer (6*N*N pixels, faces +X,-X,+Y,-Y,+Z,-Z); only the selected rows are written."""
 	s = _bytes(src.data)
 	bpp = int(src.layout) * capi.FMT_BYTES[src.format]
+	_need(s, src.w * src.h * bpp)
 	out = np.zeros(6 * face_size * face_size * bpp, np.uint8)
 	capi.check(capi.lib().cacao_img_equirect_to_cube(device, s.ctypes.data, src.w, src.h, 0, src.h, int(src.layout), src.format, out.ctypes.data, face_size, face_mask, row_begin, face_size if row_end is None else row_end, capi.MEM_HOST, None))
 	return out.view(_NP_OF_FMT[src.format])

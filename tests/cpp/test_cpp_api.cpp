@@ -97,6 +97,9 @@ int main(int argc, char** argv) {
 	bad.bitsPerChannel = 12;
 	EXPECT(thrown([&] { Flip(bad); }) == "Invalid color depth; only 8 and 16 are allowed.");
 	EXPECT(thrown([&] { Flip(make8(1, 2, L::RGB, {})); }) == "Cannot flip an image with a zero-sized data buffer!");
+	// ---- empty and ragged images
+	EXPECT(ChangeChannelLayout(make8(0, 0, L::RGBA, {}), L::RGB).data.empty());
+	EXPECT(thrown([&] { ChangeChannelLayout(make8(4, 4, L::RGB, std::vector<unsigned char>(47)), L::RGBA); }) == "Image data buffer is smaller than w * h * channels * bytes per channel!");
 	// ---- Flip: intended semantics, source untouched
 	const Image two = make8(2, 3, L::Grayscale, {1, 2, 3, 4, 5, 6});
 	EXPECT(Flip(two).data == (std::vector<unsigned char>{5, 6, 3, 4, 1, 2}) && two.data[0] == 1);

@@ -105,6 +105,26 @@ def test_python_mirror_raises_reference_messages(built_lib):
 		ce.Flip(ce.Image(0, 2, ce.Layout.RGB, 8, np.zeros(0, np.uint8)))
 
 
+def test_empty_and_ragged_images(built_lib):
+	"""Edge cases that need no device: a 0x0 image converts to an empty image (the reference loops zero
+	times, Layout.cpp:31); a buffer shorter than w*h*channels -- which the reference would read past --
+	is rejected before anything is launched."""
+	import cacaoengine_b200 as ce
+
+	empty = ce.Image(0, 0, ce.Layout.RGBA, 8, np.zeros(0, np.uint8))
+	out = ce.ChangeChannelLayout(empty, ce.Layout.RGB)
+	assert out.layout == ce.Layout.RGB and out.data.size == 0 and (out.w, out.h) == (0, 0)
+	out = ce.Convert16To8BitColor(ce.Image(0, 0, ce.Layout.RGB, 16, np.zeros(0, np.uint8)))
+	assert out.bitsPerChannel == 8 and out.data.size == 0
+	ragged = ce.Image(4, 4, ce.Layout.RGB, 8, np.zeros(4 * 4 * 3 - 1, np.uint8))
+	with pytest.raises(RuntimeError, match="smaller than w \\* h"):
+		ce.ChangeChannelLayout(ragged, ce.Layout.RGBA)
+	with pytest.raises(RuntimeError, match="smaller than w \\* h"):
+		ce.Flip(ragged)
+	with pytest.raises(RuntimeError, match="smaller than w \\* h"):
+		ce.EquirectToCubemap(ce.ImageEx(8, 4, ce.Layout.RGB, ce.FMT_F32, np.zeros(10, np.uint8)), 4)
+
+
 def test_no_cpu_fallback_without_a_device(built_lib):
 	"""On a box without CUDA the product must fail loudly, never compute on the CPU."""
 	from cacaoengine_b200 import _capi as c, device
