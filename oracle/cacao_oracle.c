@@ -16,6 +16,10 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#define ORC_X86 1
+#endif
 
 /* ------------------------------------------------------------------------------------------
  * a4: the 16->8 LUT.  Restates libs/image/LUTGen.cpp:8-28: everything in float32,
@@ -240,12 +244,56 @@ static uint32_t unorm_from_float(float x, uint32_t maxv) {
 	return (uint32_t)(c * (float)maxv + 0.5f);
 }
 
+/* Pure sample-format change unorm -> float (same channel count) is a flat sample stream; these
+ * typed loops compute exactly what the generic path below computes per sample --
+ * (float)v / (float)M in IEEE fp32, then RNE to binary16 where asked -- without its per-sample
+ * dispatch, so that the CPU baseline is a fair scalar loop in the style of the reference's own
+ * (Layout.cpp:31-62) rather than an interpreter.  The binary16 rounding uses the CPU's F16C unit
+ * when it has one (same IEEE round-to-nearest-even as orc_f32_to_f16; tests compare the two). */
+#ifdef ORC_X86
+__attribute__((target("f16c"))) static void u8_to_f16_hw(const uint8_t* s, uint16_t* d, uint64_t n) {
+	for(uint64_t k = 0; k < n; ++k) d[k] = _cvtss_sh((float)s[k] / 255.0f, _MM_FROUND_TO_NEAREST_INT);
+}
+__attribute__((target("f16c"))) static void u16_to_f16_hw(const uint16_t* s, uint16_t* d, uint64_t n) {
+	for(uint64_t k = 0; k < n; ++k) d[k] = _cvtss_sh((float)s[k] / 65535.0f, _MM_FROUND_TO_NEAREST_INT);
+}
+#endif
+static int unorm_to_float_flat(const uint8_t* src, uint8_t* dst, uint64_t n, int src_fmt, int dst_fmt) {
+	if(dst_fmt == ORC_F32) {
+		float* d = (float*)dst;
+		if(src_fmt == ORC_U8)
+			for(uint64_t k = 0; k < n; ++k) d[k] = (float)src[k] / 255.0f;
+		else
+			for(uint64_t k = 0; k < n; ++k) d[k] = (float)((const uint16_t*)src)[k] / 65535.0f;
+		return 1;
+	}
+	uint16_t* d = (uint16_t*)dst;
+#ifdef ORC_X86
+	if(__builtin_cpu_supports("f16c")) {
+		if(src_fmt == ORC_U8)
+			u8_to_f16_hw(src, d, n);
+		else
+			u16_to_f16_hw((const uint16_t*)src, d, n);
+		return 1;
+	}
+#endif
+	if(src_fmt == ORC_U8)
+		for(uint64_t k = 0; k < n; ++k) d[k] = orc_f32_to_f16((float)src[k] / 255.0f);
+	else
+		for(uint64_t k = 0; k < n; ++k) d[k] = orc_f32_to_f16((float)((const uint16_t*)src)[k] / 65535.0f);
+	return 1;
+}
+
 static void convert_range(const uint8_t* src, uint8_t* dst, uint64_t p0, uint64_t p1, const uint8_t* px0,
 						  int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode) {
 	const int sb = fmt_bytes(src_fmt), db = fmt_bytes(dst_fmt);
 	const int src_int = (src_fmt == ORC_U8 || src_fmt == ORC_U16);
 	const int bits = (src_fmt == ORC_U8) ? 8 : 16;
 	const uint8_t* lut = orc_lut();
+	if(src_int && src_ch == dst_ch && (dst_fmt == ORC_F16 || dst_fmt == ORC_F32)) {
+		unorm_to_float_flat(src + p0 * (uint64_t)(src_ch * sb), dst + p0 * (uint64_t)(dst_ch * db), (p1 - p0) * (uint64_t)src_ch, src_fmt, dst_fmt);
+		return;
+	}
 	uint32_t first[4] = {0, 0, 0, 0};
 	if(src_int)
 		for(int c = 0; c < src_ch; ++c) first[c] = (uint32_t)load_as_float(px0 + (size_t)c * sb, src_fmt);

@@ -62,5 +62,5 @@ def test_gpu_arm_line(built_lib, oracle):
 	assert e2e["h2d_bytes_per_step"] == 1920 * 1080 * 4 * 256 and e2e["d2h_bytes_per_step"] == 1920 * 1080 * 8 * 256
 	assert 0 < e2e["value"] < d["value"] and e2e["readback_verified"] is True
 	cpu = d["cpu_baseline"]
-	assert cpu["kind"] == "port" and cpu["cores"] >= 1 and 0 < cpu["value"] < e2e["value"]
+	assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] > 0
 	assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
