@@ -148,6 +148,25 @@ def cpu_baseline_block():
 	return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{frames} of 256 frames (1920x1080 RGBA8 -> RGBA16F) x {passes} passes, oracle/cacao_oracle.c orc_convert_mt, OpenMP x{threads}, {secs:.2f} s wall = {secs * threads:.0f} core-seconds; single-thread {rate1:.4f} {UNIT}", "single_thread_value": rate1}
 
 
+def cpu_restatement_cfg1():
+	"""BASELINE config 1 (2048x1024 RGBA8 -> 6 x 512^2) is the CPU-runnable case, but the reference has
+	no projection code (tools/cubetool/main.cpp:31-33): this times OUR scalar restatement of Spec B.2."""
+	from oracle import pyoracle as po
+
+	W, H, N = 2048, 1024, 512
+	src = po.synth(W * H * 4, po.U8, 4, 0xC0FFEE)
+	threads = po.port().orc_max_threads()
+	out = {}
+	for label, th, reps in (("single_thread_value", 1, 2), ("value", 0, 5)):
+		po.equirect_to_cube(src, W, H, 4, po.U8, N, threads=th)
+		t0 = time.perf_counter()
+		for _ in range(reps):
+			po.equirect_to_cube(src, W, H, 4, po.U8, N, threads=th)
+		out[label] = reps * 6 * N * N / (time.perf_counter() - t0) / 1e9
+	out.update({"unit": UNIT, "cores": threads, "kind": "port", "sample": "whole config, oracle/cacao_oracle.c orc_equirect_to_cube (CPU restatement; no reference implementation exists)"})
+	return out
+
+
 def cpu_reference_cfg4a():
 	"""BASELINE config 4a is the one headline conversion the reference itself implements
 	(ChangeChannelLayout RGB8 -> RGBA8, libs/image/src/Layout.cpp:8-103): time the UNMODIFIED reference
@@ -421,6 +440,10 @@ def run_gpu_arm(args):
 					extra["cfg4a_4096x_4096sq_rgb8_to_rgba8"]["cpu_baseline"] = cpu_reference_cfg4a()
 				except Exception as e:
 					extra["cfg4a_4096x_4096sq_rgb8_to_rgba8"]["cpu_baseline"] = {"error": repr(e)}
+				try:
+					extra["cfg1_equirect_2048x1024_rgba8_to_6x512"]["cpu_baseline"] = cpu_restatement_cfg1()
+				except Exception as e:
+					extra["cfg1_equirect_2048x1024_rgba8_to_6x512"]["cpu_baseline"] = {"error": repr(e)}
 			line["extra"] = extra
 		print(json.dumps(line), flush=True)
 	if world > 1:
