@@ -413,12 +413,22 @@ namespace cacao {
 		prm.src_row0 = src_row0;
 		prm.src_rows = src_rows;
 		prm.pc = make_proj_const(N, W, H);
-		uint32_t next = 0;
+		uint32_t next = 0, split_from = 0;
 		while(next < n_units) {
 			prm.n_units = 0;
 			while(next < n_units && prm.n_units < kMaxUnitsPerLaunch) {
-				CubeUnit u = units[next++];
+				CubeUnit u = units[next];
 				if(u.row_end > N) u.row_end = N;
+				if(u.row_begin < split_from) u.row_begin = split_from;
+				// gridDim.y is limited to 65535 blocks of 8 rows: a taller unit continues in the next slot
+				constexpr uint32_t kMaxRows = 65535u * 8u;
+				if(u.face < 6 && u.row_begin < u.row_end && u.row_end - u.row_begin > kMaxRows) {
+					split_from = u.row_begin + kMaxRows;
+					u.row_end = split_from;
+				} else {
+					split_from = 0;
+					++next;
+				}
 				if(u.face < 6 && u.row_begin < u.row_end) prm.units[prm.n_units++] = u;
 			}
 			if(prm.n_units == 0) continue;
