@@ -203,7 +203,7 @@ namespace cacao {
 		//
 		// EXPERIMENT, off by default (CACAO_EQUIRECT_STAGED=1 turns it on; tests keep it bit-identical).
 		// The gather kernel above is bound by L1 data-pipe wavefronts (ncu: l1tex__data_pipe_lsu_wavefronts
-		// 76 %): every tap is a 16-byte-per-lane global load whose 8-lane groups straddle 128-byte lines.
+		// 76 %; dev/l1_align_bench.cu shows tap alignment is irrelevant, the excess passes are the miss path).
 		// Here one thread asks the TMA unit (cp.async.bulk, one row segment per copy) to place the
 		// block's source footprint -- the bounding box of all taps of its 32x8 pixels, one box per
 		// mirror side -- in shared memory; taps then are LDS.128, which has no line granularity.  A side
