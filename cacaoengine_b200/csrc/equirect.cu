@@ -155,7 +155,7 @@ namespace cacao {
 		// This halves the kernel's dominant cost -- instruction issue, not HBM (ncu: 74% issue-active,
 		// 50% DRAM before the change) -- and stays bit-identical to the per-pixel spec.
 		template<int F, int CH, typename IDX>
-		__global__ void __launch_bounds__(256, 8) equirect_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, EquirectParams prm) {
+		__global__ void __launch_bounds__(128, 16) equirect_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, EquirectParams prm) {
 			constexpr int bpp = FmtTraits<F>::bytes * CH;
 			const CubeUnit unit = prm.units[blockIdx.z];
 			const uint32_t i = blockIdx.x * 32u + threadIdx.x;
