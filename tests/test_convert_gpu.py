@@ -327,3 +327,17 @@ def test_buffers_beyond_4_gib():
 	assert same_bits(tail_out, tail_in.astype(np.float32) / np.float32(255))
 	for b in (src, dst, ref):
 		b.free()
+
+
+def test_randomised_sizes_and_batches(oracle):
+	"""Seeded sweep: random shape, pixel count (tile edges, tails), batch split, mode and memory kind."""
+	rng = np.random.default_rng(20261)
+	for case in range(60):
+		sf, df, sc, dc = SHAPES[int(rng.integers(0, len(SHAPES)))]
+		count = int(rng.choice([1, 1, 2, 5]))
+		ppi = int(rng.choice([1, 31, 32, 33, 511, 512, 513, 4096, 8191, 70001]))
+		mode = int(rng.integers(0, 2))
+		src = random_samples(rng, count * ppi * sc, sf)
+		want = np.concatenate([oracle.convert(src[k * ppi * sc:(k + 1) * ppi * sc], sc, dc, sf, df, mode) for k in range(count)])
+		got = convert_device(src, sc, dc, sf, df, mode, count=count) if case % 3 else convert_host(src, sc, dc, sf, df, mode, count=count)
+		assert same_bits(got, want), (case, sf, df, sc, dc, count, ppi, mode)
