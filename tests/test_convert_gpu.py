@@ -341,3 +341,29 @@ def test_randomised_sizes_and_batches(oracle):
 		want = np.concatenate([oracle.convert(src[k * ppi * sc:(k + 1) * ppi * sc], sc, dc, sf, df, mode) for k in range(count)])
 		got = convert_device(src, sc, dc, sf, df, mode, count=count) if case % 3 else convert_host(src, sc, dc, sf, df, mode, count=count)
 		assert same_bits(got, want), (case, sf, df, sc, dc, count, ppi, mode)
+
+
+def test_concurrent_callers(oracle):
+	"""The reference functions are re-entrant and called from arbitrary engine threads (thread-pool tasks,
+	the GL thread: OpenGLCubemap.cpp:13-25).  Eight threads hammer the host-memory and device-memory
+	entry points of one device at once (ctypes drops the GIL); every result must still be exact."""
+	from concurrent.futures import ThreadPoolExecutor
+
+	from cacaoengine_b200 import _capi as c
+
+	rng = np.random.default_rng(5)
+	jobs = []
+	for k in range(24):
+		sf, df, sc, dc = SHAPES[int(rng.integers(0, len(SHAPES)))]
+		px = int(rng.choice([100, 5000, 300000, 1500000]))
+		src = random_samples(rng, px * sc, sf)
+		jobs.append((k, src, sc, dc, sf, df, oracle.convert(src, sc, dc, sf, df, 1)))
+
+	def run(job):
+		k, src, sc, dc, sf, df, want = job
+		got = convert_host(src, sc, dc, sf, df, 1) if k % 2 else convert_device(src, sc, dc, sf, df, 1)
+		return same_bits(got, want)
+
+	with ThreadPoolExecutor(max_workers=8) as ex:
+		for rep in range(3):
+			assert all(ex.map(run, jobs))
