@@ -3,11 +3,11 @@
 // New functionality behind `ce-cubetool project`; the reference's cubetool only packs/unpacks six
 // ready-made faces (tools/cubetool/create.cpp:32-102, extract.cpp:50-101).
 //
-// One thread = one output pixel and its mirror image in the same row; a block covers a 32 x 8 patch
-// (and the mirrored patch) of one face, so the four bilinear taps of neighbouring threads fall on
-// the same or adjacent source lines (L1 absorbs the 4x tap overlap, L2 the reuse between
-// neighbouring patches, and HBM sees each source texel about once -- ncu: 0.52 GB read for a
-// 0.54 GB source).
+// One thread = one output pixel and its mirror images (column mirror always, row mirror too when the
+// launch covers whole faces); a warp covers an 8 x 4 pixel patch, a block 8 x 16, so the four
+// bilinear taps of neighbouring threads fall on the same or adjacent source lines (L1 absorbs the 4x
+// tap overlap, L2 the reuse between neighbouring patches, and HBM sees each source texel about once
+// -- ncu: 0.52 GB read for a 0.54 GB source).
 #include "equirect.cuh"
 
 #include <algorithm>
@@ -49,14 +49,22 @@ namespace cacao {
 			}
 		}
 
-		template<int F, int CH>
+		// Integer samples become floats without an I2F: one PRMT drops the byte (or 16-bit half) into
+		// the mantissa of 2^23, one exact subtraction removes the 2^23 again -- float(v) bit for bit,
+		// on the full-rate pipes instead of the quarter-rate conversion unit.
+		constexpr uint32_t kMagicBits = 0x4B000000u; // 8388608.0f
+		constexpr float kMagic = 8388608.0f;
+
+		// BIASED leaves the 2^23 in place for callers that remove it themselves (sample_and_store).
+		template<int F, int CH, bool BIASED = false>
 		__device__ __forceinline__ void words_to_floats(const uint32_t (&w)[4], float (&v)[CH]) {
+			constexpr float kOff = BIASED ? 0.0f : kMagic;
 #pragma unroll
 			for(int c = 0; c < CH; ++c) {
 				if constexpr(F == CACAO_FMT_U8)
-					v[c] = static_cast<float>((w[c >> 2] >> ((c & 3) * 8)) & 0xFFu);
+					v[c] = __uint_as_float(__byte_perm(w[c >> 2], kMagicBits, 0x7540u | static_cast<uint32_t>(c & 3))) - kOff;
 				else if constexpr(F == CACAO_FMT_U16)
-					v[c] = static_cast<float>((w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu);
+					v[c] = __uint_as_float(__byte_perm(w[c >> 1], kMagicBits, (c & 1) ? 0x7632u : 0x7610u)) - kOff;
 				else if constexpr(F == CACAO_FMT_F16)
 					v[c] = f16_bits_to_f32(static_cast<uint16_t>((w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu));
 				else
@@ -64,38 +72,105 @@ namespace cacao {
 			}
 		}
 
-		template<int F, int CH>
+		template<int F, int CH, bool BIASED = false>
 		__device__ __forceinline__ void load_texel(const uint8_t* __restrict__ p, float (&v)[CH]) {
 			uint32_t w[4] = {0, 0, 0, 0};
 			load_words<F, CH>(p, w);
-			words_to_floats<F, CH>(w, v);
+			words_to_floats<F, CH, BIASED>(w, v);
 		}
 
+		// Three-channel texels are 3 / 6 / 12 bytes: one texel is no power-of-two load, but the two
+		// taps of a row (x0 and x0+1 when the pair does not straddle the u = 0/1 seam) are 6 / 12 / 24
+		// CONTIGUOUS bytes.  load_pair3 fetches the 8-byte-aligned window around them with 64-bit loads
+		// and realigns in registers (word select + funnel shift) -- 2-4 load instructions per row instead
+		// of 6, and a third of the (request, line) pairs the L1 tag stage has to process, which is what
+		// bounds this kernel.  `elem` = texel index of the x0 tap in the source window.
+		template<int F, bool BIASED, typename IDX>
+		__device__ __forceinline__ void load_pair3(const uint8_t* __restrict__ src, IDX elem, float (&a)[3], float (&b)[3]) {
+			constexpr int sb = FmtTraits<F>::bytes;
+			const size_t off = static_cast<size_t>(elem) * (3 * sb);
+			const uint8_t* base = src + (off & ~static_cast<size_t>(7));
+			const uint32_t o = static_cast<uint32_t>(off) & 7u;
+			const bool e = (o & 4u) != 0;
+			if constexpr(sb == 4) {
+				// 24 bytes at a 4-byte-aligned offset: words q[e .. e+5] of the window
+				const uint2 q01 = __ldg(reinterpret_cast<const uint2*>(base));
+				const uint2 q23 = __ldg(reinterpret_cast<const uint2*>(base + 8));
+				const uint2 q45 = __ldg(reinterpret_cast<const uint2*>(base + 16));
+				uint32_t q6 = 0;
+				if(e) q6 = __ldg(reinterpret_cast<const uint32_t*>(base + 24));
+				a[0] = __uint_as_float(e ? q01.y : q01.x);
+				a[1] = __uint_as_float(e ? q23.x : q01.y);
+				a[2] = __uint_as_float(e ? q23.y : q23.x);
+				b[0] = __uint_as_float(e ? q45.x : q23.y);
+				b[1] = __uint_as_float(e ? q45.y : q45.x);
+				b[2] = __uint_as_float(e ? q6 : q45.y);
+			} else if constexpr(sb == 2) {
+				// 12 bytes at a 2-byte-aligned offset: at most 18 bytes into the window
+				const uint2 q01 = __ldg(reinterpret_cast<const uint2*>(base));
+				const uint2 q23 = __ldg(reinterpret_cast<const uint2*>(base + 8));
+				uint32_t q4 = 0;
+				if(o == 6u) q4 = __ldg(reinterpret_cast<const uint32_t*>(base + 16));
+				const uint32_t sh = (o & 3u) * 8u;
+				const uint32_t w0 = e ? q01.y : q01.x, w1 = e ? q23.x : q01.y, w2 = e ? q23.y : q23.x, w3 = e ? q4 : q23.y;
+				const uint32_t v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), 0u};
+				float t[6];
+#pragma unroll
+				for(int k = 0; k < 6; ++k) {
+					if constexpr(F == CACAO_FMT_U16)
+						t[k] = __uint_as_float(__byte_perm(v[k >> 1], kMagicBits, (k & 1) ? 0x7632u : 0x7610u)) - (BIASED ? 0.0f : kMagic);
+					else
+						t[k] = f16_bits_to_f32(static_cast<uint16_t>((v[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu));
+				}
+				a[0] = t[0]; a[1] = t[1]; a[2] = t[2];
+				b[0] = t[3]; b[1] = t[4]; b[2] = t[5];
+			} else {
+				// 6 bytes at any offset: at most 13 bytes into the window
+				const uint2 q01 = __ldg(reinterpret_cast<const uint2*>(base));
+				const uint2 q23 = __ldg(reinterpret_cast<const uint2*>(base + 8));
+				const uint32_t sh = (o & 3u) * 8u;
+				const uint32_t w0 = e ? q01.y : q01.x, w1 = e ? q23.x : q01.y, w2 = e ? q23.y : q23.x;
+				const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
+				constexpr float kOff = BIASED ? 0.0f : kMagic;
+				a[0] = __uint_as_float(__byte_perm(v0, kMagicBits, 0x7540u)) - kOff;
+				a[1] = __uint_as_float(__byte_perm(v0, kMagicBits, 0x7541u)) - kOff;
+				a[2] = __uint_as_float(__byte_perm(v0, kMagicBits, 0x7542u)) - kOff;
+				b[0] = __uint_as_float(__byte_perm(v0, kMagicBits, 0x7543u)) - kOff;
+				b[1] = __uint_as_float(__byte_perm(v1, kMagicBits, 0x7540u)) - kOff;
+				b[2] = __uint_as_float(__byte_perm(v1, kMagicBits, 0x7541u)) - kOff;
+			}
+		}
+
+		// Integer stores: the spec's clamp to [0, M] cannot change anything -- every lerp is
+		// fma(f, q - p, p) with f in [0, 1] and p, q exactly representable, so its exact value lies
+		// between p and q and the (monotone) rounding keeps it there; the filtered value of integer
+		// texels is therefore already inside [0, M] and never NaN.  The clamp is dropped here, not in
+		// the spec (oracle/cacao_oracle.c keeps it), and the GPU tests compare the two bit for bit.
 		template<int F, int CH>
 		__device__ __forceinline__ void store_texel(uint8_t* __restrict__ p, const float (&v)[CH]) {
 			constexpr int sb = FmtTraits<F>::bytes;
 			constexpr int bpp = sb * CH;
-			uint32_t s[CH];
-#pragma unroll
-			for(int c = 0; c < CH; ++c) {
-				if constexpr(F == CACAO_FMT_F32)
-					s[c] = __float_as_uint(v[c]);
-				else if constexpr(F == CACAO_FMT_F16)
-					s[c] = f32_to_f16_bits(v[c]);
-				else if constexpr(F == CACAO_FMT_U16)
-					s[c] = __float2uint_rz(fminf(fmaxf(v[c], 0.0f), 65535.0f) + 0.5f);
-				else
-					s[c] = __float2uint_rz(fminf(fmaxf(v[c], 0.0f), 255.0f) + 0.5f);
-			}
 			uint32_t w[4] = {0, 0, 0, 0};
+			if constexpr(F == CACAO_FMT_F32) {
 #pragma unroll
-			for(int c = 0; c < CH; ++c) {
-				if constexpr(sb == 1)
-					w[c >> 2] |= s[c] << ((c & 3) * 8);
-				else if constexpr(sb == 2)
-					w[c >> 1] |= s[c] << ((c & 1) * 16);
-				else
-					w[c] = s[c];
+				for(int c = 0; c < CH; ++c) w[c] = __float_as_uint(v[c]);
+			} else if constexpr(F == CACAO_FMT_F16) {
+#pragma unroll
+				for(int c = 0; c < CH; c += 2) w[c >> 1] = (c + 1 < CH) ? f32x2_to_f16x2_bits(v[c], v[(c + 1 < CH) ? c + 1 : c]) : f32_to_f16_bits(v[c]);
+			} else {
+				uint32_t s[CH];
+#pragma unroll
+				for(int c = 0; c < CH; ++c) s[c] = __float2uint_rz(v[c] + 0.5f);
+				if constexpr(sb == 2) {
+#pragma unroll
+					for(int c = 0; c < CH; c += 2) w[c >> 1] = (c + 1 < CH) ? __byte_perm(s[c], s[(c + 1 < CH) ? c + 1 : c], 0x5410u) : s[c];
+				} else if constexpr(CH == 1) {
+					w[0] = s[0];
+				} else {
+					const uint32_t lo = __byte_perm(s[0], s[1], 0x0040u);
+					const uint32_t hi = (CH == 4) ? __byte_perm(s[2], s[CH - 1], 0x0040u) : s[2];
+					w[0] = __byte_perm(lo, hi, 0x5410u);
+				}
 			}
 			if constexpr(bpp == 16) {
 				*reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -118,10 +193,66 @@ namespace cacao {
 			}
 		}
 
-		// Bilinear fetch + store of one output pixel whose source rows (r0, r1, fy) are already known.
+		// ---- packed fp32 (sm_100 FFMA2): two channels per instruction --------------------------------
+		// q - p is written fma(p, -1, q): p * (-1) is exact, so the single rounding is the subtraction's.
+		__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+			uint64_t r;
+			asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+			return r;
+		}
+		__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+			uint64_t r;
+			asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+			return r;
+		}
+		// BIAS != 0: the four taps still carry the integer-conversion offset 2^23.  It cancels exactly
+		// in q - p (both are integers below 2^24), and p alone loses it through one exact packed add.
+		template<bool BIASED>
+		__device__ __forceinline__ void lerp2(float fx, float fy, const float* a, const float* b, const float* c, const float* d, float* out) {
+			const uint64_t m1 = pk2(-1.0f, -1.0f), vx = pk2(fx, fx), vy = pk2(fy, fy);
+			uint64_t A = pk2(a[0], a[1]), C = pk2(c[0], c[1]);
+			const uint64_t B = pk2(b[0], b[1]), D = pk2(d[0], d[1]);
+			const uint64_t dx0 = fma2(A, m1, B), dx1 = fma2(C, m1, D);
+			if constexpr(BIASED) {
+				const uint64_t one = pk2(1.0f, 1.0f), off = pk2(-kMagic, -kMagic);
+				A = fma2(A, one, off);
+				C = fma2(C, one, off);
+			}
+			const uint64_t top = fma2(vx, dx0, A);
+			const uint64_t bot = fma2(vx, dx1, C);
+			const uint64_t o = fma2(vy, fma2(top, m1, bot), top);
+			asm("mov.b64 {%0,%1}, %2;" : "=f"(out[0]), "=f"(out[1]) : "l"(o));
+		}
+
+		// The source rows of one output row: element offsets of the two tap rows and the row weight.
+		template<typename IDX>
+		struct RowTaps {
+			IDX row0, row1;
+			float fy;
+		};
+		template<typename IDX>
+		__device__ __forceinline__ RowTaps<IDX> row_taps(float ys, const EquirectParams& prm) {
+			const float fy0 = floorf(ys);
+			int y0 = static_cast<int>(fy0);
+			int y1 = y0 + 1;
+			const int H = static_cast<int>(prm.H);
+			y0 = min(max(y0, 0), H - 1); // rows clamp
+			y1 = min(max(y1, 0), H - 1);
+			// rows are stored from src_row0 on; the window was planned on the host with the same
+			// arithmetic, the clamp below only guards memory if a caller passes a short window
+			const int r0 = min(max(y0 - static_cast<int>(prm.src_row0), 0), static_cast<int>(prm.src_rows) - 1);
+			const int r1 = min(max(y1 - static_cast<int>(prm.src_row0), 0), static_cast<int>(prm.src_rows) - 1);
+			RowTaps<IDX> t;
+			t.row0 = static_cast<IDX>(r0) * static_cast<IDX>(prm.W);
+			t.row1 = static_cast<IDX>(r1) * static_cast<IDX>(prm.W);
+			t.fy = ys - fy0;
+			return t;
+		}
+
+		// Bilinear fetch + store of one output pixel whose source rows are already known.
 		// IDX is uint32_t when the source window has < 2^32 pixels (cheaper address arithmetic).
 		template<int F, int CH, typename IDX>
-		__device__ __forceinline__ void sample_and_store(const uint8_t* __restrict__ src, uint8_t* __restrict__ out_px, float xs, int W, IDX row0, IDX row1, float fy) {
+		__device__ __forceinline__ void sample_and_store(const uint8_t* __restrict__ src, uint8_t* __restrict__ out_px, float xs, int W, const RowTaps<IDX>& rt, IDX total_px) {
 			constexpr int bpp = FmtTraits<F>::bytes * CH;
 			const float fx0 = floorf(xs);
 			const float fx = xs - fx0;
@@ -132,70 +263,93 @@ namespace cacao {
 			if(x0 >= W) x0 -= W;
 			if(x1 < 0) x1 += W;
 			if(x1 >= W) x1 -= W;
+			constexpr bool kBiased = FmtTraits<F>::is_int; // integer taps keep their 2^23 until the lerp
 			float a[CH], b[CH], c[CH], d[CH], out[CH];
-			load_texel<F, CH>(src + static_cast<size_t>(row0 + static_cast<IDX>(x0)) * bpp, a);
-			load_texel<F, CH>(src + static_cast<size_t>(row0 + static_cast<IDX>(x1)) * bpp, b);
-			load_texel<F, CH>(src + static_cast<size_t>(row1 + static_cast<IDX>(x0)) * bpp, c);
-			load_texel<F, CH>(src + static_cast<size_t>(row1 + static_cast<IDX>(x1)) * bpp, d);
+			bool joint = false;
+			if constexpr(CH == 3) {
+				// the aligned windows of load_pair3 reach at most 24 bytes (8 texels) past the x0 tap
+				const IDX last = (rt.row0 > rt.row1 ? rt.row0 : rt.row1) + static_cast<IDX>(x0);
+				joint = (x1 == x0 + 1) && (last + static_cast<IDX>(8) <= total_px);
+				if(joint) {
+					load_pair3<F, kBiased, IDX>(src, rt.row0 + static_cast<IDX>(x0), a, b);
+					load_pair3<F, kBiased, IDX>(src, rt.row1 + static_cast<IDX>(x0), c, d);
+				}
+			}
+			if(!joint) {
+				load_texel<F, CH, kBiased>(src + static_cast<size_t>(rt.row0 + static_cast<IDX>(x0)) * bpp, a);
+				load_texel<F, CH, kBiased>(src + static_cast<size_t>(rt.row0 + static_cast<IDX>(x1)) * bpp, b);
+				load_texel<F, CH, kBiased>(src + static_cast<size_t>(rt.row1 + static_cast<IDX>(x0)) * bpp, c);
+				load_texel<F, CH, kBiased>(src + static_cast<size_t>(rt.row1 + static_cast<IDX>(x1)) * bpp, d);
+			}
+			constexpr int kPairs = CH / 2;
 #pragma unroll
-			for(int k = 0; k < CH; ++k) {
-				const float top = fmaf(fx, b[k] - a[k], a[k]);
-				const float bot = fmaf(fx, d[k] - c[k], c[k]);
-				out[k] = fmaf(fy, bot - top, top);
+			for(int k = 0; k < kPairs; ++k) lerp2<kBiased>(fx, rt.fy, a + 2 * k, b + 2 * k, c + 2 * k, d + 2 * k, out + 2 * k);
+#pragma unroll
+			for(int k = 2 * kPairs; k < CH; ++k) {
+				constexpr float kOff = kBiased ? kMagic : 0.0f;
+				const float top = fmaf(fx, b[k] - a[k], a[k] - kOff);
+				const float bot = fmaf(fx, d[k] - c[k], c[k] - kOff);
+				out[k] = fmaf(rt.fy, bot - top, top);
 			}
 			store_texel<F, CH>(out_px, out);
 		}
 
-		// One thread = the pixel (i, j) and its mirror image (N-1-i, j) in the same face row.
+		// One thread = the pixel (i, j) and its mirror images.
 		//
-		// Mirroring a pixel across the face's vertical axis negates exactly one of the direction's x / z
-		// components (face_coord is bit-exactly antisymmetric), so the pair shares |x|, |z| and y: the
-		// two divisions, two polynomials and the square root of the projection are computed ONCE, the
-		// latitude (source rows, fy) is common, and only the longitude's quadrant placement differs.
-		// This halves the kernel's dominant cost -- instruction issue, not HBM (ncu: 74% issue-active,
-		// 50% DRAM before the change) -- and stays bit-identical to the per-pixel spec.
-		template<int F, int CH, typename IDX>
-		__global__ void __launch_bounds__(128, 16) equirect_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, EquirectParams prm) {
+		// Mirroring a pixel across the face's vertical axis (i -> N-1-i) negates exactly one of the
+		// direction's x / z components (face_coord is bit-exactly antisymmetric), so the pair shares
+		// |x|, |z| and y: the two divisions, two polynomials and the square root of the projection are
+		// computed ONCE, the latitude (source rows, fy) is common, and only the longitude's quadrant
+		// placement differs.  With QUAD (launches whose units are whole faces) the thread also owns the
+		// row mirror j -> N-1-j: on the side faces that negates y, hence theta exactly (atan2 is odd in
+		// y by construction) while the longitudes stay; on the +-Y faces it negates z, so the latitude
+		// stays and only the quadrant changes again.  Four pixels per projection; every value is the
+		// one the per-pixel spec computes, bit for bit.
+		// 32 registers (16 blocks/SM) everywhere except the three-channel shapes, whose window realignment
+		// needs 40 (12 blocks/SM measured 7 % ahead of spilling at 32: rgb8 0.165 -> 0.154 ms).
+		template<int F, int CH, typename IDX, bool QUAD, int WX>
+		__global__ void __launch_bounds__(128, CH == 3 ? 12 : 16) equirect_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, EquirectParams prm) {
 			constexpr int bpp = FmtTraits<F>::bytes * CH;
+			constexpr int RY = 32 / WX; // a warp covers WX columns x RY rows, a block WX x 4*RY
 			const CubeUnit unit = prm.units[blockIdx.z];
-			const uint32_t i = blockIdx.x * 32u + threadIdx.x;
-			const uint32_t j = unit.row_begin + blockIdx.y * blockDim.y + threadIdx.y;
+			const uint32_t i = blockIdx.x * WX + (threadIdx.x % WX);
+			const uint32_t j = unit.row_begin + (blockIdx.y * 4u + threadIdx.y) * RY + threadIdx.x / WX;
 			const uint32_t face = unit.face;
 			const uint32_t half = (prm.N + 1u) >> 1;
-			if(i >= half || j >= unit.row_end) return;
+			if(i >= half || j >= (QUAD ? half : unit.row_end)) return;
 			const uint32_t im = prm.N - 1u - i;
 
 			const float sc = face_coord(i, prm.pc);
 			const float tc = face_coord(j, prm.pc);
-			float xa, ya, za, xb, yb, zb;
+			float xa, ya, za;
 			face_direction(face, sc, tc, xa, ya, za);
-			face_direction(face, -sc, tc, xb, yb, zb);
+			// which component the column mirror negates: z on the +-X faces, x elsewhere
+			const bool sc_is_z = face < 2u;
+			const float xb = sc_is_z ? xa : -xa, zb = sc_is_z ? -za : za;
 
 			// shared: first-quadrant longitude, latitude
 			const float rphi = atan2_core(fabsf(za), fabsf(xa));
 			const float rxz = sqrtf(fmaf(xa, xa, za * za));
 			const float theta = atan2_spec(ya, rxz);
-			const float ys = fmaf(-theta, prm.pc.ky, prm.pc.cy);
-			const float fy0 = floorf(ys);
-			const float fy = ys - fy0;
-			int y0 = static_cast<int>(fy0);
-			int y1 = y0 + 1;
-			const int W = static_cast<int>(prm.W), H = static_cast<int>(prm.H);
-			y0 = min(max(y0, 0), H - 1); // rows clamp
-			y1 = min(max(y1, 0), H - 1);
-			// rows are stored from src_row0 on; the window was planned on the host with the same
-			// arithmetic, the clamp below only guards memory if a caller passes a short window
-			const int r0 = min(max(y0 - static_cast<int>(prm.src_row0), 0), static_cast<int>(prm.src_rows) - 1);
-			const int r1 = min(max(y1 - static_cast<int>(prm.src_row0), 0), static_cast<int>(prm.src_rows) - 1);
-			const IDX row0 = static_cast<IDX>(r0) * static_cast<IDX>(prm.W);
-			const IDX row1 = static_cast<IDX>(r1) * static_cast<IDX>(prm.W);
+			const int W = static_cast<int>(prm.W);
+			const IDX total_px = static_cast<IDX>(prm.src_rows) * static_cast<IDX>(prm.W);
+			const RowTaps<IDX> rt = row_taps<IDX>(fmaf(-theta, prm.pc.ky, prm.pc.cy), prm);
 
 			uint8_t* orow = dst + (static_cast<size_t>(face) * prm.N + j) * prm.N * bpp;
 			const float xs_a = fmaf(atan2_quadrant(rphi, xa, za), prm.pc.kx, prm.pc.cx);
-			sample_and_store<F, CH, IDX>(src, orow + static_cast<size_t>(i) * bpp, xs_a, W, row0, row1, fy);
-			if(im != i) {
-				const float xs_b = fmaf(atan2_quadrant(rphi, xb, zb), prm.pc.kx, prm.pc.cx);
-				sample_and_store<F, CH, IDX>(src, orow + static_cast<size_t>(im) * bpp, xs_b, W, row0, row1, fy);
+			const float xs_b = fmaf(atan2_quadrant(rphi, xb, zb), prm.pc.kx, prm.pc.cx);
+			sample_and_store<F, CH, IDX>(src, orow + static_cast<size_t>(i) * bpp, xs_a, W, rt, total_px);
+			if(im != i) sample_and_store<F, CH, IDX>(src, orow + static_cast<size_t>(im) * bpp, xs_b, W, rt, total_px);
+			if constexpr(QUAD) {
+				const uint32_t jm = prm.N - 1u - j;
+				if(jm == j) return;
+				uint8_t* mrow = dst + (static_cast<size_t>(face) * prm.N + jm) * prm.N * bpp;
+				const bool polar = (face & 6u) == 2u; // +-Y: the row mirror negates z, theta stays
+				const RowTaps<IDX> rm = polar ? rt : row_taps<IDX>(fmaf(theta, prm.pc.ky, prm.pc.cy), prm);
+				const float xs_c = polar ? fmaf(atan2_quadrant(rphi, xa, -za), prm.pc.kx, prm.pc.cx) : xs_a;
+				const float xs_d = polar ? fmaf(atan2_quadrant(rphi, xb, -zb), prm.pc.kx, prm.pc.cx) : xs_b;
+				sample_and_store<F, CH, IDX>(src, mrow + static_cast<size_t>(i) * bpp, xs_c, W, rm, total_px);
+				if(im != i) sample_and_store<F, CH, IDX>(src, mrow + static_cast<size_t>(im) * bpp, xs_d, W, rm, total_px);
 			}
 		}
 
@@ -386,14 +540,35 @@ namespace cacao {
 				}
 			}
 			const bool small = static_cast<uint64_t>(prm.src_rows) * prm.W < (1ull << 32);
-			// gather kernel: 32 x 4 blocks (16 per SM at 32 registers); measured 1-2 % ahead of 32 x 8 and 32 x 2,
-			// 25 % ahead of 32 x 1 (dev/sweep_eq_block.py)
+			// gather kernel: 128-thread blocks (16 per SM at 32 registers), four warps stacked vertically.
+			// A warp covers WX columns x 32/WX rows.  Square-ish footprints (8 x 4) touch fewer distinct
+			// source lines per tap instruction than a 32 x 1 run, most of all on the +-Y faces where
+			// neighbouring columns fan out over the longitudes (dev/sweep_eq_shape.py on B200: cfg3
+			// 0.180 -> 0.169 ms, cfg5 0.682 -> 0.657 ms; 16 x 2 is level, 4 x 8 loses again).  WX stays
+			// wide enough for a warp's store to fill whole 32-byte sectors.
+			constexpr int WX = bpp >= 4 ? 8 : (bpp >= 2 ? 16 : 32);
 			block = dim3(32, 4, 1);
-			const dim3 ggrid((half + 31) / 32, (max_rows + 3) / 4, prm.n_units);
-			if(small)
-				equirect_kernel<F, CH, uint32_t><<<ggrid, block, 0, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), prm);
-			else
-				equirect_kernel<F, CH, uint64_t><<<ggrid, block, 0, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), prm);
+			// whole faces: a thread also takes the row mirror, so only the upper half of the rows is launched
+			bool quad = true;
+			for(uint32_t u = 0; u < prm.n_units; ++u) quad = quad && prm.units[u].row_begin == 0 && prm.units[u].row_end == prm.N;
+			const char* qe = getenv("CACAO_EQUIRECT_NO_QUAD"); // test / A-B switch
+			if(qe && qe[0] == '1') quad = false;
+			const uint32_t rows = quad ? half : max_rows;
+			constexpr uint32_t bh = 4 * (32 / WX);
+			const dim3 ggrid((half + WX - 1) / WX, (rows + bh - 1) / bh, prm.n_units);
+			const uint8_t* s8 = static_cast<const uint8_t*>(src);
+			uint8_t* d8 = static_cast<uint8_t*>(dst);
+			if(small) {
+				if(quad)
+					equirect_kernel<F, CH, uint32_t, true, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
+				else
+					equirect_kernel<F, CH, uint32_t, false, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
+			} else {
+				if(quad)
+					equirect_kernel<F, CH, uint64_t, true, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
+				else
+					equirect_kernel<F, CH, uint64_t, false, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
+			}
 			return cudaGetLastError();
 		}
 

@@ -62,6 +62,26 @@ def test_every_format_and_layout_matches_oracle(oracle, fmt, ch):
 		assert same_bits(got, want)
 
 
+@pytest.mark.parametrize("fmt", FMTS, ids=[NAME[f] for f in FMTS])
+@pytest.mark.parametrize("ch", (1, 3, 4))
+def test_row_mirror_sharing_is_bit_identical(oracle, monkeypatch, fmt, ch):
+	"""Whole-face launches let one thread produce a pixel, its column mirror, its row mirror and the
+	diagonal one from a single projection; row-band launches (and CACAO_EQUIRECT_NO_QUAD=1) only share
+	the column mirror.  Both must equal the per-pixel oracle, for even, odd and degenerate face sizes."""
+	for W, H, N in ((96, 48, 36), (130, 70, 37), (16, 8, 1), (16, 8, 2), (64, 32, 130)):
+		src = oracle.synth(W * H * ch, fmt, ch, 77 + N)
+		want = oracle.equirect_to_cube(src, W, H, ch, fmt, N)
+		monkeypatch.delenv("CACAO_EQUIRECT_NO_QUAD", raising=False)
+		assert same_bits(gpu_equirect_device(src, W, H, ch, fmt, N), want), ("quad", W, H, N)
+		monkeypatch.setenv("CACAO_EQUIRECT_NO_QUAD", "1")
+		assert same_bits(gpu_equirect_device(src, W, H, ch, fmt, N), want), ("pair", W, H, N)
+		monkeypatch.delenv("CACAO_EQUIRECT_NO_QUAD", raising=False)
+		# a band launch next to a whole-face launch of the other faces
+		got = gpu_equirect_device(src, W, H, ch, fmt, N, mask=0x15, r0=0, r1=max(1, N // 2))
+		ref = oracle.equirect_to_cube(src, W, H, ch, fmt, N, face_mask=0x15, row_begin=0, row_end=max(1, N // 2))
+		assert same_bits(got, ref), ("band", W, H, N)
+
+
 def test_cfg1_shape_rgba8(oracle):
 	"""BASELINE config 1: 2048x1024 RGBA8 -> 6x512^2."""
 	from cacaoengine_b200 import _capi as c
