@@ -35,10 +35,23 @@ def test_subcommand_is_required(tool):
 	assert r.returncode != 0 and "subcommand is required" in r.stderr.lower()
 
 
-def test_reference_subcommands_answer_with_cube_error(tool):
+def test_reference_subcommands_validate_their_arguments(tool, tmp_path):
+	"""create / extract keep the reference's option checks (create.cpp:14-26, extract.cpp:14-43):
+	missing input file and bad -o are argument errors, bad content is a CUBE_ERROR with exit code 1."""
 	for sub in ("create", "extract"):
-		r = run(tool, sub, "x", "-o", "y")
-		assert r.returncode == 1 and r.stderr.startswith(ERR) and r.stdout == ""
+		r = run(tool, sub, str(tmp_path / "missing"), "-o", str(tmp_path / "y"))
+		assert r.returncode != 0 and "File does not exist" in r.stderr and r.stdout == ""
+		assert run(tool, sub, "--help").returncode == 0
+	junk = tmp_path / "junk.bin"
+	junk.write_bytes(b"junk: [1, 2]\n")
+	r = run(tool, "create", str(junk), "-o", str(tmp_path / "o.xjc"))
+	assert r.returncode == 1 and r.stderr.startswith(ERR) and "right (positive X) face node is invalid: Node does not exist" in r.stderr
+	r = run(tool, "extract", str(junk), "-A", "-o", str(tmp_path / "o"))
+	assert r.returncode == 1 and r.stderr.startswith(ERR) and "Stream is not of a Cacao Engine packed object!" in r.stderr
+	r = run(tool, "extract", str(junk), "-o", str(tmp_path / "o"))
+	assert r.returncode == 1 and "No faces selected for extraction!" in r.stderr
+	assert "Invalid face name" in run(tool, "extract", str(junk), "-f", "sideways").stderr
+	assert run(tool, "extract", str(junk), "-A", "-f", "left").returncode != 0
 
 
 def test_project_argument_validation(tool, tmp_path):

@@ -35,5 +35,23 @@ struct ProjectOptions {
 	bool bench = false;       // print a JSON timing line
 };
 
+struct CreateOptions {
+	std::filesystem::path input;  // .ajc, absolute
+	std::filesystem::path output; // .xjc
+	bool toRgb8 = false;          // GPU: 16 -> 8 bit + -> RGB per face before packing (Cubemap.cpp:28-31)
+};
+
+struct ExtractOptions {
+	std::filesystem::path input;  // .xjc
+	std::filesystem::path outDir; // absolute; default = current directory
+	bool all = false;
+	std::vector<int> faces;
+	bool flip = false; // GPU: bottom row first
+};
+
 // ce-cubetool project: equirectangular panorama -> six cube faces (+ .ajc for `create`)
 int RunProject(const ProjectOptions& opt);
+// ce-cubetool create: .ajc + six face files -> packed .xjc (reference tools/cubetool/create.cpp)
+int RunCreate(const CreateOptions& opt);
+// ce-cubetool extract: packed .xjc -> <stem>_<face>.png (reference tools/cubetool/extract.cpp)
+int RunExtract(const ExtractOptions& opt);

@@ -1,6 +1,8 @@
 // imageio.cpp -- see imageio.hpp.
 #include "imageio.hpp"
 
+#include "vp8l.hpp"
+
 #include <zlib.h>
 
 #include <cstdint>
@@ -286,13 +288,26 @@ namespace {
 
 namespace cubeio {
 	ImageEx ReadImage(const std::filesystem::path& path) {
-		const std::vector<unsigned char> f = slurp(path);
+		return DecodeImage(slurp(path));
+	}
+
+	ImageEx DecodeImage(const std::vector<unsigned char>& f) {
 		static const unsigned char pngSig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
 		if(f.size() >= 8 && std::memcmp(f.data(), pngSig, 8) == 0) return read_png(f);
 		if(f.size() >= 6 && std::memcmp(f.data(), "\x93NUMPY", 6) == 0) return read_npy(f);
 		if(f.size() >= 2 && f[0] == 'P' && (f[1] == 'F' || f[1] == 'f')) return read_pfm(f);
 		if(f.size() >= 2 && f[0] == 'P' && (f[1] == '5' || f[1] == '6')) return read_pnm(f);
-		throw std::runtime_error("Unrecognised image format (this build reads PNG, PFM, NPY and binary PGM/PPM)");
+		if(vp8l::IsWebP(f.data(), f.size())) {
+			vp8l::Decoded d = vp8l::Decode(f.data(), f.size());
+			ImageEx img;
+			img.w = d.w;
+			img.h = d.h;
+			img.layout = layout_of(d.channels);
+			img.format = SampleFormat::U8;
+			img.data = std::move(d.pixels);
+			return img;
+		}
+		throw std::runtime_error("Unrecognised image format (this build reads PNG, lossless WebP, PFM, NPY and binary PGM/PPM)");
 	}
 
 	void WriteImage(const ImageEx& img, const std::filesystem::path& path, const std::string& format) {
@@ -302,8 +317,14 @@ namespace cubeio {
 			write_pfm(img, path);
 		else if(format == "npy")
 			write_npy(img, path);
-		else
-			throw std::runtime_error("Unknown output format '" + format + "' (png, pfm, npy)");
+		else if(format == "webp") {
+			if(img.format != SampleFormat::U8 || img.layout == Image::Layout::Grayscale) throw std::runtime_error("WebP output needs 8-bit RGB or RGBA samples");
+			const std::vector<uint8_t> file = vp8l::Encode(img.data.data(), img.w, img.h, static_cast<int>(img.layout));
+			std::ofstream out(path, std::ios::binary);
+			if(!out.is_open()) throw std::runtime_error("Failed to open output file stream for writing!");
+			out.write(reinterpret_cast<const char*>(file.data()), static_cast<std::streamsize>(file.size()));
+		} else
+			throw std::runtime_error("Unknown output format '" + format + "' (png, webp, pfm, npy)");
 	}
 
 	std::string DefaultFormat(const ImageEx& img) {

@@ -2,10 +2,8 @@
 //
 // Keeps the reference tool's command-line contract (tools/cubetool/main.cpp:15-38): one required
 // subcommand, -v/--version, -V/--verbose (silent by default), -h/--help, `-o` for outputs, failures
-// as "ERROR: ..." on stderr with exit code 1.  The reference's two subcommands, create and
-// extract, are I/O glue around libwebp / bzip2 / yaml-cpp (un-vendored, absent here, out of the
-// GPU hot path's scope -- DESIGN.md); they are recognised and answer with a clear error.  `project`
-// is the new, GPU-backed subcommand.
+// as "ERROR: ..." on stderr with exit code 1.  create and extract keep the reference's options
+// (create.cpp:9-30, extract.cpp:9-48); `project` is the new, GPU-backed subcommand.
 #include <algorithm>
 #include <cstring>
 #include <filesystem>
@@ -50,6 +48,26 @@ namespace {
 				  << "          --bench             Print a JSON timing line \n";
 	}
 
+	void usageCreate(const std::string& prog) {
+		std::cout << "Create a new cubemap \n\n\n"
+				  << prog << " create [OPTIONS] input\n\n\nPOSITIONALS:\n"
+				  << "  input TEXT:FILE REQUIRED    Path to an unpacked cubemap definition file (.ajc) to read as input \n\nOPTIONS:\n"
+				  << "  -h,     --help              Print this help message and exit \n"
+				  << "  -o TEXT REQUIRED            Output file path \n"
+				  << "          --to-rgb8           Convert the faces to 8-bit RGB on the GPU before packing (what the engine does at load) \n";
+	}
+
+	void usageExtract(const std::string& prog) {
+		std::cout << "Extract face images from a cubemap \n\n\n"
+				  << prog << " extract [OPTIONS] input\n\n\nPOSITIONALS:\n"
+				  << "  input TEXT:FILE REQUIRED    Path to an packed cubemap file (.xjc) to read as input \n\nOPTIONS:\n"
+				  << "  -h,     --help              Print this help message and exit \n"
+				  << "  -A,     --all-faces Excludes: --face \n                              Extract all face images from the cubemap \n"
+				  << "  -f,     --face TEXT ... Excludes: --all-faces \n                              Extract specific faces from the cubemap (left, right, up, down, front, back) \n"
+				  << "  -o TEXT                     Directory to place output files in \n"
+				  << "          --flip              Write the faces bottom row first (mirrored on the GPU) \n";
+	}
+
 	[[noreturn]] void parseError(const std::string& msg) {
 		// CLI11 prints the problem and a hint, and exits non-zero
 		std::cerr << msg << "\nRun with --help for more information.\n";
@@ -81,8 +99,79 @@ int main(int argc, char* argv[]) {
 	}
 	if(sub.empty()) parseError("A subcommand is required");
 
-	if(sub == "create" || sub == "extract") {
-		CUBE_ERROR("The '" << sub << "' subcommand is not part of this build: it needs libwebp, bzip2 and yaml-cpp (packed .xjc I/O), which are outside the GPU image path. Use the reference ce-cubetool for it; 'project' writes the .ajc and face files it consumes.")
+	if(sub == "create") {
+		CreateOptions opt;
+		bool haveInput = false, haveOut = false;
+		for(size_t i = 0; i < rest.size(); ++i) {
+			const std::string& a = rest[i];
+			if(a == "-h" || a == "--help") {
+				usageCreate(prog);
+				return 0;
+			} else if(a == "-o") {
+				if(i + 1 >= rest.size()) parseError("-o: 1 required TEXT missing");
+				opt.output = rest[++i];
+				haveOut = true;
+			} else if(a == "--to-rgb8") {
+				opt.toRgb8 = true;
+			} else if(!a.empty() && a[0] == '-') {
+				parseError("The following argument was not expected: " + a);
+			} else if(!haveInput) {
+				opt.input = std::filesystem::absolute(a);
+				haveInput = true;
+			} else {
+				parseError("The following argument was not expected: " + a);
+			}
+		}
+		if(!haveInput) parseError("input is required");
+		if(!std::filesystem::is_regular_file(opt.input)) parseError("input: File does not exist: " + opt.input.string());
+		if(!haveOut) parseError("-o is required");
+		if(std::filesystem::exists(opt.output) && !std::filesystem::is_regular_file(opt.output)) parseError("-o: The output file must either be a file to overwrite or a nonexistent file!");
+		return RunCreate(opt);
+	}
+	if(sub == "extract") {
+		ExtractOptions opt;
+		opt.outDir = std::filesystem::current_path();
+		bool haveInput = false;
+		for(size_t i = 0; i < rest.size(); ++i) {
+			const std::string& a = rest[i];
+			if(a == "-h" || a == "--help") {
+				usageExtract(prog);
+				return 0;
+			} else if(a == "-o") {
+				if(i + 1 >= rest.size()) parseError("-o: 1 required TEXT missing");
+				opt.outDir = std::filesystem::absolute(rest[++i]);
+			} else if(a == "-A" || a == "--all-faces") {
+				opt.all = true;
+			} else if(a == "-f" || a == "--face") {
+				if(i + 1 >= rest.size()) parseError("--face: At least 1 required");
+				// one or more names follow, as with the reference's vector option
+				while(i + 1 < rest.size() && !rest[i + 1].empty() && rest[i + 1][0] != '-') {
+					const std::string v = rest[i + 1];
+					const auto it = std::find_if(kFaceNames.begin(), kFaceNames.end(), [&v](const char* n) { return v == n; });
+					if(it == kFaceNames.end()) {
+						// the first name must be a face; a later non-face token is the positional input
+						if(opt.faces.empty() || haveInput) parseError("--face: Invalid face name!");
+						break;
+					}
+					opt.faces.push_back(static_cast<int>(it - kFaceNames.begin()));
+					++i;
+				}
+			} else if(a == "--flip") {
+				opt.flip = true;
+			} else if(!a.empty() && a[0] == '-') {
+				parseError("The following argument was not expected: " + a);
+			} else if(!haveInput) {
+				opt.input = a;
+				haveInput = true;
+			} else {
+				parseError("The following argument was not expected: " + a);
+			}
+		}
+		if(!haveInput) parseError("input is required");
+		if(!std::filesystem::is_regular_file(opt.input)) parseError("input: File does not exist: " + opt.input.string());
+		if(opt.all && !opt.faces.empty()) parseError("--all-faces excludes --face");
+		if(std::filesystem::exists(opt.outDir) && !std::filesystem::is_directory(opt.outDir)) parseError("-o: The output directory must either be a directory to write into or a nonexistent directory!");
+		return RunExtract(opt);
 	}
 	if(sub != "project") parseError("The following argument was not expected: " + sub);
 
