@@ -3,6 +3,7 @@
 //
 // There is deliberately no CPU implementation of any pixel loop in this file or anywhere in the
 // library: without a CUDA device every compute entry point returns CACAO_E_NO_DEVICE.
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <thread>
@@ -377,31 +378,61 @@ namespace {
 		return CACAO_OK;
 	}
 
-	int download_any(DeviceCtx* c, uint8_t* host_dst, const uint8_t* dev_src, size_t bytes, cudaStream_t stream) {
-		if(!is_pageable(host_dst) || bytes < (1u << 20)) {
-			CU_TRY(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, stream));
-			CU_TRY(cudaStreamSynchronize(stream));
-			return CACAO_OK;
+	// One or more device -> host segments, read back as ONE chunked stream: adjacent segments are
+	// merged, pinned destinations are DMA'd directly, pageable ones go through the pinned ring with the
+	// copy pool draining chunk k-1 while chunk k is on the wire -- across segment borders too, so six
+	// separate face buffers cost one pipeline fill, not six.
+	struct Segment {
+		uint8_t* host;
+		const uint8_t* dev;
+		size_t bytes;
+	};
+
+	int download_segments(DeviceCtx* c, std::vector<Segment> segs, cudaStream_t stream) {
+		// merge neighbours that are contiguous on both sides
+		std::vector<Segment> merged;
+		for(const Segment& sg : segs) {
+			if(sg.bytes == 0) continue;
+			if(!merged.empty() && merged.back().host + merged.back().bytes == sg.host && merged.back().dev + merged.back().bytes == sg.dev)
+				merged.back().bytes += sg.bytes;
+			else
+				merged.push_back(sg);
 		}
-		int rc = ensure_pinned(c, 0, kXferChunk);
-		if(rc) return rc;
-		const size_t chunks = (bytes + kXferChunk - 1) / kXferChunk;
-		for(size_t k = 0; k < chunks + 1; ++k) {
-			if(k < chunks) {
-				const int s = static_cast<int>(k % kSlots);
-				const size_t off = k * kXferChunk, n = std::min(kXferChunk, bytes - off);
-				CU_TRY(cudaMemcpyAsync(c->pin_out[s], dev_src + off, n, cudaMemcpyDeviceToHost, stream));
-				CU_TRY(cudaEventRecord(c->ev_out[s], stream));
+		struct Chunk {
+			uint8_t* host;
+			const uint8_t* dev;
+			size_t n;
+		};
+		std::vector<Chunk> staged; // chunks that travel through the pinned ring
+		for(const Segment& sg : merged) {
+			if(!is_pageable(sg.host) || sg.bytes < (1u << 20)) {
+				CU_TRY(cudaMemcpyAsync(sg.host, sg.dev, sg.bytes, cudaMemcpyDeviceToHost, stream));
+				continue;
 			}
-			if(k >= 1) { // drain the previous chunk while this one is on the wire
-				const size_t j = k - 1;
-				const int s = static_cast<int>(j % kSlots);
-				const size_t off = j * kXferChunk, n = std::min(kXferChunk, bytes - off);
-				CU_TRY(cudaEventSynchronize(c->ev_out[s]));
-				CopyPool::get().copy(host_dst + off, c->pin_out[s], n);
+			for(size_t off = 0; off < sg.bytes; off += kXferChunk) staged.push_back({sg.host + off, sg.dev + off, std::min(kXferChunk, sg.bytes - off)});
+		}
+		if(!staged.empty()) {
+			int rc = ensure_pinned(c, 0, kXferChunk);
+			if(rc) return rc;
+			for(size_t k = 0; k < staged.size() + 1; ++k) {
+				if(k < staged.size()) {
+					const int sl = static_cast<int>(k % kSlots);
+					CU_TRY(cudaMemcpyAsync(c->pin_out[sl], staged[k].dev, staged[k].n, cudaMemcpyDeviceToHost, stream));
+					CU_TRY(cudaEventRecord(c->ev_out[sl], stream));
+				}
+				if(k >= 1) { // drain the previous chunk while this one is on the wire
+					const int sl = static_cast<int>((k - 1) % kSlots);
+					CU_TRY(cudaEventSynchronize(c->ev_out[sl]));
+					CopyPool::get().copy(staged[k - 1].host, c->pin_out[sl], staged[k - 1].n);
+				}
 			}
 		}
+		CU_TRY(cudaStreamSynchronize(stream));
 		return CACAO_OK;
+	}
+
+	int download_any(DeviceCtx* c, uint8_t* host_dst, const uint8_t* dev_src, size_t bytes, cudaStream_t stream) {
+		return download_segments(c, {{host_dst, dev_src, bytes}}, stream);
 	}
 
 	// ---- argument checks -----------------------------------------------------------------------
@@ -515,6 +546,124 @@ namespace {
 			}
 		}
 		CU_TRY(cudaStreamSynchronize(q_out));
+		return CACAO_OK;
+	}
+
+	// Host-memory resampling of a list of (face, row band) units, pipelined.
+	//
+	// A unit only reads a window of source rows, so nothing forces "upload everything, resample,
+	// read everything back": the source goes up top to bottom in ~32 MiB row chunks (stream s_in), a
+	// unit is launched as soon as the last row of its window has been enqueued (s_run waits on the
+	// upload event), and its rows start their way back (s_out) while later chunks are still going up.
+	// Units are first cut into bands of about 16 MiB of output and ordered by the end of their
+	// window, so the +Y face leaves after the first ~30 % of the upload.  PCIe then moves in both
+	// directions at once and the call costs about max(upload, readback) instead of their sum.
+	// Pinned buffers only; pageable ones and small jobs take the sequential form below.
+	// faces[f] = host base of face f (N x N pixels), only needed for faces that units name.
+	int equirect_host_pipeline(DeviceCtx* c, const uint8_t* hsrc, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, uint8_t* const* faces, uint32_t N, const CubeUnit* units_in, uint32_t n_units_in) {
+		const uint64_t bpp = static_cast<uint64_t>(ch) * fmt_bytes(fmt);
+		const uint64_t pitch = static_cast<uint64_t>(W) * bpp;
+		const uint64_t face_bytes = static_cast<uint64_t>(N) * N * bpp;
+		struct Piece {
+			CubeUnit u;
+			uint32_t w0, w1; // source rows [w0, w1) it reads
+		};
+		std::vector<Piece> pieces;
+		const uint64_t row_bytes = static_cast<uint64_t>(N) * bpp;
+		const uint32_t band_rows = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(N, (16ull << 20) / row_bytes)));
+		uint32_t lo = UINT32_MAX, hi = 0;
+		for(uint32_t k = 0; k < n_units_in; ++k) {
+			CubeUnit u = units_in[k];
+			if(u.row_end > N) u.row_end = N;
+			if(u.face > 5 || u.row_begin >= u.row_end) continue;
+			if(!faces[u.face]) return fail(CACAO_E_BAD_ARG, "equirect: no destination for face %u", u.face);
+			for(uint32_t r = u.row_begin; r < u.row_end; r += band_rows) {
+				Piece p;
+				p.u = {u.face, r, std::min(u.row_end, r + band_rows)};
+				uint32_t w0 = 0, wn = 0;
+				equirect_src_window(W, H, N, 1u << p.u.face, p.u.row_begin, p.u.row_end, &w0, &wn);
+				// clip to the rows the caller holds (the kernel clamps the same way)
+				const uint32_t a = std::max(w0, src_row0), b = std::min<uint64_t>(static_cast<uint64_t>(w0) + wn, static_cast<uint64_t>(src_row0) + src_rows);
+				p.w0 = a;
+				p.w1 = b > a ? b : a + 1;
+				lo = std::min(lo, p.w0);
+				hi = std::max(hi, p.w1);
+				pieces.push_back(p);
+			}
+		}
+		if(pieces.empty()) return CACAO_OK;
+		hi = std::min<uint64_t>(hi, static_cast<uint64_t>(src_row0) + src_rows);
+		std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& a, const Piece& b) { return a.w1 != b.w1 ? a.w1 < b.w1 : a.w0 < b.w0; });
+
+		std::lock_guard<std::mutex> lock(c->pipe_mutex);
+		int rc = ensure_stage(c, static_cast<uint64_t>(hi - lo) * pitch, 6 * face_bytes, 1);
+		if(rc) return rc;
+		const uint8_t* up_base = hsrc + static_cast<uint64_t>(lo - src_row0) * pitch;
+		const bool src_pg = is_pageable(up_base);
+		bool dst_pg = false;
+		for(const Piece& p : pieces) dst_pg = dst_pg || is_pageable(faces[p.u.face]);
+		// Pageable buffers are staged by host threads in both directions; one orchestrating thread
+		// cannot keep both stagings busy at once (measured: 16384x8192 RGBA32F, 89 ms pipelined against
+		// 79 ms one after the other), and small jobs only pay for the extra launches and event hops.
+		// Those run the three steps in sequence, each still chunk-overlapped inside upload_any /
+		// download_any, with whole-face units kept whole for the four-fold kernel.
+		uint64_t out_bytes = 0;
+		for(const Piece& p : pieces) out_bytes += static_cast<uint64_t>(p.u.row_end - p.u.row_begin) * row_bytes;
+		if(src_pg || dst_pg || static_cast<uint64_t>(hi - lo) * pitch + out_bytes < (32ull << 20)) {
+			rc = upload_any(c, c->stage_in[0], up_base, static_cast<uint64_t>(hi - lo) * pitch, c->s_run);
+			if(rc) return rc;
+			unsigned launches = 0;
+			cudaError_t e = equirect_launch_units(c->stage_in[0], c->stage_out[0], ch, fmt, W, H, lo, hi - lo, N, units_in, n_units_in, c->s_run, &launches);
+			g_launches.fetch_add(launches, std::memory_order_relaxed);
+			if(e != cudaSuccess) return fail_cuda(e, "equirect kernel launch");
+			std::vector<Segment> segs;
+			for(uint32_t k = 0; k < n_units_in; ++k) {
+				CubeUnit u = units_in[k];
+				if(u.row_end > N) u.row_end = N;
+				if(u.face > 5 || u.row_begin >= u.row_end) continue;
+				const uint64_t off = static_cast<uint64_t>(u.row_begin) * row_bytes;
+				segs.push_back({faces[u.face] + off, c->stage_out[0] + u.face * face_bytes + off, static_cast<size_t>(u.row_end - u.row_begin) * row_bytes});
+			}
+			return download_segments(c, segs, c->s_run);
+		}
+		const uint64_t rows_per_chunk = std::max<uint64_t>(1, kXferChunk / pitch);
+		auto read_back = [&](const Piece& p) -> int {
+			const uint64_t off = static_cast<uint64_t>(p.u.row_begin) * row_bytes, n = static_cast<uint64_t>(p.u.row_end - p.u.row_begin) * row_bytes;
+			CU_TRY(cudaMemcpyAsync(faces[p.u.face] + off, c->stage_out[0] + p.u.face * face_bytes + off, n, cudaMemcpyDeviceToHost, c->s_out));
+			return CACAO_OK;
+		};
+
+		size_t next = 0;
+		uint64_t k = 0;
+		for(uint64_t row = lo; row < hi; ++k) {
+			const uint64_t rows = std::min<uint64_t>(rows_per_chunk, hi - row);
+			const uint8_t* from = hsrc + (row - src_row0) * pitch;
+			const int sl = static_cast<int>(k % kSlots);
+			CU_TRY(cudaMemcpyAsync(c->stage_in[0] + (row - lo) * pitch, from, rows * pitch, cudaMemcpyHostToDevice, c->s_in));
+			CU_TRY(cudaEventRecord(c->ev_in[sl], c->s_in));
+			row += rows;
+			// every piece whose window is now on its way
+			size_t ready_end = next;
+			while(ready_end < pieces.size() && pieces[ready_end].w1 <= row) ++ready_end;
+			if(row >= hi) ready_end = pieces.size();
+			if(ready_end > next) {
+				CU_TRY(cudaStreamWaitEvent(c->s_run, c->ev_in[sl], 0));
+				std::vector<CubeUnit> batch;
+				for(size_t q = next; q < ready_end; ++q) batch.push_back(pieces[q].u);
+				unsigned launches = 0;
+				cudaError_t e = equirect_launch_units(c->stage_in[0], c->stage_out[0], ch, fmt, W, H, lo, hi - lo, N, batch.data(), static_cast<uint32_t>(batch.size()), c->s_run, &launches);
+				g_launches.fetch_add(launches, std::memory_order_relaxed);
+				if(e != cudaSuccess) return fail_cuda(e, "equirect kernel launch");
+				CU_TRY(cudaEventRecord(c->ev_run[0], c->s_run));
+				CU_TRY(cudaStreamWaitEvent(c->s_out, c->ev_run[0], 0));
+				for(size_t q = next; q < ready_end; ++q) {
+					rc = read_back(pieces[q]);
+					if(rc) return rc;
+				}
+				next = ready_end;
+			}
+		}
+		CU_TRY(cudaStreamSynchronize(c->s_out));
 		return CACAO_OK;
 	}
 
@@ -753,29 +902,33 @@ int cacao_img_equirect_to_cube(int device, const void* src, uint32_t W, uint32_t
 		g_launches.fetch_add(1, std::memory_order_relaxed);
 		return CACAO_OK;
 	}
-	// host memory: upload only the source rows this work unit reads, read back only what it wrote
-	uint32_t need0 = 0, need_rows = 0;
-	equirect_src_window(W, H, N, face_mask, row_begin, row_end, &need0, &need_rows);
-	if(need0 < src_row0) need0 = src_row0;
-	if(need0 + need_rows > src_row0 + src_rows) need_rows = src_row0 + src_rows - need0;
-	const uint64_t pitch = static_cast<uint64_t>(W) * bpp;
-	const uint64_t cube_bytes = 6ull * N * N * bpp;
-	std::lock_guard<std::mutex> lock(c->pipe_mutex);
-	rc = ensure_stage(c, need_rows * pitch, cube_bytes, 1);
-	if(rc) return rc;
-	const uint8_t* hsrc = static_cast<const uint8_t*>(src) + static_cast<uint64_t>(need0 - src_row0) * pitch;
-	rc = upload_any(c, c->stage_in[0], hsrc, need_rows * pitch, c->s_run);
-	if(rc) return rc;
-	cudaError_t e = equirect_launch(c->stage_in[0], c->stage_out[0], ch, fmt, W, H, need0, need_rows, N, face_mask, row_begin, row_end, c->s_run);
-	if(e != cudaSuccess) return fail_cuda(e, "equirect kernel launch");
-	g_launches.fetch_add(1, std::memory_order_relaxed);
+	// host memory: a pipelined upload / resample / readback of only the rows involved
+	(void)bpp;
+	uint8_t* faces[6];
+	CubeUnit units[6];
+	uint32_t n = 0;
 	for(uint32_t f = 0; f < 6; ++f) {
-		if(!(face_mask & (1u << f))) continue;
-		const uint64_t off = (static_cast<uint64_t>(f) * N + row_begin) * N * bpp;
-		rc = download_any(c, static_cast<uint8_t*>(dst) + off, c->stage_out[0] + off, static_cast<uint64_t>(row_end - row_begin) * N * bpp, c->s_run);
-		if(rc) return rc;
+		faces[f] = static_cast<uint8_t*>(dst) + static_cast<uint64_t>(f) * N * N * bpp;
+		if(face_mask & (1u << f)) units[n++] = {f, row_begin, row_end};
 	}
-	return CACAO_OK;
+	return equirect_host_pipeline(c, static_cast<const uint8_t*>(src), W, H, src_row0, src_rows, ch, fmt, faces, N, units, n);
+}
+
+int cacao_img_equirect_to_cube_units_host(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* const* faces, uint32_t N, const cacao_cube_unit* units, uint32_t n_units) {
+	if(!ch_ok(ch) || !fmt_ok(fmt)) return fail(CACAO_E_BAD_ARG, "equirect: bad channel count %d or format %d", ch, fmt);
+	if(W == 0 || H == 0 || N == 0) return fail(CACAO_E_ZERO_DIM, "equirect: zero-sized image or face");
+	if(!src || !faces || (!units && n_units)) return fail(CACAO_E_BAD_ARG, "null pointer");
+	if(W > (1u << 24) || H > (1u << 24) || N > (1u << 23)) return fail(CACAO_E_BAD_ARG, "equirect: dimensions beyond exact float range");
+	if(src_rows == 0 || src_row0 + static_cast<uint64_t>(src_rows) > H) return fail(CACAO_E_BAD_ARG, "equirect: source window [%u,+%u) outside the image (H=%u)", src_row0, src_rows, H);
+	for(uint32_t u = 0; u < n_units; ++u)
+		if(units[u].face > 5) return fail(CACAO_E_BAD_ARG, "equirect: unit %u names face %u", u, units[u].face);
+	if(n_units == 0) return CACAO_OK;
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	static_assert(sizeof(cacao_cube_unit) == sizeof(CubeUnit), "unit layouts must match");
+	return equirect_host_pipeline(c, static_cast<const uint8_t*>(src), W, H, src_row0, src_rows, ch, fmt, reinterpret_cast<uint8_t* const*>(faces), N, reinterpret_cast<const CubeUnit*>(units), n_units);
 }
 
 int cacao_img_equirect_to_cube_units(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, const cacao_cube_unit* units, uint32_t n_units, void* stream) {

@@ -633,9 +633,13 @@ namespace cacao {
 		return equirect_launch_units(src, dst, ch, fmt, W, H, src_row0, src_rows, N, units, n, stream, nullptr);
 	}
 
-	// Host-side planning with the same arithmetic as the kernel.  theta (hence ys) is monotone in tc
-	// for fixed sc on the side faces and a function of sc^2+tc^2 on the +-Y faces, so its extremes over
-	// a full-width row band lie on the band's first/last row or on the centre/edge columns.
+	// Host-side planning with the same arithmetic as the kernel, in O(1) evaluations per face.
+	// On a side face theta = atan2(-tc, sqrt(1 + sc^2)) is monotone in tc for any sc and, for a given
+	// tc, monotone in |sc|: over a full-width row band its extremes lie on the band's first / last row
+	// at the centre or edge columns.  On the +-Y faces theta is a monotone function of sc^2 + tc^2: the
+	// extremes are the pixel nearest the face centre (centre columns; the centre row if the band
+	// contains it, else the nearer border row) and a corner of the band.  fp32 rounding moves ys by
+	// ~1e-3 rows at most; the window carries a whole row of slack on each side.
 	void equirect_src_window(uint32_t W, uint32_t H, uint32_t N, uint32_t face_mask, uint32_t row_begin, uint32_t row_end, uint32_t* src_row0, uint32_t* src_rows) {
 		const ProjConst pc = make_proj_const(N, W, H);
 		float lo = 3.0e38f, hi = -3.0e38f;
@@ -649,12 +653,11 @@ namespace cacao {
 		for(uint32_t f = 0; f < 6; ++f) {
 			if(!(face_mask & (1u << f)) || row_begin >= row_end) continue;
 			const uint32_t cols[4] = {0, (N - 1) / 2, N / 2, N - 1};
-			for(uint32_t j = row_begin; j < row_end; ++j)
+			uint32_t rows[4] = {row_begin, row_end - 1, row_begin, row_end - 1};
+			if((N - 1) / 2 >= row_begin && (N - 1) / 2 < row_end) rows[2] = (N - 1) / 2;
+			if(N / 2 >= row_begin && N / 2 < row_end) rows[3] = N / 2;
+			for(uint32_t j : rows)
 				for(uint32_t i : cols) visit(f, i, j);
-			for(uint32_t i = 0; i < N; ++i) {
-				visit(f, i, row_begin);
-				visit(f, i, row_end - 1);
-			}
 		}
 		if(hi < lo) {
 			*src_row0 = 0;

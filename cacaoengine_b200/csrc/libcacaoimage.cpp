@@ -222,50 +222,68 @@ namespace libcacaoimage {
 			faces[f].data.resize(face_bytes);
 		}
 
-		// (face, row band) work units dealt round-robin, band-major, so with several devices each one gets
-		// a mix of polar and side faces.  Each device thread uploads the union of the source-row windows
-		// its units read ONCE, resamples all its units in one launch, and reads back only its own rows.
+		// One device: the whole cube as six units; the library pipelines upload, resampling and
+		// readback by itself.  Several devices: (face, row band) units ordered by the latitude they
+		// read and dealt in contiguous runs of equal output size, so every device uploads only a band
+		// of the source (about 1/4 of it with 8 devices) instead of nearly all of it -- the host side of
+		// this call is PCIe- and memcpy-bound, the kernels are noise.  Each device thread then makes ONE
+		// pipelined call for its run and the rows land straight in the six result vectors.
 		const std::vector<int> devs = devices.empty() ? std::vector<int>{-1} : devices;
-		unsigned bands = 1;
-		while((6 * bands) % devs.size() != 0 && bands < 64) ++bands;
 		std::vector<cacao_cube_unit> units;
-		for(unsigned b = 0; b < bands; ++b)
-			for(unsigned f = 0; f < 6; ++f) {
-				const unsigned r0 = static_cast<unsigned>(static_cast<uint64_t>(faceSize) * b / bands);
-				const unsigned r1 = static_cast<unsigned>(static_cast<uint64_t>(faceSize) * (b + 1) / bands);
-				if(r1 > r0) units.push_back({f, r0, r1});
+		if(devs.size() == 1) {
+			for(unsigned f = 0; f < 6; ++f) units.push_back({f, 0, faceSize});
+		} else {
+			const unsigned bands = static_cast<unsigned>(std::min<std::size_t>(faceSize, 2 * devs.size()));
+			struct Keyed {
+				cacao_cube_unit u;
+				uint64_t mid; // twice the centre of its source-row window
+			};
+			std::vector<Keyed> keyed;
+			for(unsigned f = 0; f < 6; ++f)
+				for(unsigned b = 0; b < bands; ++b) {
+					const unsigned r0 = static_cast<unsigned>(static_cast<uint64_t>(faceSize) * b / bands);
+					const unsigned r1 = static_cast<unsigned>(static_cast<uint64_t>(faceSize) * (b + 1) / bands);
+					if(r1 <= r0) continue;
+					uint32_t w0 = 0, wn = 0;
+					check(cacao_img_equirect_src_window(src.w, src.h, faceSize, 1u << f, r0, r1, &w0, &wn));
+					keyed.push_back({{f, r0, r1}, 2ull * w0 + wn});
+				}
+			std::stable_sort(keyed.begin(), keyed.end(), [](const Keyed& x, const Keyed& y) { return x.mid < y.mid; });
+			for(const Keyed& k : keyed) units.push_back(k.u);
+		}
+		// contiguous runs with (nearly) equal numbers of output rows
+		uint64_t total_rows = 0;
+		for(const auto& un : units) total_rows += un.row_end - un.row_begin;
+		std::vector<std::size_t> run_begin(devs.size() + 1, units.size());
+		{
+			uint64_t acc = 0;
+			std::size_t d = 0;
+			run_begin[0] = 0;
+			for(std::size_t u = 0; u < units.size(); ++u) {
+				while(d + 1 < devs.size() && acc * devs.size() >= (d + 1) * total_rows) run_begin[++d] = u;
+				acc += units[u].row_end - units[u].row_begin;
 			}
+			while(d + 1 < devs.size()) run_begin[++d] = units.size();
+		}
 		std::vector<std::string> errors(devs.size());
 		auto worker = [&](std::size_t k) {
-			auto fail_if = [&](int rc) {
-				if(rc != CACAO_OK && errors[k].empty()) errors[k] = cacao_img_last_error();
-				return rc != CACAO_OK;
-			};
-			std::vector<cacao_cube_unit> mine;
-			for(std::size_t u = k; u < units.size(); u += devs.size()) mine.push_back(units[u]);
-			if(mine.empty()) return;
+			const std::size_t u0 = run_begin[k], u1 = run_begin[k + 1];
+			if(u1 <= u0) return;
 			uint32_t lo = UINT32_MAX, hi = 0;
-			for(const auto& un : mine) {
+			for(std::size_t u = u0; u < u1; ++u) {
 				uint32_t w0 = 0, wn = 0;
-				if(fail_if(cacao_img_equirect_src_window(src.w, src.h, faceSize, 1u << un.face, un.row_begin, un.row_end, &w0, &wn))) return;
+				if(cacao_img_equirect_src_window(src.w, src.h, faceSize, 1u << units[u].face, units[u].row_begin, units[u].row_end, &w0, &wn) != CACAO_OK) {
+					errors[k] = cacao_img_last_error();
+					return;
+				}
 				lo = std::min(lo, w0);
 				hi = std::max(hi, w0 + wn);
 			}
 			const std::size_t pitch = static_cast<std::size_t>(src.w) * bpp;
-			void *dsrc = nullptr, *dcube = nullptr;
-			if(fail_if(cacao_img_malloc(devs[k], &dsrc, static_cast<uint64_t>(hi - lo) * pitch))) return;
-			if(!fail_if(cacao_img_malloc(devs[k], &dcube, 6 * face_bytes))) {
-				bool bad = fail_if(cacao_img_upload(devs[k], dsrc, src.data.data() + static_cast<std::size_t>(lo) * pitch, static_cast<uint64_t>(hi - lo) * pitch, nullptr));
-				bad = bad || fail_if(cacao_img_equirect_to_cube_units(devs[k], dsrc, src.w, src.h, lo, hi - lo, static_cast<int>(src.layout), static_cast<int>(src.format), dcube, faceSize, mine.data(), static_cast<uint32_t>(mine.size()), nullptr));
-				for(const auto& un : mine) {
-					if(bad) break;
-					const std::size_t in_face = static_cast<std::size_t>(un.row_begin) * faceSize * bpp;
-					bad = fail_if(cacao_img_download(devs[k], faces[un.face].data.data() + in_face, static_cast<unsigned char*>(dcube) + un.face * face_bytes + in_face, static_cast<uint64_t>(un.row_end - un.row_begin) * faceSize * bpp, nullptr));
-				}
-				if(!bad) fail_if(cacao_img_sync(devs[k], nullptr));
-				cacao_img_free(devs[k], dcube);
-			}
-			cacao_img_free(devs[k], dsrc);
+			void* dst[6];
+			for(unsigned f = 0; f < 6; ++f) dst[f] = faces[f].data.data();
+			if(cacao_img_equirect_to_cube_units_host(devs[k], src.data.data() + static_cast<std::size_t>(lo) * pitch, src.w, src.h, lo, hi - lo, static_cast<int>(src.layout), static_cast<int>(src.format), dst, faceSize, units.data() + u0, static_cast<uint32_t>(u1 - u0)) != CACAO_OK)
+				errors[k] = cacao_img_last_error();
 		};
 		if(devs.size() == 1) {
 			worker(0);

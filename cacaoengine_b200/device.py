@@ -90,6 +90,14 @@ def equirect_to_cube_units(src: int, W: int, H: int, ch: int, fmt: int, dst: int
 	capi.check(capi.lib().cacao_img_equirect_to_cube_units(device, src, W, H, src_row0, H if src_rows is None else src_rows, ch, fmt, dst, N, flat.ctypes.data, len(flat), stream))
 
 
+def equirect_to_cube_units_host(src: int, W: int, H: int, ch: int, fmt: int, faces, N: int, units, src_row0: int = 0, src_rows: int | None = None, device: int = -1) -> None:
+	"""Host-memory, pipelined form: src = host address of source rows [src_row0, src_row0 + src_rows),
+	faces = six host addresses (0 for faces no unit names)."""
+	flat = np.array([(u.face, u.row_begin, u.row_end) if hasattr(u, "face") else tuple(u) for u in units], np.uint32).reshape(-1, 3)
+	ptrs = (C.c_void_p * 6)(*[int(f) if f else None for f in faces])
+	capi.check(capi.lib().cacao_img_equirect_to_cube_units_host(device, src, W, H, src_row0, H if src_rows is None else src_rows, ch, fmt, ptrs, N, flat.ctypes.data, len(flat)))
+
+
 def equirect_src_window(W: int, H: int, N: int, face_mask: int, row_begin: int, row_end: int) -> tuple[int, int]:
 	r0, n = C.c_uint32(), C.c_uint32()
 	capi.check(capi.lib().cacao_img_equirect_src_window(W, H, N, face_mask, row_begin, row_end, C.byref(r0), C.byref(n)))

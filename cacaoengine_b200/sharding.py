@@ -38,18 +38,20 @@ class CubeUnit:
 		return self.row_end - self.row_begin
 
 
-def cube_units(face_size: int, bands_per_face: int) -> list[CubeUnit]:
-	"""6 x bands_per_face work units, band-major so that consecutive units are different faces
-	(round-robin dealing then gives every rank a mix of polar and side faces)."""
-	bands_per_face = max(1, min(bands_per_face, face_size))
+def cube_units(face_size: int, bands_per_face: int, polar_factor: int = 1) -> list[CubeUnit]:
+	"""Work units of a cube: bands_per_face row bands on each side face and polar_factor times as
+	many on the +-Y faces (their rows cost up to twice as much, so they are cut finer), band-major so
+	that consecutive units are different faces."""
 	units = []
-	for b in range(bands_per_face):
-		r0 = face_size * b // bands_per_face
-		r1 = face_size * (b + 1) // bands_per_face
-		for f in range(6):
+	for f in range(6):
+		n = bands_per_face * (polar_factor if f in (2, 3) else 1)
+		n = max(1, min(n, face_size))
+		for b in range(n):
+			r0 = face_size * b // n
+			r1 = face_size * (b + 1) // n
 			if r1 > r0:
 				units.append(CubeUnit(f, r0, r1))
-	return units
+	return sorted(units, key=lambda u: (u.row_begin / face_size, u.face))
 
 
 def bands_for_world(world: int) -> int:
@@ -64,15 +66,16 @@ def bands_for_world(world: int) -> int:
 
 
 def unit_cost(u: CubeUnit, face_size: int) -> float:
-	"""Relative cost of a unit.  Measured on B200 (dev/unit_costs.py, 16384x8192 -> 4096^2): every
-	side-face row costs the same; rows of the +-Y faces cost 1.1x at the face edge rising to 2.2x at the
-	centre, where neighbouring pixels fan out over all longitudes and taps stop coalescing."""
+	"""Relative cost of a unit.  Measured on B200 (dev/unit_costs.py, 16384x8192 -> 4096^2, 8 bands per
+	face: 15.2 us for every side-face band; 15.4 / 17.4 / 21.3 / 32.1 us from the edge to the centre
+	of a +-Y face): a side-face row costs 1, a row of the +-Y faces 1.0 at the face edge rising to 2.1
+	at the centre, where neighbouring pixels fan out over all longitudes and taps stop coalescing."""
 	if u.face not in (2, 3):
 		return float(u.rows)
 	total = 0.0
 	for r in range(u.row_begin, u.row_end):
 		d = abs((2 * r + 1) / face_size - 1.0)  # 0 at the centre row, 1 at the edge
-		total += 1.1 + 1.1 * (1.0 - d) ** 2
+		total += 1.0 + 1.57 * (1.0 - d) ** 2.75
 	return total
 
 
@@ -83,7 +86,9 @@ def units_for_rank(rank: int, world: int, face_size: int, bands_per_face: int | 
 	if not (0 <= rank < world):
 		raise ValueError(f"rank {rank} outside world of {world}")
 	bands = bands_for_world(world) if bands_per_face is None else bands_per_face
-	units = cube_units(face_size, bands)
+	# the +-Y faces are cut twice as fine: their centre bands would otherwise be the largest units by
+	# a factor of two and cap the balance (8 ranks: max/mean 1.04 -> 1.002)
+	units = cube_units(face_size, bands, polar_factor=2 if world > 1 else 1)
 	order = sorted(range(len(units)), key=lambda k: (-unit_cost(units[k], face_size), k))
 	load = [0.0] * world
 	mine = []

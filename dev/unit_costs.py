@@ -26,7 +26,7 @@ for bands in (4, 8):
 	for world in (8,):
 		sums = []
 		for r in range(world):
-			mine = units[r::world]
+			mine = sharding.units_for_rank(r, world, N, bands)
 			sums.append((sum(cost[(u.face, u.row_begin)] for u in mine), t(mine)))
 		print(f"  world={world}: per-rank sum-of-units ms {[round(s[0],4) for s in sums]}")
 		print(f"  world={world}: per-rank one-launch   ms {[round(s[1],4) for s in sums]}  max {max(s[1] for s in sums):.4f}  ideal {sum(s[1] for s in sums)/world:.4f}")

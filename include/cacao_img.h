@@ -131,7 +131,9 @@ int cacao_img_flip_rows(int device, const void* src, void* dst, uint32_t w, uint
  *   dst       base of the FULL cube buffer: 6 faces x N x N pixels, face-major in the order
  *             +X,-X,+Y,-Y,+Z,-Z (libs/formats/include/libcacaoformats.hpp:213), rows top first
  *   face_mask bit f set = produce face f;  rows [row_begin,row_end) of each selected face are written
- * With CACAO_MEM_HOST only the written rows are read back into dst.
+ * With CACAO_MEM_HOST the call is the pipelined pass described at
+ * cacao_img_equirect_to_cube_units_host: only the source rows that are read go up, only the written
+ * rows come back, and the two directions overlap.
  */
 int cacao_img_equirect_to_cube(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0,
 							   uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, uint32_t face_mask,
@@ -150,6 +152,18 @@ typedef struct cacao_cube_unit {
 int cacao_img_equirect_to_cube_units(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0,
 									 uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N,
 									 const cacao_cube_unit* units, uint32_t n_units, void* stream);
+
+/* The host-memory form of the unit list: src = host rows [src_row0, src_row0+src_rows) of the
+ * equirect image, faces[f] = host base of face f's N x N pixels (may be NULL for faces no unit
+ * names; the six faces need not be contiguous -- libcacaoimage::EquirectToCubemap hands over six
+ * std::vectors).  One pipelined pass: the source goes up in row chunks, a unit is resampled as soon
+ * as the last row of its window is on the device, and its rows travel back while later chunks still
+ * go up, so the call costs about max(upload, readback) rather than their sum.  Pinned and pageable
+ * buffers both work (pageable ones are staged through the library's pinned rings).  Returns when
+ * every named row is in place. */
+int cacao_img_equirect_to_cube_units_host(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0,
+											 uint32_t src_rows, int ch, int fmt, void* const* faces, uint32_t N,
+											 const cacao_cube_unit* units, uint32_t n_units);
 
 /* Host-side planning: the inclusive-exclusive window of source rows that the work unit
  * (face_mask, [row_begin,row_end)) reads, so a shard can upload just that band. */

@@ -143,12 +143,14 @@ def test_src_window_planner_covers_all_taps(built_lib, oracle):
 	the window the library plans for that work unit."""
 	from cacaoengine_b200 import device
 
-	W, H, N = 256, 128, 48
-	for face in range(6):
-		for (r0, r1) in ((0, 48), (0, 12), (12, 30), (40, 48)):
-			w0, wn = device.equirect_src_window(W, H, N, 1 << face, r0, r1)
-			ys = np.array([oracle.project(face, i, j, N, W, H)[1] for j in range(r0, r1) for i in range(N)])
-			lo = max(0, int(np.floor(ys.min())))
-			hi = min(H - 1, int(np.floor(ys.max())) + 1)
-			assert w0 <= lo and w0 + wn - 1 >= hi, (face, r0, r1, w0, wn, lo, hi)
-			assert wn <= H
+	for W, H, N, bands in ((256, 128, 48, ((0, 48), (0, 12), (12, 30), (40, 48), (23, 25), (24, 25))), (300, 140, 37, ((0, 37), (0, 9), (9, 19), (18, 19), (17, 30), (36, 37))), (64, 32, 1, ((0, 1),))):
+		for face in range(6):
+			for (r0, r1) in bands:
+				w0, wn = device.equirect_src_window(W, H, N, 1 << face, r0, r1)
+				ys = np.array([oracle.project(face, i, j, N, W, H)[1] for j in range(r0, r1) for i in range(N)])
+				lo = max(0, int(np.floor(ys.min())))
+				hi = min(H - 1, int(np.floor(ys.max())) + 1)
+				assert w0 <= lo and w0 + wn - 1 >= hi, (face, r0, r1, w0, wn, lo, hi)
+				assert wn <= H
+				# and it is tight: the taps' rows plus the planner's slack (one row each side, one for floor + 1)
+				assert w0 >= lo - 2 and w0 + wn - 1 <= hi + 2, (face, r0, r1, w0, wn, lo, hi)
