@@ -265,14 +265,14 @@ def roof(alg_bytes, ms, peak, traffic=None):
 def extra_configs(torch, dist, world, rank, dev, stream, peak):
 	"""The other BASELINE configs, device-resident, sharded over the ranks exactly as DESIGN.md
 	"Multi-GPU" says (images by index, cube by face/row band); rooflines are per GPU (x world)."""
-	from cacaoengine_b200 import FMT_F32, FMT_U8, device, sharding
+	from cacaoengine_b200 import FMT_F32, FMT_U8, MEM_HOST, device, sharding
 
 	out = {}
 
 	def alloc(n):
 		return torch.empty(max(n, 16), dtype=torch.uint8, device=f"cuda:{dev}")
 
-	def equirect(key, W, H, N, ch, fmt, bps, steps, note=None):
+	def equirect(key, W, H, N, ch, fmt, bps, steps, note=None, e2e=False):
 		bpp = ch * bps
 		units = sharding.units_for_rank(rank, world, N) if world > 1 else [sharding.CubeUnit(-1, 0, N)]
 		if world > 1:
@@ -294,11 +294,29 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 		out[key] = {"value": 6 * N * N / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "units_per_rank": len(units), "source_rows_per_rank": wn, "roofline": roof(alg, ms, peak * world, traffic_for(key))}
 		if note:
 			out[key]["note"] = note
+		if e2e and world == 1:
+			# the same job host -> host through cacao_img_equirect_to_cube(CACAO_MEM_HOST) with pinned
+			# buffers: pipelined upload / resample / readback, wall-clock timed (the call is synchronous)
+			import numpy as np
+
+			sp, s_host = device.host_alloc(W * H * bpp)
+			dp, d_host = device.host_alloc(6 * N * N * bpp)
+			device.download(s_host, src.data_ptr(), device=dev)
+			device.equirect_to_cube(sp, W, H, ch, fmt, dp, N, mem=MEM_HOST, device=dev)  # warm-up: staging buffers
+			t0 = time.perf_counter()
+			for _ in range(3):
+				device.equirect_to_cube(sp, W, H, ch, fmt, dp, N, mem=MEM_HOST, device=dev)
+			dt = (time.perf_counter() - t0) / 3
+			ref = np.empty(6 * N * N * bpp, np.uint8)
+			device.download(ref, dst.data_ptr(), device=dev)
+			out[key]["e2e"] = {"value": 6 * N * N / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": W * H * bpp, "d2h_bytes_per_step": 6 * N * N * bpp, "readback_verified": bool(np.array_equal(ref, d_host)),
+							   "path": "cacao_img_equirect_to_cube(CACAO_MEM_HOST): pinned host -> row-chunk upload, units resampled as their source window lands, rows read back while later chunks go up -> pinned host"}
+			device.host_free(sp), device.host_free(dp)
 		del src, dst
 
 	if world == 1:
 		equirect("cfg1_equirect_2048x1024_rgba8_to_6x512", 2048, 1024, 512, 4, FMT_U8, 1, 50, "14.7 MB problem: fits L2, launch-latency bound")
-		equirect("cfg3_equirect_8192x4096_rgba32f_to_6x2048", 8192, 4096, 2048, 4, FMT_F32, 4, 20)
+		equirect("cfg3_equirect_8192x4096_rgba32f_to_6x2048", 8192, 4096, 2048, 4, FMT_F32, 4, 20, e2e=True)
 	equirect("cfg5_equirect_16384x8192_rgba32f_to_6x4096", 16384, 8192, 4096, 4, FMT_F32, 4, 10)
 
 	# cfg4: 4096 x 4096^2 RGB8 -> RGBA8 / RGBA32F sharded by image index.  206 GB of input and up to

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "cacao_device.cuh"
 #include "projection.cuh"
@@ -592,25 +593,44 @@ namespace cacao {
 		prm.src_row0 = src_row0;
 		prm.src_rows = src_rows;
 		prm.pc = make_proj_const(N, W, H);
-		uint32_t next = 0, split_from = 0;
-		while(next < n_units) {
-			prm.n_units = 0;
-			while(next < n_units && prm.n_units < kMaxUnitsPerLaunch) {
-				CubeUnit u = units[next];
-				if(u.row_end > N) u.row_end = N;
-				if(u.row_begin < split_from) u.row_begin = split_from;
-				// gridDim.y is limited to 65535 blocks of 4 rows: a taller unit continues in the next slot
-				constexpr uint32_t kMaxRows = 65535u * 4u;
-				if(u.face < 6 && u.row_begin < u.row_end && u.row_end - u.row_begin > kMaxRows) {
-					split_from = u.row_begin + kMaxRows;
-					u.row_end = split_from;
-				} else {
-					split_from = 0;
-					++next;
-				}
-				if(u.face < 6 && u.row_begin < u.row_end) prm.units[prm.n_units++] = u;
+		// The grid's y extent is that of the tallest unit in a launch, and blocks beyond a shorter unit's
+		// rows exit at once but are not free (a sharded 16384x8192 job whose +-Y bands are half as tall as
+		// its side-face bands lost 5 % to them on two ranks).  So the units of a call are first cut to a
+		// common height -- the shortest unit's, when the heights are within a factor of eight -- then
+		// sorted tallest first, and a launch takes up to kMaxUnitsPerLaunch units no shorter than 4/5
+		// of its first one.  A rank's mixed list of side-face and half-height polar bands then still is
+		// ONE launch without empty blocks.
+		std::vector<CubeUnit> todo;
+		uint32_t hmin = 0xFFFFFFFFu, hmax = 0;
+		for(uint32_t k = 0; k < n_units; ++k) {
+			CubeUnit u = units[k];
+			if(u.row_end > N) u.row_end = N;
+			if(u.face > 5 || u.row_begin >= u.row_end) continue;
+			hmin = std::min(hmin, u.row_end - u.row_begin);
+			hmax = std::max(hmax, u.row_end - u.row_begin);
+			todo.push_back(u);
+		}
+		// gridDim.y is limited to 65535 blocks of at least 4 rows
+		constexpr uint32_t kMaxRows = 65535u * 4u;
+		uint32_t piece = hmax; // target height
+		if(hmax > hmin && hmin >= 16 && hmax / hmin < 8) piece = hmin;
+		if(piece > kMaxRows) piece = kMaxRows;
+		if(piece < hmax) {
+			std::vector<CubeUnit> cut;
+			for(const CubeUnit& u : todo) {
+				const uint32_t rows = u.row_end - u.row_begin;
+				const uint32_t parts = std::max(1u, (rows + piece / 2) / piece);
+				const uint32_t each = (rows + parts - 1) / parts;
+				for(uint32_t r = u.row_begin; r < u.row_end; r += each) cut.push_back({u.face, r, std::min(u.row_end, r + each)});
 			}
-			if(prm.n_units == 0) continue;
+			todo.swap(cut);
+		}
+		std::stable_sort(todo.begin(), todo.end(), [](const CubeUnit& x, const CubeUnit& y) { return x.row_end - x.row_begin > y.row_end - y.row_begin; });
+		size_t next = 0;
+		while(next < todo.size()) {
+			prm.n_units = 0;
+			const uint64_t tallest = todo[next].row_end - todo[next].row_begin;
+			while(next < todo.size() && prm.n_units < kMaxUnitsPerLaunch && 5ull * (todo[next].row_end - todo[next].row_begin) >= 4ull * tallest) prm.units[prm.n_units++] = todo[next++];
 			cudaError_t e;
 			switch(fmt) {
 				case CACAO_FMT_U8: e = launch_ch<CACAO_FMT_U8>(src, dst, ch, prm, stream); break;

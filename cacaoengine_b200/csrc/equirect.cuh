@@ -9,7 +9,7 @@
 
 namespace cacao {
 
-	constexpr int kMaxUnitsPerLaunch = 8;
+	constexpr int kMaxUnitsPerLaunch = 32;
 
 	// one work unit = rows [row_begin,row_end) of one face
 	struct CubeUnit {
@@ -25,7 +25,8 @@ namespace cacao {
 		ProjConst pc;
 	};
 
-	// Enqueue the resampling of a list of (face, row band) units: ceil(n/8) launches, *launches gets the count.
+	// Enqueue the resampling of a list of (face, row band) units in as few launches as their heights allow
+	// (normally one), *launches gets the count.
 	cudaError_t equirect_launch_units(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, const CubeUnit* units, uint32_t n_units, cudaStream_t stream, unsigned* launches);
 
 	// Enqueue the resampling of rows [row_begin,row_end) of every face in face_mask (one launch).

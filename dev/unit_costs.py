@@ -17,13 +17,13 @@ def t(units, reps=10):
 	for _ in range(reps): device.equirect_to_cube_units(src.data_ptr(), W, H, 4, FMT_F32, dst.data_ptr(), N, units, stream=stream)
 	b.record(); torch.cuda.synchronize()
 	return a.elapsed_time(b) / reps
-for bands in (4, 8):
-	units = sharding.cube_units(N, bands)
+for bands in (2, 4, 8):
+	units = sharding.cube_units(N, bands, 2)
 	cost = {(u.face, u.row_begin): t([u]) for u in units}
 	print(f"bands={bands}: per-unit ms by face:")
 	for f in range(6):
 		print("  face", f, " ".join(f"{cost[(u.face,u.row_begin)]*1e3:6.1f}" for u in units if u.face == f), "us")
-	for world in (8,):
+	for world in (2, 4, 8):
 		sums = []
 		for r in range(world):
 			mine = sharding.units_for_rank(r, world, N, bands)

@@ -147,8 +147,8 @@ typedef struct cacao_cube_unit {
 } cacao_cube_unit;
 
 /* The same resampling for an explicit list of work units -- what one GPU of a sharded job owns
- * (cacaoengine_b200/sharding.py deals units out) -- in ceil(n_units/8) kernel launches instead of
- * one per unit.  src/dst/window arguments as above; device memory only. */
+ * (cacaoengine_b200/sharding.py deals units out) -- normally in ONE kernel launch (units are cut to a
+ * common height; up to 32 pieces per launch) instead of one per unit.  src/dst/window arguments as above; device memory only. */
 int cacao_img_equirect_to_cube_units(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0,
 									 uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N,
 									 const cacao_cube_unit* units, uint32_t n_units, void* stream);

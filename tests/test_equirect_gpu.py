@@ -130,8 +130,8 @@ def test_face_masks_row_bands_and_source_windows(oracle):
 
 
 def test_unit_list_launch_matches_per_unit_calls(oracle):
-	"""cacao_img_equirect_to_cube_units: a rank's whole unit list (more than 8 -> two launches) in one
-	call equals the oracle on exactly those rows and writes nothing else."""
+	"""cacao_img_equirect_to_cube_units: a rank's whole unit list in one call (one launch when the units
+	are equally tall) equals the oracle on exactly those rows and writes nothing else."""
 	from cacaoengine_b200 import _capi as c, device, sharding
 
 	W, H, N, ch, fmt = 300, 150, 70, 3, c.FMT_U16
@@ -146,11 +146,33 @@ def test_unit_list_launch_matches_per_unit_calls(oracle):
 	device.upload(b.ptr, np.zeros_like(want))
 	before = device.launch_count()
 	device.equirect_to_cube_units(a.ptr, W, H, ch, fmt, b.ptr, N, units)
-	assert device.launch_count() - before == 2
+	assert device.launch_count() - before == 1
 	got = np.empty_like(want)
 	device.download(got, b.ptr)
-	a.free(), b.free()
 	assert same_bits(got, want)
+	# a launch's grid is as tall as its tallest unit, so very different heights go to separate launches
+	# (70 | 35, 34 | 10 rows -> three); heights within a factor of eight are cut to a common height instead
+	mixed = [(0, 0, 70), (3, 10, 20), (1, 0, 35), (2, 36, 70)]
+	want2 = np.zeros_like(want)
+	for f, r0, r1 in mixed:
+		oracle.equirect_to_cube(src, W, H, ch, fmt, N, face_mask=1 << f, row_begin=r0, row_end=r1, out=want2)
+	device.upload(b.ptr, np.zeros_like(want))
+	before = device.launch_count()
+	device.equirect_to_cube_units(a.ptr, W, H, ch, fmt, b.ptr, N, mixed)
+	assert device.launch_count() - before == 3
+	device.download(got, b.ptr)
+	assert same_bits(got, want2)
+	similar = [(0, 0, 70), (1, 0, 35), (2, 36, 70), (4, 3, 40)]  # 70 -> 2 x 35: one launch of five pieces
+	want3 = np.zeros_like(want)
+	for f, r0, r1 in similar:
+		oracle.equirect_to_cube(src, W, H, ch, fmt, N, face_mask=1 << f, row_begin=r0, row_end=r1, out=want3)
+	device.upload(b.ptr, np.zeros_like(want))
+	before = device.launch_count()
+	device.equirect_to_cube_units(a.ptr, W, H, ch, fmt, b.ptr, N, similar)
+	assert device.launch_count() - before == 1
+	device.download(got, b.ptr)
+	a.free(), b.free()
+	assert same_bits(got, want3)
 	with pytest.raises(c.CacaoError):
 		device.equirect_to_cube_units(1, W, H, ch, fmt, 1, N, [(7, 0, 1)])
 
