@@ -220,33 +220,50 @@ def test_python_mirror_equirect(oracle):
 	assert same_bits(out, oracle.equirect_to_cube(src, W, H, 3, ce.FMT_U16, N))
 
 
-def test_cfg3_shape_band_sample(oracle):
-	"""BASELINE config 3 at full size (8192x4096 RGBA32F -> 6x2048^2) on the device; three row bands
-	per face are compared with the oracle bit for bit, and the whole cube is checked through a
-	size-independent property: producing it as 6x4 separate (face, band) launches gives the same
-	checksum as one launch."""
-	from cacaoengine_b200 import _capi as c, device
+@pytest.mark.parametrize("W,H,N,seed", [(8192, 4096, 2048, 0xC0FFEE + 3), (16384, 8192, 4096, 0xC0FFEE + 5)], ids=["cfg3", "cfg5"])
+def test_full_size_shapes_band_sample(oracle, W, H, N, seed):
+	"""BASELINE configs 3 and 5 at full size (8192x4096 -> 6x2048^2, 16384x8192 -> 6x4096^2, RGBA32F) on
+	the device; three row bands per face are compared with the oracle bit for bit, and the whole cube
+	is checked through size-independent properties: producing it as 6x4 separate (face, band)
+	launches, as one cost-dealt unit list per rank of an 8-rank job, and through the pipelined
+	host-memory call gives the same checksum as one launch."""
+	from cacaoengine_b200 import _capi as c, device, sharding
 
-	W, H, N, ch, fmt = 8192, 4096, 2048, 4, c.FMT_F32
+	ch, fmt = 4, c.FMT_F32
 	src = DevBuf(W * H * 16)
-	device.synth(src.ptr, W * H * 4, fmt, 4, 0xC0FFEE + 3)
+	device.synth(src.ptr, W * H * 4, fmt, 4, seed)
 	cube = DevBuf(6 * N * N * 16)
 	device.equirect_to_cube(src.ptr, W, H, ch, fmt, cube.ptr, N)
 	whole = device.checksum(cube.ptr, 6 * N * N * 16)
-	host_src = oracle.synth(W * H * 4, fmt, 4, 0xC0FFEE + 3)
-	for (r0, r1) in ((0, 8), (1020, 1028), (2040, 2048)):
+	host_src = oracle.synth(W * H * 4, fmt, 4, seed)
+	for (r0, r1) in ((0, 8), (N // 2 - 4, N // 2 + 4), (N - 8, N)):
 		want = oracle.equirect_to_cube(host_src, W, H, ch, fmt, N, row_begin=r0, row_end=r1)
 		for f in range(6):
 			got = np.empty((r1 - r0) * N * 4, np.float32)
 			off = (f * N + r0) * N
 			device.download(got, cube.ptr + off * 16)
 			assert same_bits(got, want[off * 4: off * 4 + got.size]), (f, r0)
+		del want
 	cube2 = DevBuf(6 * N * N * 16)
 	for f in range(6):
 		for b in range(4):
-			device.equirect_to_cube(src.ptr, W, H, ch, fmt, cube2.ptr, N, 1 << f, b * 512, (b + 1) * 512)
+			device.equirect_to_cube(src.ptr, W, H, ch, fmt, cube2.ptr, N, 1 << f, b * (N // 4), (b + 1) * (N // 4))
 	assert device.checksum(cube2.ptr, 6 * N * N * 16) == whole
-	for x in (src, cube, cube2):
+	# the eight unit lists of a sharded job (mixed side / half-height polar bands, one launch each)
+	device.upload(cube2.ptr, np.zeros(1 << 20, np.uint8))
+	for rank in range(8):
+		device.equirect_to_cube_units(src.ptr, W, H, ch, fmt, cube2.ptr, N, sharding.units_for_rank(rank, 8, N))
+	assert device.checksum(cube2.ptr, 6 * N * N * 16) == whole
+	cube2.free()
+	# host -> host through pinned buffers: the pipelined upload / resample / readback
+	sp, s_host = device.host_alloc(W * H * 16)
+	dp, d_host = device.host_alloc(6 * N * N * 16)
+	s_host[:] = host_src.view(np.uint8)
+	device.equirect_to_cube(sp, W, H, ch, fmt, dp, N, mem=c.MEM_HOST)
+	device.upload(cube.ptr, d_host)
+	assert device.checksum(cube.ptr, 6 * N * N * 16) == whole
+	device.host_free(sp), device.host_free(dp)
+	for x in (src, cube):
 		x.free()
 
 
