@@ -1,7 +1,7 @@
 """Small driver for ncu captures: launches each hot kernel of the BASELINE configs a few times on
 device-resident synthetic data, through the C ABI only (no torch).  Usage:
 
-    python profiles/prof_driver.py [cfg2] [cfg3] [cfg4a] [cfg4b] [lut] [--reps N]
+    python profiles/prof_driver.py [cfg1] [cfg2] [cfg3] [cfg5] [rgb32f] [cfg4a] [cfg4b] [lut] [--reps N]
 """
 import os
 import sys
@@ -33,6 +33,14 @@ def main():
 			device.equirect_to_cube(a, W, H, 4, FMT_F32, b, N)
 		device.sync()
 		device.free(a), device.free(b)
+	for key, (W, H, N, ch, fmt, bps) in {"cfg1": (2048, 1024, 512, 4, FMT_U8, 1), "cfg5": (16384, 8192, 4096, 4, FMT_F32, 4), "rgb32f": (8192, 4096, 2048, 3, FMT_F32, 4)}.items():
+		if key in which:
+			a, b = device.malloc(W * H * ch * bps), device.malloc(6 * N * N * ch * bps)
+			device.synth(a, W * H * ch, fmt, ch, 2)
+			for _ in range(reps):
+				device.equirect_to_cube(a, W, H, ch, fmt, b, N)
+			device.sync()
+			device.free(a), device.free(b)
 	if "cfg4a" in which or "cfg4b" in which:
 		px, ring = 4096 * 4096, 16
 		a = device.malloc(ring * px * 3)

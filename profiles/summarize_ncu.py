@@ -31,6 +31,12 @@ TRAFFIC_KEYS = {
 	"convert_wide_kernel<1, 0, 4, 3": "lut_64x_2048sq_rgba16_to_rgb8",
 	"equirect_kernel<3, 4": "cfg3_equirect_8192x4096_rgba32f_to_6x2048",
 }
+# equirect launches are told apart by their grid (same kernel for cfg3 and cfg5)
+GRID_KEYS = {
+	("equirect_kernel<3, 4", "(128, 64, 6)"): "cfg3_equirect_8192x4096_rgba32f_to_6x2048",
+	("equirect_kernel<3, 4", "(256, 128, 6)"): "cfg5_equirect_16384x8192_rgba32f_to_6x4096",
+	("equirect_kernel<0, 4", "(32, 16, 6)"): "cfg1_equirect_2048x1024_rgba8_to_6x512",
+}
 UNIT_SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0, "msecond": 1e-3, "usecond": 1e-6, "nsecond": 1e-9, "second": 1.0}
 
 
@@ -47,7 +53,14 @@ def main():
 		for r in rows[2:]:
 			name = r[idx["Kernel Name"]]
 			w.writerow([name[:90]] + [r[idx[m]] for m in METRICS if m in idx])
-			for frag, key in TRAFFIC_KEYS.items():
+			grid = r[idx["Grid Size"]].replace(" ", "").replace(",", ", ") if "Grid Size" in idx else ""
+			keys = dict(TRAFFIC_KEYS)
+			for (frag, g), key in GRID_KEYS.items():
+				if frag in name:
+					keys.pop(frag, None)
+					if g == grid:
+						keys[frag] = key
+			for frag, key in keys.items():
 				if frag in name:
 					rd = float(r[idx["dram__bytes_read.sum"]]) * UNIT_SCALE[units[idx["dram__bytes_read.sum"]]]
 					wr = float(r[idx["dram__bytes_write.sum"]]) * UNIT_SCALE[units[idx["dram__bytes_write.sum"]]]
