@@ -94,18 +94,24 @@ namespace cacao {
 			const uint32_t o = static_cast<uint32_t>(off) & 7u;
 			const bool e = (o & 4u) != 0;
 			if constexpr(sb == 4) {
-				// 24 bytes at a 4-byte-aligned offset: words q[e .. e+5] of the window
-				const uint2 q01 = __ldg(reinterpret_cast<const uint2*>(base));
-				const uint2 q23 = __ldg(reinterpret_cast<const uint2*>(base + 8));
-				const uint2 q45 = __ldg(reinterpret_cast<const uint2*>(base + 16));
-				uint32_t q6 = 0;
-				if(e) q6 = __ldg(reinterpret_cast<const uint32_t*>(base + 24));
-				a[0] = __uint_as_float(e ? q01.y : q01.x);
-				a[1] = __uint_as_float(e ? q23.x : q01.y);
-				a[2] = __uint_as_float(e ? q23.y : q23.x);
-				b[0] = __uint_as_float(e ? q45.x : q23.y);
-				b[1] = __uint_as_float(e ? q45.y : q45.x);
-				b[2] = __uint_as_float(e ? q6 : q45.y);
+				// 24 bytes at a 4-byte-aligned offset: words q[o .. o+5] of the 16-byte-aligned window, o in 0..3
+				const uint8_t* b16 = src + (off & ~static_cast<size_t>(15));
+				const uint32_t o4 = (static_cast<uint32_t>(off) & 15u) >> 2;
+				const uint4 lo = __ldg(reinterpret_cast<const uint4*>(b16));
+				const uint4 hi = __ldg(reinterpret_cast<const uint4*>(b16 + 16));
+				uint32_t q8 = 0;
+				if(o4 == 3u) q8 = __ldg(reinterpret_cast<const uint32_t*>(b16 + 32));
+				const uint32_t q[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, q8};
+				const bool s1 = (o4 & 1u) != 0, s2 = (o4 & 2u) != 0;
+				uint32_t u[8];
+#pragma unroll
+				for(int k = 0; k < 8; ++k) u[k] = s1 ? q[k + 1] : q[k];
+				a[0] = __uint_as_float(s2 ? u[2] : u[0]);
+				a[1] = __uint_as_float(s2 ? u[3] : u[1]);
+				a[2] = __uint_as_float(s2 ? u[4] : u[2]);
+				b[0] = __uint_as_float(s2 ? u[5] : u[3]);
+				b[1] = __uint_as_float(s2 ? u[6] : u[4]);
+				b[2] = __uint_as_float(s2 ? u[7] : u[5]);
 			} else if constexpr(sb == 2) {
 				// 12 bytes at a 2-byte-aligned offset: at most 18 bytes into the window
 				const uint2 q01 = __ldg(reinterpret_cast<const uint2*>(base));
