@@ -6,7 +6,10 @@
 #include <array>
 #include <cstdlib>
 #include <filesystem>
+#include <functional>
+#include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "toolutil.hpp"
@@ -21,6 +24,26 @@
 inline const std::array<const char*, 6> kFaceNames = {"right", "left", "up", "down", "front", "back"};
 // keys of the unpacked cubemap definition (.ajc) in the same slot order (UnpackedDecode.cpp:29-40)
 inline const std::array<const char*, 6> kAjcKeys = {"right", "left", "top", "bottom", "front", "back"};
+
+// The six faces are independent and their codecs (zlib, VP8L) are sequential host code: run fn(0..5)
+// on six threads.  Returns the first failure in face order ("" when all went well) so the caller can
+// report it the usual way -- CUBE_ERROR must not be raised from a worker thread.
+inline std::string ForEachFace(const std::function<void(int)>& fn) {
+	std::array<std::string, 6> errors;
+	std::vector<std::thread> pool;
+	for(int i = 0; i < 6; ++i)
+		pool.emplace_back([&errors, &fn, i] {
+			try {
+				fn(i);
+			} catch(const std::exception& e) {
+				errors[i] = e.what()[0] ? e.what() : "unknown error";
+			}
+		});
+	for(auto& t : pool) t.join();
+	for(const auto& e : errors)
+		if(!e.empty()) return e;
+	return "";
+}
 
 struct ProjectOptions {
 	std::filesystem::path input;

@@ -34,6 +34,7 @@ int RunCreate(const CreateOptions& opt) {
 	//Decode the definition and the six faces
 	VLOG("Loading input files:")
 	std::array<libcacaoimage::Image, 6> faces;
+	std::array<std::vector<unsigned char>, 6> fileBytes;
 	try {
 		const std::vector<unsigned char> text = readAll(in);
 		const std::array<std::string, 6> paths = xjc::ReadAjc(std::string(text.begin(), text.end()));
@@ -52,13 +53,15 @@ int RunCreate(const CreateOptions& opt) {
 				CUBE_ERROR("Failed to open face file stream for reading!")
 			}
 			VLOG("Done.")
-			const std::vector<unsigned char> blob = readAll(fs);
-			if(blob.empty()) throw std::runtime_error(std::string(streamNames[i]) + " face data input stream is invalid!");
-			faces[i] = xjc::DecodeFace(blob);
+			fileBytes[i] = readAll(fs);
+			if(fileBytes[i].empty()) throw std::runtime_error(std::string(streamNames[i]) + " face data input stream is invalid!");
 		}
 	} catch(const std::runtime_error& e) {
 		CUBE_ERROR(e.what());
 	}
+	// the six decodes are independent (inflate / VP8L are sequential per image): one thread each
+	const std::string derr = ForEachFace([&](int i) { faces[i] = xjc::DecodeFace(fileBytes[i]); });
+	if(!derr.empty()) CUBE_ERROR(derr)
 
 	//Optional GPU conversion to what the engine wants (one fused kernel per face)
 	if(opt.toRgb8) {
@@ -75,14 +78,15 @@ int RunCreate(const CreateOptions& opt) {
 	//Encode the file
 	VLOG_NONL("Generating output... ")
 	std::vector<unsigned char> packed;
+	std::array<std::vector<unsigned char>, 6> blobs;
+	const std::string eerr = ForEachFace([&](int i) {
+		// validation of PackedEncode.cpp:20-23
+		if(!(faces[i].w > 0 && faces[i].h > 0)) throw std::runtime_error("Cubemap face for packed encoding has invalid dimensions or channel count!");
+		if(faces[i].data.empty()) throw std::runtime_error("Cubemap face for packed encoding has empty data buffer!");
+		blobs[i] = xjc::EncodeFaceWebP(faces[i]);
+	});
+	if(!eerr.empty()) CUBE_ERROR(eerr)
 	try {
-		std::array<std::vector<unsigned char>, 6> blobs;
-		for(int i = 0; i < 6; ++i) {
-			// validation of PackedEncode.cpp:20-23
-			if(!(faces[i].w > 0 && faces[i].h > 0)) throw std::runtime_error("Cubemap face for packed encoding has invalid dimensions or channel count!");
-			if(faces[i].data.empty()) throw std::runtime_error("Cubemap face for packed encoding has empty data buffer!");
-			blobs[i] = xjc::EncodeFaceWebP(faces[i]);
-		}
 		packed = xjc::WriteContainer(xjc::MakeCubemapContainer(blobs));
 	} catch(const std::runtime_error& e) {
 		CUBE_ERROR(e.what())

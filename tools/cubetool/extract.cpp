@@ -4,6 +4,7 @@
 // -A/--all-faces or -f/--face NAME..., -o DIR (created when missing), output files
 // <stem>_<face>.png.  One addition: --flip mirrors the rows on the GPU before writing (the
 // orientation the OpenGL backend uploads, engine/src/opengl/impls/OpenGLCubemap.cpp:25).
+#include <algorithm>
 #include <fstream>
 #include <iterator>
 #include <sstream>
@@ -35,31 +36,32 @@ int RunExtract(const ExtractOptions& optIn) {
 	//Decode the file
 	VLOG_NONL("Decoding input file... ")
 	std::array<libcacaoimage::Image, 6> decoded;
+	std::array<std::vector<unsigned char>, 6> blobs;
 	try {
 		const std::vector<unsigned char> file((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
 		const xjc::Container pc = xjc::ReadContainer(file);
-		const std::array<std::vector<unsigned char>, 6> blobs = xjc::SplitCubemapPayload(pc);
-		for(int i = 0; i < 6; ++i) decoded[i] = xjc::DecodeFace(blobs[i]);
+		blobs = xjc::SplitCubemapPayload(pc);
 	} catch(const std::runtime_error& e) {
 		CUBE_ERROR(e.what());
 	}
+	// all six are decoded, as PackedDecoder::DecodeCubemap does -- a damaged face fails the command even
+	// when it was not asked for -- one thread per face
+	const std::string derr = ForEachFace([&](int i) { decoded[i] = xjc::DecodeFace(blobs[i]); });
+	if(!derr.empty()) CUBE_ERROR(derr)
 	VLOG("Done.")
 
 	//Extract the requested faces
 	const std::string original = opt.input.filename().stem().string();
 	for(int i : opt.faces) {
-		std::stringstream fname;
-		fname << original << "_" << kFaceNames[i] << ".png";
-		const std::filesystem::path outfile = opt.outDir / fname.str();
-		VLOG("Opening output stream for " << kFaceNames[i] << ": " << outfile << "... ")
-		VLOG("Writing output... ")
-		try {
-			libcacaoimage::Image face = decoded[i];
-			if(opt.flip) face = libcacaoimage::Flip(face);
-			cubeio::WriteImage(libcacaoimage::FromImage(face), outfile, "png");
-		} catch(const std::runtime_error& e) {
-			CUBE_ERROR(e.what())
-		}
+		VLOG("Opening output stream for " << kFaceNames[i] << ": " << (opt.outDir / (original + "_" + kFaceNames[i] + ".png")) << "... ")
 	}
+	VLOG("Writing output... ")
+	const std::string werr = ForEachFace([&](int i) {
+		if(std::find(opt.faces.begin(), opt.faces.end(), i) == opt.faces.end()) return;
+		libcacaoimage::Image face = decoded[i];
+		if(opt.flip) face = libcacaoimage::Flip(face);
+		cubeio::WriteImage(libcacaoimage::FromImage(face), opt.outDir / (original + "_" + kFaceNames[i] + ".png"), "png");
+	});
+	if(!werr.empty()) CUBE_ERROR(werr)
 	return 0;
 }

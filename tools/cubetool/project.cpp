@@ -82,18 +82,14 @@ int RunProject(const ProjectOptions& opt) {
 	const std::string stem = opt.input.filename().stem().string();
 	const std::string format = opt.format.empty() ? cubeio::DefaultFormat(faces[0]) : opt.format;
 	std::array<std::string, 6> names;
-	for(int i = 0; i < 6; ++i) {
-		names[i] = stem + "_" + kFaceNames[i] + "." + format;
-		if(!opt.faces.empty() && std::find(opt.faces.begin(), opt.faces.end(), i) == opt.faces.end()) continue;
-		const std::filesystem::path outfile = opt.outDir / names[i];
-		VLOG_NONL("Writing " << kFaceNames[i] << " face to " << outfile << "... ")
-		try {
-			cubeio::WriteImage(faces[i], outfile, format);
-		} catch(const std::runtime_error& e) {
-			CUBE_ERROR(e.what())
-		}
-		VLOG("Done.")
-	}
+	for(int i = 0; i < 6; ++i) names[i] = stem + "_" + kFaceNames[i] + "." + format;
+	VLOG_NONL("Writing face files to " << opt.outDir << "... ")
+	const std::string werr = ForEachFace([&](int i) {
+		if(!opt.faces.empty() && std::find(opt.faces.begin(), opt.faces.end(), i) == opt.faces.end()) return;
+		cubeio::WriteImage(faces[i], opt.outDir / names[i], format);
+	});
+	if(!werr.empty()) CUBE_ERROR(werr)
+	VLOG("Done.")
 	if(opt.faces.empty()) {
 		const std::filesystem::path ajc = opt.outDir / (stem + ".ajc");
 		std::ofstream def(ajc);
