@@ -296,4 +296,88 @@ namespace libcacaoimage {
 			if(!e.empty()) throw std::runtime_error("libcacaoimage-b200: " + e);
 		return faces;
 	}
+	// ---- DeviceImage ---------------------------------------------------------------------------
+
+	namespace {
+		std::shared_ptr<void> device_alloc(int device, std::size_t bytes) {
+			void* p = nullptr;
+			check(cacao_img_malloc(device, &p, bytes));
+			return std::shared_ptr<void>(p, [device](void* q) { cacao_img_free(device, q); });
+		}
+	}
+
+	DeviceImage::DeviceImage(unsigned int w, unsigned int h, Image::Layout layout, SampleFormat format, int device) : w_(w), h_(h), layout_(layout), format_(format), device_(device) {
+		if(w == 0 || h == 0) check(CACAO_E_ZERO_DIM);
+		owner_ = device_alloc(device, Bytes());
+		ptr_ = owner_.get();
+	}
+
+	DeviceImage DeviceImage::Upload(const ImageEx& src, int device) {
+		DeviceImage d(src.w, src.h, src.layout, src.format, device);
+		if(src.data.size() < d.Bytes()) throw std::runtime_error("Image data buffer is smaller than w * h * channels * bytes per channel!");
+		check(cacao_img_upload(device, d.ptr_, src.data.data(), d.Bytes(), nullptr));
+		check(cacao_img_sync(device, nullptr)); // src may go away as soon as this returns
+		return d;
+	}
+
+	DeviceImage DeviceImage::Upload(const Image& src, int device) {
+		if(!(src.bitsPerChannel == 8 || src.bitsPerChannel == 16)) check(CACAO_E_BAD_DEPTH);
+		DeviceImage d(src.w, src.h, src.layout, src.bitsPerChannel == 16 ? SampleFormat::U16 : SampleFormat::U8, device);
+		if(src.data.size() < d.Bytes()) throw std::runtime_error("Image data buffer is smaller than w * h * channels * bytes per channel!");
+		check(cacao_img_upload(device, d.ptr_, src.data.data(), d.Bytes(), nullptr));
+		check(cacao_img_sync(device, nullptr));
+		return d;
+	}
+
+	ImageEx DeviceImage::Download() const {
+		if(Empty()) check(CACAO_E_EMPTY);
+		ImageEx out;
+		out.w = w_;
+		out.h = h_;
+		out.layout = layout_;
+		out.format = format_;
+		out.data.resize(Bytes());
+		check(cacao_img_download(device_, out.data.data(), ptr_, Bytes(), nullptr));
+		check(cacao_img_sync(device_, nullptr));
+		return out;
+	}
+
+	DeviceImage DeviceImage::Convert(Image::Layout layout, SampleFormat format, ConvertMode mode) const {
+		if(Empty()) check(CACAO_E_EMPTY);
+		if(layout == layout_ && format == format_) check(CACAO_E_SAME_LAYOUT);
+		DeviceImage out(w_, h_, layout, format, device_);
+		check(cacao_img_convert(device_, ptr_, out.ptr_, static_cast<uint64_t>(w_) * h_, static_cast<int>(layout_), static_cast<int>(layout), static_cast<int>(format_), static_cast<int>(format), static_cast<int>(mode), CACAO_MEM_DEVICE, nullptr));
+		return out;
+	}
+
+	DeviceImage DeviceImage::ToRGB8() const {
+		if(layout_ == Image::Layout::RGB && format_ == SampleFormat::U8) return *this;
+		return Convert(Image::Layout::RGB, SampleFormat::U8);
+	}
+
+	DeviceImage DeviceImage::Flip() const {
+		if(Empty()) check(CACAO_E_EMPTY);
+		if(h_ == 1) return *this;
+		DeviceImage out(w_, h_, layout_, format_, device_);
+		check(cacao_img_flip_rows(device_, ptr_, out.ptr_, w_, h_, static_cast<uint32_t>(BytesPerPixel(layout_, format_)), CACAO_MEM_DEVICE, nullptr));
+		return out;
+	}
+
+	std::array<DeviceImage, 6> DeviceImage::EquirectToCubemap(unsigned int faceSize) const {
+		if(Empty()) check(CACAO_E_EMPTY);
+		if(faceSize == 0) check(CACAO_E_ZERO_DIM);
+		const std::size_t face_bytes = static_cast<std::size_t>(faceSize) * faceSize * BytesPerPixel(layout_, format_);
+		std::shared_ptr<void> cube = device_alloc(device_, 6 * face_bytes);
+		check(cacao_img_equirect_to_cube(device_, ptr_, w_, h_, 0, h_, static_cast<int>(layout_), static_cast<int>(format_), cube.get(), faceSize, 0x3Fu, 0, faceSize, CACAO_MEM_DEVICE, nullptr));
+		std::array<DeviceImage, 6> faces;
+		for(unsigned f = 0; f < 6; ++f) {
+			faces[f].owner_ = cube;
+			faces[f].ptr_ = static_cast<unsigned char*>(cube.get()) + f * face_bytes;
+			faces[f].w_ = faces[f].h_ = faceSize;
+			faces[f].layout_ = layout_;
+			faces[f].format_ = format_;
+			faces[f].device_ = device_;
+		}
+		return faces;
+	}
 }

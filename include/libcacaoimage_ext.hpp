@@ -6,6 +6,7 @@
 
 #include <array>
 #include <cstdint>
+#include <memory>
 #include <vector>
 
 #include "cacao_img.h"
@@ -48,4 +49,47 @@ namespace libcacaoimage {
 
 	// Flip for any sample format.
 	ImageEx Flip(const ImageEx& src);
+
+	// An image that lives in the memory of one GPU.  The host API above pays one PCIe round trip per
+	// call; a chain such as "project, then convert, then flip" (what `ce-cubetool project --depth 8
+	// --layout rgb --flip` does, or the engine's 16 -> 8 bit, -> RGB, Flip sequence of
+	// engine/src/core/Cubemap.cpp:28-31 + engine/src/opengl/impls/OpenGLCubemap.cpp:25) uploads once,
+	// runs its kernels back to back on the device and downloads once.  Copies share the pixels
+	// (reference-counted device allocation); every operation returns a new image and leaves its input
+	// untouched, like the host functions.  Work is enqueued in order on the device's default stream;
+	// Download() returns when the pixels are in host memory.  Same exceptions as the host API.
+	class DeviceImage {
+	  public:
+		DeviceImage() = default;
+		// uninitialised pixels
+		DeviceImage(unsigned int w, unsigned int h, Image::Layout layout, SampleFormat format, int device = -1);
+
+		static DeviceImage Upload(const ImageEx& src, int device = -1);
+		static DeviceImage Upload(const Image& src, int device = -1);
+		ImageEx Download() const;
+
+		DeviceImage Convert(Image::Layout layout, SampleFormat format, ConvertMode mode = ConvertMode::ReferenceExact) const;
+		DeviceImage ToRGB8() const; // U16 -> U8 through the engine's table, then -> RGB, one kernel
+		DeviceImage Flip() const;
+		// six faces that are views of ONE contiguous face-major allocation (+X,-X,+Y,-Y,+Z,-Z) -- the
+		// layout the Vulkan backend concatenates by hand (engine/src/vulkan/impls/VulkanCubemap.cpp:30-41)
+		std::array<DeviceImage, 6> EquirectToCubemap(unsigned int faceSize) const;
+
+		unsigned int Width() const { return w_; }
+		unsigned int Height() const { return h_; }
+		Image::Layout Layout() const { return layout_; }
+		SampleFormat Format() const { return format_; }
+		int Device() const { return device_; }
+		void* Data() const { return ptr_; } // device pointer, tightly packed rows, top row first
+		std::size_t Bytes() const { return static_cast<std::size_t>(w_) * h_ * BytesPerPixel(layout_, format_); }
+		bool Empty() const { return ptr_ == nullptr; }
+
+	  private:
+		std::shared_ptr<void> owner_; // the allocation (possibly shared with sibling views)
+		void* ptr_ = nullptr;
+		unsigned int w_ = 0, h_ = 0;
+		Image::Layout layout_ = Image::Layout::RGBA;
+		SampleFormat format_ = SampleFormat::U8;
+		int device_ = -1;
+	};
 }

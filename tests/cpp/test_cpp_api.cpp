@@ -138,6 +138,38 @@ int main(int argc, char** argv) {
 	pano.data.assign(64 * 32 * 3, 99);
 	const auto cube = EquirectToCubemap(pano, 8);
 	for(const auto& f : cube) EXPECT(f.w == 8 && f.h == 8 && f.data.size() == 8 * 8 * 3 && f.data[0] == 99 && f.data.back() == 99);
+	// the same over several devices (latitude-ordered unit runs, one pipelined call per device)
+	{
+		ImageEx noisy;
+		noisy.w = 192;
+		noisy.h = 96;
+		noisy.layout = L::RGBA;
+		noisy.format = SampleFormat::U16;
+		noisy.data.resize(192 * 96 * 8);
+		for(std::size_t b = 0; b < noisy.data.size(); ++b) noisy.data[b] = static_cast<unsigned char>((b * 2654435761u) >> 13);
+		std::vector<int> devs;
+		for(int d = 0; d < n_devices; ++d) devs.push_back(d);
+		const auto one = EquirectToCubemap(noisy, 40);
+		const auto many = EquirectToCubemap(noisy, 40, devs);
+		for(int f = 0; f < 6; ++f) EXPECT(one[f].data == many[f].data && one[f].data.size() == 40 * 40 * 8);
+		// ---- DeviceImage: the same chain without leaving the GPU equals the host calls stage by stage
+		const DeviceImage dpano = DeviceImage::Upload(noisy);
+		EXPECT(dpano.Width() == 192 && dpano.Height() == 96 && dpano.Bytes() == noisy.data.size() && !dpano.Empty());
+		EXPECT(dpano.Download().data == noisy.data);
+		const auto dfaces = dpano.EquirectToCubemap(40);
+		for(int f = 0; f < 6; ++f) {
+			EXPECT(dfaces[f].Download().data == one[f].data);
+			if(f) EXPECT(static_cast<unsigned char*>(dfaces[f].Data()) == static_cast<unsigned char*>(dfaces[0].Data()) + f * dfaces[0].Bytes()); // one contiguous cube
+			const DeviceImage chain = dfaces[f].ToRGB8().Flip();
+			const ImageEx host_chain = Flip(FromImage(ToRGB8(ToImage(one[f]))));
+			EXPECT(chain.Layout() == L::RGB && chain.Format() == SampleFormat::U8 && chain.Download().data == host_chain.data);
+			EXPECT(dfaces[f].Convert(L::RGBA, SampleFormat::F16).Download().data == Convert(one[f], L::RGBA, SampleFormat::F16).data);
+		}
+		EXPECT(thrown([&] { dpano.Convert(L::RGBA, SampleFormat::U16); }) == "Cannot change an image's channel layout to its current layout!");
+		EXPECT(thrown([&] { DeviceImage().Download(); }) == "Cannot flip an image with a zero-sized data buffer!" || !thrown([&] { DeviceImage().Download(); }).empty());
+		DeviceImage copy = dfaces[3]; // shares the allocation; the cube outlives the array it came from
+		EXPECT(copy.Data() == dfaces[3].Data() && copy.Download().data == one[3].data);
+	}
 	std::printf(failures ? "%d FAILURES\n" : "cpp api ok\n", failures);
 	return failures ? 1 : 0;
 }

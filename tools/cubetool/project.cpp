@@ -31,32 +31,7 @@ int RunProject(const ProjectOptions& opt) {
 	const unsigned N = opt.faceSize ? opt.faceSize : pano.w / 4;
 	if(N == 0) CUBE_ERROR("Face size must be at least 1 pixel!")
 
-	//Project
-	std::vector<int> devices;
-	for(int d = 0; d < opt.gpus; ++d) devices.push_back(d);
-	if(devices.size() == 1) devices.clear(); // current device
-	std::array<ImageEx, 6> faces;
-	VLOG_NONL("Projecting onto 6 faces of " << N << "x" << N << " on " << opt.gpus << " GPU(s)... ")
-	const auto t0 = std::chrono::steady_clock::now();
-	try {
-		faces = EquirectToCubemap(pano, N, devices);
-	} catch(const std::runtime_error& e) {
-		CUBE_ERROR(e.what())
-	}
-	const auto t1 = std::chrono::steady_clock::now();
-	VLOG("Done.")
-	double warm = 0.0;
-	if(opt.bench) { // second pass: CUDA contexts, staging buffers and pinned rings exist now
-		const auto w0 = std::chrono::steady_clock::now();
-		try {
-			faces = EquirectToCubemap(pano, N, devices);
-		} catch(const std::runtime_error& e) {
-			CUBE_ERROR(e.what())
-		}
-		warm = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
-	}
-
-	//Optional conversion of the faces (fused layout + depth change, one kernel per face)
+	//What the faces should look like in the end
 	Image::Layout layout = pano.layout;
 	SampleFormat fmt = pano.format;
 	if(opt.layout == "gray") layout = Image::Layout::Grayscale;
@@ -68,13 +43,52 @@ int RunProject(const ProjectOptions& opt) {
 	else if(opt.depth == "f16") fmt = SampleFormat::F16;
 	else if(opt.depth == "f32") fmt = SampleFormat::F32;
 	else if(!opt.depth.empty()) CUBE_ERROR("Invalid depth! (8, 16, f16, f32)")
-	try {
+	const bool post = layout != pano.layout || fmt != pano.format || opt.flip;
+
+	//Project (+ convert + flip).  One GPU with post-processing: the panorama goes up once, the faces
+	//stay on the device through projection, fused layout/depth conversion and row mirror, and come
+	//back once.  Several GPUs (or nothing to post-process): the host-memory call, which shards the
+	//(face, row band) units over the devices and pipelines upload / resampling / readback.
+	std::array<ImageEx, 6> faces;
+	auto run = [&]() {
+		if(opt.gpus == 1 && post) {
+			const DeviceImage dpano = DeviceImage::Upload(pano);
+			const std::array<DeviceImage, 6> dfaces = dpano.EquirectToCubemap(N);
+			for(int i = 0; i < 6; ++i) {
+				DeviceImage f = dfaces[i];
+				if(layout != f.Layout() || fmt != f.Format()) f = f.Convert(layout, fmt);
+				if(opt.flip) f = f.Flip();
+				faces[i] = f.Download();
+			}
+			return;
+		}
+		std::vector<int> devices;
+		for(int d = 0; d < opt.gpus; ++d) devices.push_back(d);
+		if(devices.size() == 1) devices.clear(); // current device
+		faces = EquirectToCubemap(pano, N, devices);
 		for(auto& f : faces) {
 			if(layout != f.layout || fmt != f.format) f = Convert(f, layout, fmt);
 			if(opt.flip) f = Flip(f);
 		}
+	};
+	VLOG_NONL("Projecting onto 6 faces of " << N << "x" << N << " on " << opt.gpus << " GPU(s)... ")
+	const auto t0 = std::chrono::steady_clock::now();
+	try {
+		run();
 	} catch(const std::runtime_error& e) {
 		CUBE_ERROR(e.what())
+	}
+	const auto t1 = std::chrono::steady_clock::now();
+	VLOG("Done.")
+	double warm = 0.0;
+	if(opt.bench) { // second pass: CUDA contexts, staging buffers and pinned rings exist now
+		const auto w0 = std::chrono::steady_clock::now();
+		try {
+			run();
+		} catch(const std::runtime_error& e) {
+			CUBE_ERROR(e.what())
+		}
+		warm = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
 	}
 
 	//Write faces + definition
