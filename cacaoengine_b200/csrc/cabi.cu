@@ -528,7 +528,8 @@ namespace {
 		const bool quirk = (src_fmt == CACAO_FMT_U8 || src_fmt == CACAO_FMT_U16) && src_ch == 1 && dst_ch == 4 && mode == CACAO_MODE_REF_EXACT;
 		// chunk = a multiple of 8192 pixels (every tile size divides it; chunk byte offsets stay
 		// 16-byte aligned) moving about 32 MiB across PCIe in the heavier direction
-		uint64_t chunk_px = (32ull << 20) / (sbpp > dbpp ? sbpp : dbpp);
+		static const uint64_t chunk_mib = getenv("CACAO_CHUNK_MIB") ? strtoull(getenv("CACAO_CHUNK_MIB"), nullptr, 10) : 32;
+		uint64_t chunk_px = (chunk_mib << 20) / (sbpp > dbpp ? sbpp : dbpp);
 		// small jobs still want several chunks in flight so copy-in, DMA, kernel and copy-out overlap
 		const uint64_t sixth = (pixels + 5) / 6;
 		if(sixth < chunk_px) chunk_px = sixth < 131072 ? 131072 : sixth;
