@@ -912,6 +912,61 @@ int cacao_img_shift_left_u16(int device, const void* src, void* dst, uint64_t sa
 	return download_any(c, static_cast<uint8_t*>(dst), c->stage_in[0], samples * 2, c->s_run);
 }
 
+int cacao_img_unpack_texels(int device, const void* src, void* dst, uint64_t texels, const char* hint, int* out_channels, int mem, void* stream) {
+	if(!src || !dst) return fail(CACAO_E_BAD_ARG, "null image pointer");
+	if(mem != CACAO_MEM_HOST && mem != CACAO_MEM_DEVICE) return fail(CACAO_E_BAD_ARG, "unknown memory kind %d", mem);
+	if(!hint || strnlen(hint, 8) < 8) return fail(CACAO_E_BAD_ARG, "texel format hint must have eight characters (four channel letters, four bit counts)");
+	// Model.cpp:250-270: letters -> bit counts, validation, layout
+	int src_index[4] = {-1, -1, -1, -1}, bits[4] = {0, 0, 0, 0}, zeroed = 0;
+	for(int i = 0; i < 4; ++i) {
+		const char* order = "rgba";
+		const char* at = strchr(order, hint[i]);
+		if(!at || hint[i + 4] < '0' || hint[i + 4] > '8') return fail(CACAO_E_BAD_ARG, "texel format hint '%.8s' is not four of r,g,b,a followed by four digits 0-8", hint);
+		const int ch = static_cast<int>(at - order);
+		if(src_index[ch] >= 0) return fail(CACAO_E_BAD_ARG, "texel format hint '%.8s' names a channel twice", hint);
+		src_index[ch] = i;
+		bits[ch] = hint[i + 4] - '0';
+	}
+	for(int ch = 0; ch < 4; ++ch) zeroed += bits[ch] == 0;
+	if(zeroed == 2) return fail(CACAO_E_BAD_ARG, "Invalid zeroed-channel layout for model embedded texture!");                                                         // Model.cpp:259
+	if(zeroed == 1 && bits[3] != 0) return fail(CACAO_E_BAD_ARG, "Only the alpha channel may be zero for a model embedded texture layout with only one zeroed channel!"); // :260
+	if(zeroed == 4) return fail(CACAO_E_BAD_ARG, "Impossible channel layout for model embedded texture!");                                                               // :269
+	TexelPlan plan;
+	plan.out_ch = static_cast<uint32_t>(4 - zeroed);
+	plan.sel = 0;
+	int o = 0;
+	for(int ch = 0; ch < 4; ++ch) {
+		plan.bits[ch] = 8;
+		if(bits[ch] == 0) continue;
+		plan.sel |= static_cast<uint32_t>(src_index[ch]) << (4 * o);
+		plan.bits[o] = static_cast<uint32_t>(bits[ch]);
+		++o;
+	}
+	for(; o < 4; ++o) plan.sel |= 4u << (4 * o); // byte 0 of the zero operand
+	if(out_channels) *out_channels = static_cast<int>(plan.out_ch);
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	if(texels == 0) return CACAO_OK;
+	unsigned launches = 0;
+	if(mem == CACAO_MEM_DEVICE) {
+		cudaError_t e = unpack_texels_launch(src, dst, texels, plan, static_cast<cudaStream_t>(stream), &launches);
+		g_launches.fetch_add(launches, std::memory_order_relaxed);
+		if(e != cudaSuccess) return fail_cuda(e, "texel unpack kernel launch");
+		return CACAO_OK;
+	}
+	std::lock_guard<std::mutex> lock(c->pipe_mutex);
+	rc = ensure_stage(c, texels * 4, texels * plan.out_ch, 1);
+	if(rc) return rc;
+	rc = upload_any(c, c->stage_in[0], static_cast<const uint8_t*>(src), texels * 4, c->s_run);
+	if(rc) return rc;
+	cudaError_t e = unpack_texels_launch(c->stage_in[0], c->stage_out[0], texels, plan, c->s_run, &launches);
+	g_launches.fetch_add(launches, std::memory_order_relaxed);
+	if(e != cudaSuccess) return fail_cuda(e, "texel unpack kernel launch");
+	return download_any(c, static_cast<uint8_t*>(dst), c->stage_out[0], texels * plan.out_ch, c->s_run);
+}
+
 int cacao_img_equirect_src_window(uint32_t W, uint32_t H, uint32_t N, uint32_t face_mask, uint32_t row_begin, uint32_t row_end, uint32_t* src_row0, uint32_t* src_rows) {
 	if(!src_row0 || !src_rows) return fail(CACAO_E_BAD_ARG, "null out-pointer");
 	if(W == 0 || H == 0 || N == 0) return fail(CACAO_E_ZERO_DIM, "equirect: zero-sized image or face");

@@ -66,6 +66,15 @@ namespace cacao {
 		asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 	}
 
+	// 256-bit forms (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256): one whole 32-byte DRAM sector per lane,
+	// p 32-byte aligned
+	__device__ __forceinline__ void ldg256_stream(const void* p, uint32_t* w) {
+		asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+	}
+	__device__ __forceinline__ void stg256_stream(void* p, const uint32_t* w) {
+		asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+	}
+
 	// ---- binary16 <-> binary32, round-to-nearest-even ------------------------------------------
 	// The bits come out of the packed two-lane convert into a 32-bit register on purpose: ptxas
 	// 12.9 miscompiles "cvt.rn.f16.f32 into a .b16 register, then store/extract its low byte" into

@@ -46,13 +46,6 @@ namespace cacao {
 		static constexpr int U = KIN >= 2 ? 1 : 2;
 	};
 
-	__device__ __forceinline__ void ldg256_stream(const void* p, uint32_t* w) {
-		asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
-	}
-	__device__ __forceinline__ void stg256_stream(void* p, const uint32_t* w) {
-		asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
-	}
-
 	// LUT_DIRECT: the 16->8 table sits in shared memory in full (64 KiB, one LDS.U8 per sample);
 	// otherwise its 8 KiB two-level form (convert_pixel.cuh).
 	template<int SF, int DF, int SC, int DC, bool LUT_DIRECT>

@@ -296,6 +296,26 @@ namespace libcacaoimage {
 			if(!e.empty()) throw std::runtime_error("libcacaoimage-b200: " + e);
 		return faces;
 	}
+	Image UnpackTexels(const unsigned char* texels, unsigned int w, unsigned int h, const std::string& hint) {
+		Image out = {};
+		out.w = w;
+		out.h = h;
+		out.bitsPerChannel = 8; // Model.cpp:248
+		out.format = Image::Format::PNG;
+		out.quality = 0;
+		out.lossy = false;
+		const uint64_t n = static_cast<uint64_t>(w) * h;
+		std::vector<unsigned char> tmp(n * 4 ? n * 4 : 4);
+		int ch = 0;
+		const int rc = cacao_img_unpack_texels(-1, n ? texels : tmp.data(), tmp.data(), n, hint.c_str(), &ch, CACAO_MEM_HOST, nullptr);
+		if(rc == CACAO_E_BAD_ARG) throw std::runtime_error(cacao_img_last_error()); // the reference's texts for rejected hints
+		check(rc);
+		out.layout = static_cast<Image::Layout>(ch);
+		tmp.resize(n * static_cast<uint64_t>(ch));
+		out.data = std::move(tmp);
+		return out;
+	}
+
 	// ---- DeviceImage ---------------------------------------------------------------------------
 
 	namespace {

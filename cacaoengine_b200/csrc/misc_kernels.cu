@@ -42,6 +42,61 @@ namespace cacao {
 			if(k < end) dst[k] = static_cast<uint16_t>(static_cast<uint32_t>(src[k]) << shift);
 		}
 
+		// ---- texel unpack ----------------------------------------------------------------------------
+		// One source word -> [r,g,b,a] bytes with the hint's sub-8-bit channels widened exactly as
+		// Model.cpp:305-310 does: v = (v & ((1 << bits) - 1)) << (8 - bits); v |= v >> bits.
+		template<bool ALL8>
+		__device__ __forceinline__ uint32_t unpack_word(uint32_t w, const TexelPlan& pl) {
+			const uint32_t t = __byte_perm(w, 0u, pl.sel);
+			if constexpr(ALL8) return t;
+			uint32_t r = 0;
+#pragma unroll
+			for(int c = 0; c < 4; ++c) {
+				const uint32_t b = pl.bits[c];
+				uint32_t v = ((t >> (8 * c)) & ((1u << b) - 1u)) << (8u - b);
+				v |= v >> b;
+				r |= (v & 0xFFu) << (8 * c);
+			}
+			return r;
+		}
+
+		// 16 texels (64 B = two whole 32-byte sectors) per thread in, 64 / 48 / 16 B out
+		template<int OUT_CH, bool ALL8>
+		__global__ void __launch_bounds__(256) unpack_texels_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t runs, TexelPlan pl) {
+			const uint64_t r = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+			if(r >= runs) return;
+			uint32_t t[16];
+			ldg256_stream(src + r * 4, t);
+			ldg256_stream(src + r * 4 + 2, t + 8);
+#pragma unroll
+			for(int k = 0; k < 16; ++k) t[k] = unpack_word<ALL8>(t[k], pl);
+			if constexpr(OUT_CH == 4) {
+				stg256_stream(dst + r * 4, t);
+				stg256_stream(dst + r * 4 + 2, t + 8);
+			} else if constexpr(OUT_CH == 3) {
+#pragma unroll
+				for(int k = 0; k < 4; ++k) { // four texels -> three words
+					const uint32_t a = t[4 * k], b = t[4 * k + 1], c = t[4 * k + 2], d = t[4 * k + 3];
+					t[3 * k + 0] = __byte_perm(a, b, 0x4210u);
+					t[3 * k + 1] = __byte_perm(b, c, 0x5421u);
+					t[3 * k + 2] = __byte_perm(c, d, 0x6542u);
+				}
+#pragma unroll
+				for(int k = 0; k < 3; ++k) stg_stream(dst + r * 3 + k, make_uint4(t[4 * k], t[4 * k + 1], t[4 * k + 2], t[4 * k + 3]));
+			} else {
+				uint32_t o[4];
+#pragma unroll
+				for(int k = 0; k < 4; ++k) o[k] = __byte_perm(__byte_perm(t[4 * k], t[4 * k + 1], 0x0040u), __byte_perm(t[4 * k + 2], t[4 * k + 3], 0x0040u), 0x5410u);
+				stg_stream(dst + r, make_uint4(o[0], o[1], o[2], o[3]));
+			}
+		}
+		__global__ void __launch_bounds__(256) unpack_texels_tail_kernel(const uint32_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t begin, uint64_t end, TexelPlan pl) {
+			const uint64_t k = begin + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+			if(k >= end) return;
+			const uint32_t t = unpack_word<false>(src[k], pl);
+			for(uint32_t c = 0; c < pl.out_ch; ++c) dst[k * pl.out_ch + c] = static_cast<uint8_t>(t >> (8 * c));
+		}
+
 		__device__ __forceinline__ float synth_float(uint32_t hsh) {
 			// (1 + m/65536) * 2^(e-8), e in [0,16): assembled from bits so host and device agree exactly
 			const uint32_t e = (hsh >> 24) & 15u, m = (hsh >> 8) & 0xFFFFu;
@@ -107,6 +162,41 @@ namespace cacao {
 		if(units * 8 < samples) {
 			const uint64_t rest = samples - units * 8;
 			shl16_scalar_kernel<<<static_cast<unsigned>((rest + 255) / 256), 256, 0, stream>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), units * 8, samples, shift);
+			return cudaGetLastError();
+		}
+		return cudaSuccess;
+	}
+
+	cudaError_t unpack_texels_launch(const void* src, void* dst, uint64_t texels, const TexelPlan& plan, cudaStream_t stream, unsigned* launches) {
+		if(launches) *launches = 0;
+		const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 31u) == 0; // 256-bit accesses
+		const uint64_t runs = vec ? texels / 16 : 0;
+		const bool all8 = plan.bits[0] == 8 && plan.bits[1] == 8 && plan.bits[2] == 8 && plan.bits[3] == 8;
+		if(runs) {
+			const unsigned grid = static_cast<unsigned>((runs + 255) / 256);
+			const uint4* s4 = static_cast<const uint4*>(src);
+			uint4* d4 = static_cast<uint4*>(dst);
+#define CACAO_UNPACK(CHV)                                                                                   \
+	if(all8)                                                                                                \
+		unpack_texels_kernel<CHV, true><<<grid, 256, 0, stream>>>(s4, d4, runs, plan);                      \
+	else                                                                                                    \
+		unpack_texels_kernel<CHV, false><<<grid, 256, 0, stream>>>(s4, d4, runs, plan);
+			if(plan.out_ch == 4) {
+				CACAO_UNPACK(4)
+			} else if(plan.out_ch == 3) {
+				CACAO_UNPACK(3)
+			} else {
+				CACAO_UNPACK(1)
+			}
+#undef CACAO_UNPACK
+			cudaError_t e = cudaGetLastError();
+			if(e != cudaSuccess) return e;
+			if(launches) *launches += 1;
+		}
+		if(runs * 16 < texels) {
+			const uint64_t rest = texels - runs * 16;
+			unpack_texels_tail_kernel<<<static_cast<unsigned>((rest + 255) / 256), 256, 0, stream>>>(static_cast<const uint32_t*>(src), static_cast<uint8_t*>(dst), runs * 16, texels, plan);
+			if(launches) *launches += 1;
 			return cudaGetLastError();
 		}
 		return cudaSuccess;

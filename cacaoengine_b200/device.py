@@ -76,6 +76,13 @@ def shift_left_u16(src: int, dst: int, samples: int, shift: int, mem: int = capi
 	capi.check(capi.lib().cacao_img_shift_left_u16(device, src, dst, samples, shift, mem, stream))
 
 
+def unpack_texels(src: int, dst: int, texels: int, hint: str, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> int:
+	"""Four-byte texels laid out as `hint` says -> 8-bit pixels in r,g,b,a order (Model.cpp:245-316); returns the channel count."""
+	ch = C.c_int(0)
+	capi.check(capi.lib().cacao_img_unpack_texels(device, src, dst, texels, hint.encode(), C.byref(ch), mem, stream))
+	return int(ch.value)
+
+
 def flip_rows(src: int, dst: int, w: int, h: int, bytes_per_pixel: int, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> None:
 	capi.check(capi.lib().cacao_img_flip_rows(device, src, dst, w, h, bytes_per_pixel, mem, stream))
 

@@ -115,6 +115,20 @@ int cacao_img_shift_left_u16(int device, const void* src, void* dst, uint64_t sa
 							 void* stream);
 
 /*
+ * Texel unpack for textures embedded in model files: `texels` source texels of four bytes each, laid
+ * out as `hint` says -- assimp's aiTexture::achFormatHint, four channel letters then four bit counts,
+ * e.g. "rgba8888", "argb8888", "bgra5650" -- become tightly packed 8-bit pixels in r,g,b,a order;
+ * channels with a zero count are dropped (none -> RGBA, alpha -> RGB, three -> Grayscale), counts
+ * below 8 are widened by bit replication.
+ *   replaces the swizzle / expand loop of engine/src/core/Model.cpp:245-316, with
+ *   its validation: a hint with two or four zero counts, or one zero count that is not alpha, fails
+ *   with CACAO_E_BAD_ARG and the reference's message in cacao_img_last_error().
+ * *out_channels (may be NULL) receives 4, 3 or 1; dst needs texels * that many bytes.
+ */
+int cacao_img_unpack_texels(int device, const void* src, void* dst, uint64_t texels, const char* hint,
+							int* out_channels, int mem, void* stream);
+
+/*
  * Vertical mirror, out.row[y] = src.row[h-1-y], src untouched: the semantics
  * libs/image/src/Flip.cpp:6-42 intends (the reference itself overruns its buffer for h >= 2).
  */

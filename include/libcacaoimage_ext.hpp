@@ -7,6 +7,7 @@
 #include <array>
 #include <cstdint>
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "cacao_img.h"
@@ -49,6 +50,13 @@ namespace libcacaoimage {
 
 	// Flip for any sample format.
 	ImageEx Flip(const ImageEx& src);
+
+	// The uncompressed-texture branch of Cacao::Model::GetTexture (engine/src/core/Model.cpp:245-316):
+	// w*h four-byte texels laid out as assimp's format hint says ("rgba8888", "argb8888", "bgra5650",
+	// ...) become an 8-bit RGBA / RGB / Grayscale Image -- channels in r,g,b,a order, zero-count
+	// channels dropped, counts below 8 widened by bit replication.  Throws the reference's messages
+	// for the hints it rejects (Model.cpp:259-269).
+	Image UnpackTexels(const unsigned char* texels, unsigned int w, unsigned int h, const std::string& hint);
 
 	// An image that lives in the memory of one GPU.  The host API above pays one PCIe round trip per
 	// call; a chain such as "project, then convert, then flip" (what `ce-cubetool project --depth 8

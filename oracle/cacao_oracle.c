@@ -426,6 +426,55 @@ int orc_flip_rows(const void* src, void* dst, uint32_t w, uint32_t h, uint32_t b
 }
 
 /* ------------------------------------------------------------------------------------------
+ * f-3: texel unpack for assimp embedded textures, engine/src/core/Model.cpp:245-316.
+ *
+ * hint = aiTexture::achFormatHint, e.g. "rgba8888", "argb8888", "bgra5650": four channel letters,
+ * then four bit counts (Model.cpp:250-253).  Validation and layout choice follow :255-270
+ * (zeroed channels: none -> RGBA, alpha only -> RGB, three -> Grayscale).  Each kept channel moves
+ * to its place in r,g,b,a order (:280-293) and counts below 8 are widened as :305-310 do:
+ *     v = (v & ((1 << bits) - 1)) << (8 - bits);  v |= v >> bits;
+ * Reference-exact for hints without a zero count.  With zeroed channels the reference indexes the
+ * 4-byte source texels with the output stride (base = texel * (4 - zeroed), :299,:304) and its
+ * grayscale branch (:318-331) widens every source byte with a different, ineffective formula; those
+ * cannot be the intent, so -- as with Flip -- the intended semantics are restated: 4 source bytes
+ * per texel, out_ch output bytes per texel, the same widening everywhere.
+ * Returns the output channel count (4, 3 or 1) or a negative error.
+ * ---------------------------------------------------------------------------------------- */
+int orc_unpack_texels(const uint8_t* src, uint8_t* dst, uint64_t texels, const char* hint) {
+	static const char order[5] = "rgba";
+	int src_index[4] = {-1, -1, -1, -1}, bits[4] = {0, 0, 0, 0}, zeroed = 0;
+	if(!hint) return ORC_E_BAD_ARG;
+	for(int i = 0; i < 8; ++i)
+		if(hint[i] == 0) return ORC_E_BAD_ARG;
+	for(int i = 0; i < 4; ++i) {
+		const char* at = strchr(order, hint[i]);
+		if(!at || hint[i + 4] < '0' || hint[i + 4] > '8') return ORC_E_BAD_ARG;
+		const int c = (int)(at - order);
+		if(src_index[c] >= 0) return ORC_E_BAD_ARG; /* letter used twice */
+		src_index[c] = i;
+		bits[c] = hint[i + 4] - '0';
+	}
+	for(int c = 0; c < 4; ++c)
+		if(bits[c] == 0) ++zeroed;
+	if(zeroed == 2 || zeroed == 4) return ORC_E_BAD_ARG;       /* Model.cpp:259,269 */
+	if(zeroed == 1 && bits[3] != 0) return ORC_E_BAD_ARG;      /* :260 only alpha may be zero */
+	const int out_ch = 4 - zeroed;
+	for(uint64_t t = 0; t < texels; ++t) {
+		int o = 0;
+		for(int c = 0; c < 4; ++c) {
+			if(bits[c] == 0) continue;
+			uint8_t v = src[t * 4 + (uint64_t)src_index[c]];
+			if(bits[c] < 8) {
+				v = (uint8_t)((v & ((1 << bits[c]) - 1)) << (8 - bits[c]));
+				v |= (uint8_t)(v >> bits[c]);
+			}
+			dst[t * (uint64_t)out_ch + (uint64_t)o++] = v;
+		}
+	}
+	return out_ch;
+}
+
+/* ------------------------------------------------------------------------------------------
  * a7 (NEW, Spec B.2): equirectangular -> cubemap.
  *
  * Everything below is fp32 with a fixed operation order; fused multiply-adds appear ONLY as

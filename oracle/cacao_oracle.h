@@ -56,6 +56,8 @@ int orc_convert_mt(const void* src, void* dst, uint64_t pixels, int src_ch, int 
 
 /* Spec f-1 -- vertical mirror with the semantics Flip.cpp:6-42 intends. */
 int orc_flip_rows(const void* src, void* dst, uint32_t w, uint32_t h, uint32_t bytes_per_pixel);
+/* f-3: engine/src/core/Model.cpp:245-316 (texel unpack: swizzle to r,g,b,a order + widen sub-8-bit channels) */
+int orc_unpack_texels(const uint8_t* src, uint8_t* dst, uint64_t texels, const char* hint);
 
 /* Spec B.2 -- equirect (W x H, ch channels, fmt) -> rows [row_begin,row_end) of the faces in
  * face_mask (bit f = face f; order +X,-X,+Y,-Y,+Z,-Z).  dst is the FULL 6*N*N cube buffer

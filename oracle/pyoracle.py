@@ -59,6 +59,7 @@ def port() -> C.CDLL:
 		lib.orc_convert.argtypes = [vp, vp, u64, i, i, i, i, i]
 		lib.orc_convert_mt.argtypes = [vp, vp, u64, i, i, i, i, i, i]
 		lib.orc_flip_rows.argtypes = [vp, vp, u32, u32, u32]
+		lib.orc_unpack_texels.argtypes = [vp, vp, C.c_uint64, C.c_char_p]
 		lib.orc_equirect_to_cube.argtypes = [vp, u32, u32, i, i, vp, u32, u32, u32, u32, i]
 		lib.orc_equirect_to_cube_f64.argtypes = [vp, u32, u32, i, i, vp, u32, u32, u32, u32]
 		lib.orc_project.argtypes = [u32, u32, u32, u32, u32, u32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -151,6 +152,16 @@ def flip_rows(src: np.ndarray, w: int, h: int, bpp: int) -> np.ndarray:
 	if rc != 0:
 		raise ValueError(f"orc_flip_rows rc={rc}")
 	return dst.view(src.dtype)
+
+
+def unpack_texels(src: np.ndarray, hint: str) -> np.ndarray:
+	"""(texels, out_ch) uint8 from (texels, 4) uint8 source bytes laid out as `hint` says (Model.cpp:245-316)."""
+	s = np.ascontiguousarray(src, np.uint8).reshape(-1, 4)
+	dst = np.zeros((s.shape[0], 4), np.uint8)
+	ch = port().orc_unpack_texels(_ptr(s), _ptr(dst), s.shape[0], hint.encode())
+	if ch < 0:
+		raise ValueError(f"orc_unpack_texels rc={ch}")
+	return dst.reshape(-1)[: s.shape[0] * ch].reshape(s.shape[0], ch).copy()
 
 
 def equirect_to_cube(src: np.ndarray, W: int, H: int, ch: int, fmt: int, N: int, face_mask: int = 0x3F,

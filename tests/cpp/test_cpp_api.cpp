@@ -104,6 +104,18 @@ int main(int argc, char** argv) {
 	const Image two = make8(2, 3, L::Grayscale, {1, 2, 3, 4, 5, 6});
 	EXPECT(Flip(two).data == (std::vector<unsigned char>{5, 6, 3, 4, 1, 2}) && two.data[0] == 1);
 	EXPECT(Flip(make8(3, 1, L::Grayscale, {7, 8, 9})).data == (std::vector<unsigned char>{7, 8, 9}));
+	// ---- texel unpack (engine/src/core/Model.cpp:245-316)
+	{
+		const unsigned char tx[8] = {0x12, 0x34, 0x56, 0x78, 0xFF, 0x00, 0x80, 0x01};
+		const Image bgra = UnpackTexels(tx, 2, 1, "bgra8888");
+		EXPECT(bgra.layout == L::RGBA && bgra.bitsPerChannel == 8 && bgra.w == 2 && bgra.h == 1);
+		EXPECT(bgra.data == (std::vector<unsigned char>{0x56, 0x34, 0x12, 0x78, 0x80, 0x00, 0xFF, 0x01}));
+		const Image rgb565 = UnpackTexels(tx, 2, 1, "rgba5650");
+		EXPECT(rgb565.layout == L::RGB && rgb565.data == (std::vector<unsigned char>{148, 211, 181, 255, 0, 0}));
+		EXPECT(UnpackTexels(tx, 2, 1, "rgba0800").layout == L::Grayscale);
+		EXPECT(thrown([&] { UnpackTexels(tx, 2, 1, "rgba8800"); }) == "Invalid zeroed-channel layout for model embedded texture!");
+		EXPECT(thrown([&] { UnpackTexels(tx, 2, 1, "rgba0888"); }) == "Only the alpha channel may be zero for a model embedded texture layout with only one zeroed channel!");
+	}
 	// ---- extensions: float formats and the projection
 	ImageEx ex = FromImage(rgb8);
 	const ImageEx f32 = Convert(ex, L::RGBA, SampleFormat::F32);

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from gpu_util import FMTS, NAME, NP, convert_device, convert_host, random_samples, same_bits
+from gpu_util import FMTS, NAME, NP, DevBuf, convert_device, convert_host, random_samples, same_bits
 
 pytestmark = pytest.mark.gpu
 
@@ -367,3 +367,59 @@ def test_concurrent_callers(oracle):
 	with ThreadPoolExecutor(max_workers=8) as ex:
 		for rep in range(3):
 			assert all(ex.map(run, jobs))
+
+
+TEXEL_HINTS = ["rgba8888", "argb8888", "bgra8888", "abgr8888", "rgba8880", "bgra8880", "rgba5650", "bgra5650", "rgba4444", "argb1555", "rgba5551", "rgba8000", "rgba0800", "bgra0050", "rgba2222", "rgba1111", "rgba3320"]
+
+
+@pytest.mark.parametrize("hint", TEXEL_HINTS)
+def test_unpack_texels_matches_oracle(oracle, hint):
+	"""cacao_img_unpack_texels (engine/src/core/Model.cpp:245-316: swizzle to r,g,b,a order, drop zero-count
+	channels, widen sub-8-bit counts) against the oracle: vector body + scalar tail, device and host memory,
+	aligned and unaligned buffers."""
+	from cacaoengine_b200 import _capi as c, device
+
+	for texels in (1, 15, 16, 17, 4099, 1 << 16):
+		src = oracle.synth(texels * 4, c.FMT_U8, 4, 900 + texels).reshape(-1, 4)
+		want = oracle.unpack_texels(src, hint)
+		ch = want.shape[1]
+		got = np.zeros(texels * ch, np.uint8)
+		assert device.unpack_texels(src.ctypes.data, got.ctypes.data, texels, hint, mem=c.MEM_HOST) == ch
+		assert np.array_equal(got.reshape(-1, ch), want), (hint, texels, "host")
+		for shift in (0, 4):  # 16-byte aligned, and 4-byte aligned only (scalar kernel)
+			a, b = DevBuf(texels * 4 + 16), DevBuf(texels * ch + 16)
+			device.upload(a.ptr + shift, src)
+			assert device.unpack_texels(a.ptr + shift, b.ptr + shift, texels, hint) == ch
+			device.download(got, b.ptr + shift)
+			a.free(), b.free()
+			assert np.array_equal(got.reshape(-1, ch), want), (hint, texels, shift)
+
+
+def test_unpack_texels_rejects_what_the_reference_rejects():
+	from cacaoengine_b200 import _capi as c, device
+
+	buf = np.zeros(64, np.uint8)
+	for hint, text in (("rgba8800", "Invalid zeroed-channel layout for model embedded texture!"), ("rgba0888", "Only the alpha channel may be zero for a model embedded texture layout with only one zeroed channel!"),
+					   ("rgba0000", "Impossible channel layout for model embedded texture!"), ("rgbx8888", "not four of r,g,b,a"), ("rgba888", "eight characters")):
+		with pytest.raises(c.CacaoError) as e:
+			device.unpack_texels(buf.ctypes.data, buf.ctypes.data, 4, hint, mem=c.MEM_HOST)
+		assert e.value.status == c.E_BAD_ARG and text in str(e.value)
+
+
+def test_unpack_texels_full_size_property(oracle):
+	"""64 Mtexels on the device: the all-8-bit hints are pure byte permutations, so unpacking with
+	"bgra8888" and then again with "bgra8888" (its own inverse) is the identity, and the RGB result of
+	"rgba8880" equals the RGBA -> RGB layout change of the conversion kernel."""
+	from cacaoengine_b200 import _capi as c, device
+
+	n = 1 << 26
+	a, b, d = DevBuf(n * 4), DevBuf(n * 4), DevBuf(n * 4)
+	device.synth(a.ptr, n * 4, c.FMT_U8, 4, 4242)
+	device.unpack_texels(a.ptr, b.ptr, n, "bgra8888")
+	device.unpack_texels(b.ptr, d.ptr, n, "bgra8888")
+	assert device.checksum(d.ptr, n * 4) == device.checksum(a.ptr, n * 4) != device.checksum(b.ptr, n * 4)
+	device.unpack_texels(a.ptr, b.ptr, n, "rgba8880")
+	device.convert(a.ptr, d.ptr, n, 4, 3, c.FMT_U8, c.FMT_U8)
+	assert device.checksum(b.ptr, n * 3) == device.checksum(d.ptr, n * 3)
+	for x in (a, b, d):
+		x.free()
