@@ -262,6 +262,33 @@ def roof(alg_bytes, ms, peak, traffic=None):
 	return {"bound": "hbm", "achieved": alg_bytes / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg_bytes / ms / 1e6 / peak, "traffic": traffic}
 
 
+def verify_ring(device, dev, src, dst, px, ring, dfmt, dbytes):
+	"""Untimed check of the cfg4 output ring: a 1 Mpixel band of three ring slots is read
+	back together with its input and recomputed on the CPU -- by the reference's own ChangeChannelLayout
+	(oracle/_ref) for RGB8 -> RGBA8 when it is present, by the C restatement otherwise -- and compared
+	byte for byte.  The oracle is used as the checker only."""
+	from cacaoengine_b200 import FMT_U8
+
+	from oracle import pyoracle as po
+
+	band = 1 << 20
+	slots = sorted({0, ring // 2, ring - 1})
+	ok, against = True, "restatement"
+	for slot in slots:
+		first = slot * px + (px - band) // 2  # a band from the middle of the image
+		a = np.empty(band * 3, np.uint8)
+		b = np.empty(band * dbytes, np.uint8)
+		device.download(a, src.data_ptr() + first * 3, device=dev)
+		device.download(b, dst.data_ptr() + first * dbytes, device=dev)
+		if dfmt == FMT_U8 and po.have_ref():
+			want = po.ref_change_layout(a, band, 1, 3, 4)
+			against = "compiled reference (oracle/_ref)"
+		else:
+			want = po.convert(a, 3, 4, po.U8, dfmt, threads=0)
+		ok = ok and bool(np.array_equal(want.view(np.uint8).reshape(-1), b))
+	return {"ok": ok, "ring_slots": slots, "band_pixels": band, "against": against}
+
+
 def extra_configs(torch, dist, world, rank, dev, stream, peak):
 	"""The other BASELINE configs, device-resident, sharded over the ranks exactly as DESIGN.md
 	"Multi-GPU" says (images by index, cube by face/row band); rooflines are per GPU (x world)."""
@@ -342,6 +369,8 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 		per_launch = traffic_for(key.split("_")[0] + "_16x_4096sq_" + key.split("sq_")[1] + "_per_launch")  # ncu: one 16-image launch
 		launches = (total + ring - 1) // ring
 		out[key] = {"value": total * px / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "logical_images": total, "images_per_rank": hi - lo, "resident_ring": ring, "launches_per_step_all_ranks": launches, "roofline": roof(alg, ms, peak * world, per_launch * launches if per_launch else None)}
+		if rank == 0:
+			out[key]["verified"] = verify_ring(device, dev, src, dst, px, ring, dfmt, dbytes)
 		del dst
 	del src
 	torch.cuda.empty_cache()
