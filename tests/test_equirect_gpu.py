@@ -82,6 +82,18 @@ def test_row_mirror_sharing_is_bit_identical(oracle, monkeypatch, fmt, ch):
 		assert same_bits(got, ref), ("band", W, H, N)
 
 
+@pytest.mark.parametrize("fmt", FMTS, ids=[NAME[f] for f in FMTS])
+def test_degenerate_panoramas(oracle, fmt):
+	"""One-texel, one-row, one-column and few-texel panoramas (every tap wraps or clamps; the joint
+	two-tap loads of three-channel texels must fall back near the end of the buffer), device and host."""
+	for ch in (1, 3, 4):
+		for W, H, N in ((1, 1, 3), (2, 1, 4), (1, 2, 5), (3, 2, 7), (5, 3, 16), (9, 1, 8), (8, 2, 33)):
+			src = oracle.synth(W * H * ch, fmt, ch, 11 * W + H)
+			want = oracle.equirect_to_cube(src, W, H, ch, fmt, N)
+			assert same_bits(gpu_equirect_device(src, W, H, ch, fmt, N), want), (ch, W, H, N, "device")
+			assert same_bits(gpu_equirect_host(src, W, H, ch, fmt, N), want), (ch, W, H, N, "host")
+
+
 def test_cfg1_shape_rgba8(oracle):
 	"""BASELINE config 1: 2048x1024 RGBA8 -> 6x512^2."""
 	from cacaoengine_b200 import _capi as c
