@@ -21,6 +21,7 @@
 #include "cacao_img.h"
 #include "convert_dispatch.cuh"
 #include "equirect.cuh"
+#include "mip.cuh"
 #include "misc_kernels.cuh"
 
 namespace {
@@ -910,6 +911,36 @@ int cacao_img_shift_left_u16(int device, const void* src, void* dst, uint64_t sa
 	if(e != cudaSuccess) return fail_cuda(e, "shift kernel launch");
 	g_launches.fetch_add(n_launch, std::memory_order_relaxed);
 	return download_any(c, static_cast<uint8_t*>(dst), c->stage_in[0], samples * 2, c->s_run);
+}
+
+int cacao_img_downsample2x(int device, const void* src, void* dst, uint32_t w, uint32_t h, int ch, int fmt, int mem, void* stream) {
+	if(!ch_ok(ch) || !fmt_ok(fmt)) return fail(CACAO_E_BAD_ARG, "downsample: bad channel count %d or format %d", ch, fmt);
+	if(w == 0 || h == 0) return fail(CACAO_E_ZERO_DIM, "downsample: zero-sized image");
+	if(!src || !dst) return fail(CACAO_E_BAD_ARG, "null image pointer");
+	if(mem != CACAO_MEM_HOST && mem != CACAO_MEM_DEVICE) return fail(CACAO_E_BAD_ARG, "unknown memory kind %d", mem);
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	const uint64_t bpp = static_cast<uint64_t>(ch) * fmt_bytes(fmt);
+	const uint64_t in_bytes = static_cast<uint64_t>(w) * h * bpp;
+	const uint64_t out_bytes = static_cast<uint64_t>(w / 2 ? w / 2 : 1) * (h / 2 ? h / 2 : 1) * bpp;
+	unsigned launches = 0;
+	if(mem == CACAO_MEM_DEVICE) {
+		cudaError_t e = downsample2x_launch(src, dst, w, h, ch, fmt, static_cast<cudaStream_t>(stream), &launches);
+		g_launches.fetch_add(launches, std::memory_order_relaxed);
+		if(e != cudaSuccess) return fail_cuda(e, "downsample kernel launch");
+		return CACAO_OK;
+	}
+	std::lock_guard<std::mutex> lock(c->pipe_mutex);
+	rc = ensure_stage(c, in_bytes, out_bytes, 1);
+	if(rc) return rc;
+	rc = upload_any(c, c->stage_in[0], static_cast<const uint8_t*>(src), in_bytes, c->s_run);
+	if(rc) return rc;
+	cudaError_t e = downsample2x_launch(c->stage_in[0], c->stage_out[0], w, h, ch, fmt, c->s_run, &launches);
+	g_launches.fetch_add(launches, std::memory_order_relaxed);
+	if(e != cudaSuccess) return fail_cuda(e, "downsample kernel launch");
+	return download_any(c, static_cast<uint8_t*>(dst), c->stage_out[0], out_bytes, c->s_run);
 }
 
 int cacao_img_unpack_texels(int device, const void* src, void* dst, uint64_t texels, const char* hint, int* out_channels, int mem, void* stream) {

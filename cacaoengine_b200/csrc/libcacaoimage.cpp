@@ -296,6 +296,29 @@ namespace libcacaoimage {
 			if(!e.empty()) throw std::runtime_error("libcacaoimage-b200: " + e);
 		return faces;
 	}
+	ImageEx Downsample2x(const ImageEx& src) {
+		if(src.w == 0 || src.h == 0) check(CACAO_E_ZERO_DIM);
+		if(src.data.size() < static_cast<std::size_t>(src.w) * src.h * BytesPerPixel(src.layout, src.format)) throw std::runtime_error("Image data buffer is smaller than w * h * channels * bytes per channel!");
+		ImageEx out;
+		out.w = src.w / 2 ? src.w / 2 : 1;
+		out.h = src.h / 2 ? src.h / 2 : 1;
+		out.layout = src.layout;
+		out.format = src.format;
+		out.data.resize(static_cast<std::size_t>(out.w) * out.h * BytesPerPixel(src.layout, src.format));
+		check(cacao_img_downsample2x(-1, src.data.data(), out.data.data(), src.w, src.h, static_cast<int>(src.layout), static_cast<int>(src.format), CACAO_MEM_HOST, nullptr));
+		return out;
+	}
+
+	std::vector<ImageEx> GenerateMipChain(const ImageEx& base) {
+		std::vector<ImageEx> levels;
+		DeviceImage cur = DeviceImage::Upload(base);
+		while(cur.Width() > 1 || cur.Height() > 1) {
+			cur = cur.Downsample2x();
+			levels.push_back(cur.Download());
+		}
+		return levels;
+	}
+
 	Image UnpackTexels(const unsigned char* texels, unsigned int w, unsigned int h, const std::string& hint) {
 		Image out = {};
 		out.w = w;
@@ -380,6 +403,13 @@ namespace libcacaoimage {
 		if(h_ == 1) return *this;
 		DeviceImage out(w_, h_, layout_, format_, device_);
 		check(cacao_img_flip_rows(device_, ptr_, out.ptr_, w_, h_, static_cast<uint32_t>(BytesPerPixel(layout_, format_)), CACAO_MEM_DEVICE, nullptr));
+		return out;
+	}
+
+	DeviceImage DeviceImage::Downsample2x() const {
+		if(Empty()) check(CACAO_E_EMPTY);
+		DeviceImage out(w_ / 2 ? w_ / 2 : 1, h_ / 2 ? h_ / 2 : 1, layout_, format_, device_);
+		check(cacao_img_downsample2x(device_, ptr_, out.ptr_, w_, h_, static_cast<int>(layout_), static_cast<int>(format_), CACAO_MEM_DEVICE, nullptr));
 		return out;
 	}
 

@@ -76,6 +76,11 @@ def shift_left_u16(src: int, dst: int, samples: int, shift: int, mem: int = capi
 	capi.check(capi.lib().cacao_img_shift_left_u16(device, src, dst, samples, shift, mem, stream))
 
 
+def downsample2x(src: int, dst: int, w: int, h: int, ch: int, fmt: int, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> None:
+	"""One mip level (2x2 box average): dst is max(1, w//2) x max(1, h//2)."""
+	capi.check(capi.lib().cacao_img_downsample2x(device, src, dst, w, h, ch, fmt, mem, stream))
+
+
 def unpack_texels(src: int, dst: int, texels: int, hint: str, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> int:
 	"""Four-byte texels laid out as `hint` says -> 8-bit pixels in r,g,b,a order (Model.cpp:245-316); returns the channel count."""
 	ch = C.c_int(0)

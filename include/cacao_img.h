@@ -115,6 +115,16 @@ int cacao_img_shift_left_u16(int device, const void* src, void* dst, uint64_t sa
 							 void* stream);
 
 /*
+ * One mip level: dst (max(1,w/2) x max(1,h/2) pixels) = 2x2 box average of src (w x h), per channel on
+ * stored values -- integers (a+b+c+d+2)>>2, floats ((a+b)+(c+d))*0.25f in fp32 (DESIGN.md "Spec B.3").
+ * No reference counterpart: the engine leaves mip generation to the graphics API (glGenerateMipmap,
+ * engine/src/opengl/impls/OpenGLTex2D.cpp:51); with the pixels already on the GPU the chain can be
+ * produced where they are.  Call it repeatedly for a chain.
+ */
+int cacao_img_downsample2x(int device, const void* src, void* dst, uint32_t w, uint32_t h, int ch, int fmt,
+						   int mem, void* stream);
+
+/*
  * Texel unpack for textures embedded in model files: `texels` source texels of four bytes each, laid
  * out as `hint` says -- assimp's aiTexture::achFormatHint, four channel letters then four bit counts,
  * e.g. "rgba8888", "argb8888", "bgra5650" -- become tightly packed 8-bit pixels in r,g,b,a order;

@@ -51,6 +51,13 @@ namespace libcacaoimage {
 	// Flip for any sample format.
 	ImageEx Flip(const ImageEx& src);
 
+	// Mip levels (2x2 box average per level, DESIGN.md "Spec B.3"; the engine leaves this to the graphics
+	// API, engine/src/opengl/impls/OpenGLTex2D.cpp:51).  Downsample2x gives the next level
+	// (max(1,w/2) x max(1,h/2)); GenerateMipChain gives every level below `base` down to 1x1 with one
+	// upload, the whole chain on the GPU, and one readback per level.
+	ImageEx Downsample2x(const ImageEx& src);
+	std::vector<ImageEx> GenerateMipChain(const ImageEx& base);
+
 	// The uncompressed-texture branch of Cacao::Model::GetTexture (engine/src/core/Model.cpp:245-316):
 	// w*h four-byte texels laid out as assimp's format hint says ("rgba8888", "argb8888", "bgra5650",
 	// ...) become an 8-bit RGBA / RGB / Grayscale Image -- channels in r,g,b,a order, zero-count
@@ -79,6 +86,7 @@ namespace libcacaoimage {
 		DeviceImage Convert(Image::Layout layout, SampleFormat format, ConvertMode mode = ConvertMode::ReferenceExact) const;
 		DeviceImage ToRGB8() const; // U16 -> U8 through the engine's table, then -> RGB, one kernel
 		DeviceImage Flip() const;
+		DeviceImage Downsample2x() const; // the next mip level
 		// six faces that are views of ONE contiguous face-major allocation (+X,-X,+Y,-Y,+Z,-Z) -- the
 		// layout the Vulkan backend concatenates by hand (engine/src/vulkan/impls/VulkanCubemap.cpp:30-41)
 		std::array<DeviceImage, 6> EquirectToCubemap(unsigned int faceSize) const;

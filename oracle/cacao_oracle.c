@@ -426,6 +426,43 @@ int orc_flip_rows(const void* src, void* dst, uint32_t w, uint32_t h, uint32_t b
 }
 
 /* ------------------------------------------------------------------------------------------
+ * f-4 follow-on (NEW, Spec B.3): one mip level, 2x2 box average.  No reference counterpart: the
+ * engine leaves mips to the graphics API (glGenerateMipmap, engine/src/opengl/impls/OpenGLTex2D.cpp:51).
+ *   out is max(1, w/2) x max(1, h/2); out(x, y) averages src(2x, 2y), src(min(2x+1, w-1), 2y),
+ *   src(2x, min(2y+1, h-1)), src(min(2x+1, w-1), min(2y+1, h-1)) per channel, on stored values:
+ *   integers (a + b + c + d + 2) >> 2; floats ((a + b) + (c + d)) * 0.25f in fp32 (F16 widened first,
+ *   rounded to nearest even afterwards).
+ * ---------------------------------------------------------------------------------------- */
+int orc_downsample2x(const void* src, void* dst, uint32_t w, uint32_t h, int ch, int fmt) {
+	if(w == 0 || h == 0 || !(ch == 1 || ch == 3 || ch == 4) || fmt < ORC_U8 || fmt > ORC_F32) return ORC_E_BAD_ARG;
+	const uint32_t wo = w / 2 ? w / 2 : 1, ho = h / 2 ? h / 2 : 1;
+	for(uint32_t y = 0; y < ho; ++y)
+		for(uint32_t x = 0; x < wo; ++x) {
+			const uint32_t x0 = 2 * x, x1 = (2 * x + 1 < w) ? 2 * x + 1 : w - 1, y0 = 2 * y, y1 = (2 * y + 1 < h) ? 2 * y + 1 : h - 1;
+			for(int c = 0; c < ch; ++c) {
+				const size_t ia = ((size_t)y0 * w + x0) * ch + c, ib = ((size_t)y0 * w + x1) * ch + c, ic = ((size_t)y1 * w + x0) * ch + c, id = ((size_t)y1 * w + x1) * ch + c;
+				const size_t io = ((size_t)y * wo + x) * ch + c;
+				if(fmt == ORC_U8) {
+					const uint8_t* s = (const uint8_t*)src;
+					((uint8_t*)dst)[io] = (uint8_t)(((uint32_t)s[ia] + s[ib] + s[ic] + s[id] + 2u) >> 2);
+				} else if(fmt == ORC_U16) {
+					const uint16_t* s = (const uint16_t*)src;
+					((uint16_t*)dst)[io] = (uint16_t)(((uint32_t)s[ia] + s[ib] + s[ic] + s[id] + 2u) >> 2);
+				} else if(fmt == ORC_F32) {
+					const float* s = (const float*)src;
+					const float top = s[ia] + s[ib], bot = s[ic] + s[id];
+					((float*)dst)[io] = (top + bot) * 0.25f;
+				} else {
+					const uint16_t* s = (const uint16_t*)src;
+					const float top = orc_f16_to_f32(s[ia]) + orc_f16_to_f32(s[ib]), bot = orc_f16_to_f32(s[ic]) + orc_f16_to_f32(s[id]);
+					((uint16_t*)dst)[io] = orc_f32_to_f16((top + bot) * 0.25f);
+				}
+			}
+		}
+	return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
  * f-3: texel unpack for assimp embedded textures, engine/src/core/Model.cpp:245-316.
  *
  * hint = aiTexture::achFormatHint, e.g. "rgba8888", "argb8888", "bgra5650": four channel letters,

@@ -56,6 +56,8 @@ int orc_convert_mt(const void* src, void* dst, uint64_t pixels, int src_ch, int 
 
 /* Spec f-1 -- vertical mirror with the semantics Flip.cpp:6-42 intends. */
 int orc_flip_rows(const void* src, void* dst, uint32_t w, uint32_t h, uint32_t bytes_per_pixel);
+/* f-4 follow-on (Spec B.3): one mip level, 2x2 box average; dst is max(1,w/2) x max(1,h/2) */
+int orc_downsample2x(const void* src, void* dst, uint32_t w, uint32_t h, int ch, int fmt);
 /* f-3: engine/src/core/Model.cpp:245-316 (texel unpack: swizzle to r,g,b,a order + widen sub-8-bit channels) */
 int orc_unpack_texels(const uint8_t* src, uint8_t* dst, uint64_t texels, const char* hint);
 

@@ -60,6 +60,7 @@ def port() -> C.CDLL:
 		lib.orc_convert_mt.argtypes = [vp, vp, u64, i, i, i, i, i, i]
 		lib.orc_flip_rows.argtypes = [vp, vp, u32, u32, u32]
 		lib.orc_unpack_texels.argtypes = [vp, vp, C.c_uint64, C.c_char_p]
+		lib.orc_downsample2x.argtypes = [vp, vp, u32, u32, C.c_int, C.c_int]
 		lib.orc_equirect_to_cube.argtypes = [vp, u32, u32, i, i, vp, u32, u32, u32, u32, i]
 		lib.orc_equirect_to_cube_f64.argtypes = [vp, u32, u32, i, i, vp, u32, u32, u32, u32]
 		lib.orc_project.argtypes = [u32, u32, u32, u32, u32, u32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -152,6 +153,17 @@ def flip_rows(src: np.ndarray, w: int, h: int, bpp: int) -> np.ndarray:
 	if rc != 0:
 		raise ValueError(f"orc_flip_rows rc={rc}")
 	return dst.view(src.dtype)
+
+
+def downsample2x(src: np.ndarray, w: int, h: int, ch: int, fmt: int) -> np.ndarray:
+	"""One mip level (Spec B.3): (max(1,h/2), max(1,w/2), ch) from (h, w, ch)."""
+	s = np.ascontiguousarray(src).reshape(-1)
+	assert s.dtype == FMT_DTYPE[fmt] and s.size == w * h * ch
+	dst = np.empty(max(1, w // 2) * max(1, h // 2) * ch, FMT_DTYPE[fmt])
+	rc = port().orc_downsample2x(_ptr(s), _ptr(dst), w, h, ch, fmt)
+	if rc != 0:
+		raise ValueError(f"orc_downsample2x rc={rc}")
+	return dst
 
 
 def unpack_texels(src: np.ndarray, hint: str) -> np.ndarray:

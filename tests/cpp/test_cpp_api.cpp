@@ -104,6 +104,19 @@ int main(int argc, char** argv) {
 	const Image two = make8(2, 3, L::Grayscale, {1, 2, 3, 4, 5, 6});
 	EXPECT(Flip(two).data == (std::vector<unsigned char>{5, 6, 3, 4, 1, 2}) && two.data[0] == 1);
 	EXPECT(Flip(make8(3, 1, L::Grayscale, {7, 8, 9})).data == (std::vector<unsigned char>{7, 8, 9}));
+	// ---- mip levels
+	{
+		ImageEx m;
+		m.w = 4;
+		m.h = 2;
+		m.layout = L::Grayscale;
+		m.format = SampleFormat::U8;
+		m.data = {1, 2, 10, 20, 3, 4, 30, 41};
+		const ImageEx half = Downsample2x(m);
+		EXPECT(half.w == 2 && half.h == 1 && half.data == (std::vector<unsigned char>{3, 25})); // (1+2+3+4+2)>>2, (10+20+30+41+2)>>2
+		const auto chain = GenerateMipChain(m);
+		EXPECT(chain.size() == 2 && chain[0].data == half.data && chain[1].w == 1 && chain[1].h == 1 && chain[1].data == (std::vector<unsigned char>{14}));
+	}
 	// ---- texel unpack (engine/src/core/Model.cpp:245-316)
 	{
 		const unsigned char tx[8] = {0x12, 0x34, 0x56, 0x78, 0xFF, 0x00, 0x80, 0x01};

@@ -423,3 +423,62 @@ def test_unpack_texels_full_size_property(oracle):
 	assert device.checksum(b.ptr, n * 3) == device.checksum(d.ptr, n * 3)
 	for x in (a, b, d):
 		x.free()
+
+
+@pytest.mark.parametrize("fmt", FMTS, ids=[NAME[f] for f in FMTS])
+@pytest.mark.parametrize("ch", (1, 3, 4))
+def test_downsample2x_matches_oracle(oracle, fmt, ch):
+	"""One mip level (Spec B.3) against the oracle: sizes that take the 256-bit vector kernel, odd sizes
+	that take the per-pixel kernel, a vector body with a scalar remainder, one-wide / one-high images;
+	device and host memory."""
+	from cacaoengine_b200 import _capi as c, device
+
+	for w, h in ((256, 64), (254, 63), (1, 1), (1, 7), (7, 1), (2, 2), (96, 5), (160, 40), (224, 3), (34, 34)):
+		src = oracle.synth(w * h * ch, fmt, ch, 70 + w)
+		want = oracle.downsample2x(src, w, h, ch, fmt)
+		got = np.zeros_like(want)
+		device.downsample2x(src.ctypes.data, got.ctypes.data, w, h, ch, fmt, mem=c.MEM_HOST)
+		assert same_bits(got, want), (w, h, "host")
+		a, b = DevBuf(src.nbytes), DevBuf(want.nbytes)
+		device.upload(a.ptr, src)
+		device.downsample2x(a.ptr, b.ptr, w, h, ch, fmt)
+		got[:] = 0
+		device.download(got, b.ptr)
+		a.free(), b.free()
+		assert same_bits(got, want), (w, h, "device")
+
+
+def test_mip_chain_full_size(oracle):
+	"""A 4096 x 4096 RGBA8 chain on the device: every level's checksum equals the oracle's for the
+	levels small enough to recompute (<= 512^2, from the downloaded parent), and a constant image
+	stays constant all the way down to 1 x 1."""
+	from cacaoengine_b200 import _capi as c, device
+
+	n, ch, fmt = 4096, 4, c.FMT_U8
+	cur = DevBuf(n * n * ch)
+	device.synth(cur.ptr, n * n * ch, fmt, ch, 808)
+	w = n
+	while w > 1:
+		nxt = DevBuf((w // 2) * (w // 2) * ch)
+		device.downsample2x(cur.ptr, nxt.ptr, w, w, ch, fmt)
+		if w <= 1024:
+			parent = np.empty(w * w * ch, np.uint8)
+			device.download(parent, cur.ptr)
+			child = np.empty((w // 2) * (w // 2) * ch, np.uint8)
+			device.download(child, nxt.ptr)
+			assert same_bits(child, oracle.downsample2x(parent, w, w, ch, fmt)), w
+		cur.free()
+		cur, w = nxt, w // 2
+	cur.free()
+	flat = DevBuf(1024 * 1024 * 4)
+	device.upload(flat.ptr, np.full(1024 * 1024 * 4, 77, np.uint8))
+	w = 1024
+	while w > 1:
+		nxt = DevBuf((w // 2) * (w // 2) * 4)
+		device.downsample2x(flat.ptr, nxt.ptr, w, w, 4, fmt)
+		flat.free()
+		flat, w = nxt, w // 2
+	last = np.empty(4, np.uint8)
+	device.download(last, flat.ptr)
+	flat.free()
+	assert (last == 77).all()
