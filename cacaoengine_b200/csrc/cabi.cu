@@ -537,6 +537,21 @@ namespace {
 		chunk_px = ((chunk_px + 8191) / 8192) * 8192;
 		if(quirk || chunk_px > pixels) chunk_px = pixels; // the pixel-0 quirk needs each image whole
 		std::lock_guard<std::mutex> lock(c->pipe_mutex);
+		// Small images (icons, 64x64 textures): two DMA copies and their stream hops cost more than the
+		// data.  The kernel reads and writes the pinned staging slots directly over PCIe instead
+		// (host memory from cudaHostAlloc is device-addressable under unified addressing): one memcpy
+		// in, ONE stream operation, one synchronize, one memcpy out.
+		static const uint64_t zero_copy_limit = getenv("CACAO_ZERO_COPY_KIB") ? strtoull(getenv("CACAO_ZERO_COPY_KIB"), nullptr, 10) << 10 : (512ull << 10);
+		if(pixels * (sbpp + dbpp) <= zero_copy_limit) {
+			int rc0 = ensure_pinned(c, std::max<uint64_t>(pixels * sbpp, 64u << 10), std::max<uint64_t>(pixels * dbpp, 64u << 10));
+			if(rc0) return rc0;
+			std::memcpy(c->pin_in[0], src, pixels * sbpp);
+			rc0 = enqueue_convert(c, c->pin_in[0], c->pin_out[0], pixels, ppi, src_ch, dst_ch, src_fmt, dst_fmt, mode, c->s_run);
+			if(rc0) return rc0;
+			CU_TRY(cudaStreamSynchronize(c->s_run));
+			std::memcpy(dst, c->pin_out[0], pixels * dbpp);
+			return CACAO_OK;
+		}
 		int rc = ensure_stage(c, chunk_px * sbpp, chunk_px * dbpp);
 		if(rc) return rc;
 		// pageable buffers (std::vector, numpy) travel through the pinned ring; pinned ones are DMA'd directly

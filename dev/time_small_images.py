@@ -14,7 +14,7 @@ def bench(fn, reps):
 	for _ in range(reps): fn()
 	return (time.perf_counter() - t0) / reps
 print(f"{'size':>10s} {'op':>22s} {'gpu ms':>9s} {'ref cpu ms':>11s}")
-for n in (64, 256, 1024, 2048, 4096):
+for n in (16, 32, 64, 96, 128, 256, 1024, 2048, 4096):
 	d8 = rng.integers(0, 256, n * n * 4).astype(np.uint8)
 	d16 = rng.integers(0, 65536, n * n * 4).astype(np.uint16)
 	img8 = ce.Image(n, n, ce.Layout.RGBA, 8, d8)
