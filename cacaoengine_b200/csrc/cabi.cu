@@ -521,6 +521,8 @@ namespace {
 		return CACAO_OK;
 	}
 
+	uint64_t zero_copy_limit();
+
 	// Host-memory conversion: chunks flow upload -> kernel -> readback over three streams, so PCIe
 	// moves in both directions while the SMs convert the chunk in between.
 	int convert_host_pipeline(DeviceCtx* c, const uint8_t* src, uint8_t* dst, uint64_t pixels, uint64_t ppi, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode) {
@@ -541,8 +543,7 @@ namespace {
 		// data.  The kernel reads and writes the pinned staging slots directly over PCIe instead
 		// (host memory from cudaHostAlloc is device-addressable under unified addressing): one memcpy
 		// in, ONE stream operation, one synchronize, one memcpy out.
-		static const uint64_t zero_copy_limit = getenv("CACAO_ZERO_COPY_KIB") ? strtoull(getenv("CACAO_ZERO_COPY_KIB"), nullptr, 10) << 10 : (512ull << 10);
-		if(pixels * (sbpp + dbpp) <= zero_copy_limit) {
+		if(pixels * (sbpp + dbpp) <= zero_copy_limit()) {
 			int rc0 = ensure_pinned(c, std::max<uint64_t>(pixels * sbpp, 64u << 10), std::max<uint64_t>(pixels * dbpp, 64u << 10));
 			if(rc0) return rc0;
 			std::memcpy(c->pin_in[0], src, pixels * sbpp);
@@ -722,6 +723,36 @@ namespace {
 		return CACAO_OK;
 	}
 
+	// One-shot host-memory operation (flip, shift, texel unpack, mip level): small jobs run zero-copy on
+	// the pinned staging slots (see convert_host_pipeline), larger ones upload, run and read back through
+	// device staging slot 0.  launch(src_dev, dst_dev, stream) enqueues the kernels.
+	uint64_t zero_copy_limit() {
+		static const uint64_t limit = getenv("CACAO_ZERO_COPY_KIB") ? strtoull(getenv("CACAO_ZERO_COPY_KIB"), nullptr, 10) << 10 : (512ull << 10);
+		return limit;
+	}
+
+	template<class Launch>
+	int run_host_op(DeviceCtx* c, const void* src, uint64_t in_bytes, void* dst, uint64_t out_bytes, Launch launch) {
+		std::lock_guard<std::mutex> lock(c->pipe_mutex);
+		if(in_bytes + out_bytes <= zero_copy_limit()) {
+			int rc = ensure_pinned(c, std::max<uint64_t>(in_bytes, 64u << 10), std::max<uint64_t>(out_bytes, 64u << 10));
+			if(rc) return rc;
+			std::memcpy(c->pin_in[0], src, in_bytes);
+			rc = launch(c->pin_in[0], c->pin_out[0], c->s_run);
+			if(rc) return rc;
+			CU_TRY(cudaStreamSynchronize(c->s_run));
+			std::memcpy(dst, c->pin_out[0], out_bytes);
+			return CACAO_OK;
+		}
+		int rc = ensure_stage(c, in_bytes, out_bytes, 1);
+		if(rc) return rc;
+		rc = upload_any(c, c->stage_in[0], static_cast<const uint8_t*>(src), in_bytes, c->s_run);
+		if(rc) return rc;
+		rc = launch(c->stage_in[0], c->stage_out[0], c->s_run);
+		if(rc) return rc;
+		return download_any(c, static_cast<uint8_t*>(dst), c->stage_out[0], out_bytes, c->s_run);
+	}
+
 } // namespace
 
 extern "C" {
@@ -889,16 +920,13 @@ int cacao_img_flip_rows(int device, const void* src, void* dst, uint32_t w, uint
 		g_launches.fetch_add(1, std::memory_order_relaxed);
 		return CACAO_OK;
 	}
-	std::lock_guard<std::mutex> lock(c->pipe_mutex);
 	const uint64_t bytes = pitch * h;
-	rc = ensure_stage(c, bytes, bytes, 1);
-	if(rc) return rc;
-	rc = upload_any(c, c->stage_in[0], static_cast<const uint8_t*>(src), bytes, c->s_run);
-	if(rc) return rc;
-	cudaError_t e = flip_rows_launch(c->stage_in[0], c->stage_out[0], pitch, h, c->sm_count, c->s_run);
-	if(e != cudaSuccess) return fail_cuda(e, "flip kernel launch");
-	g_launches.fetch_add(1, std::memory_order_relaxed);
-	return download_any(c, static_cast<uint8_t*>(dst), c->stage_out[0], bytes, c->s_run);
+	return run_host_op(c, src, bytes, dst, bytes, [&](uint8_t* s, uint8_t* d, cudaStream_t q) -> int {
+		cudaError_t e = flip_rows_launch(s, d, pitch, h, c->sm_count, q);
+		if(e != cudaSuccess) return fail_cuda(e, "flip kernel launch");
+		g_launches.fetch_add(1, std::memory_order_relaxed);
+		return CACAO_OK;
+	});
 }
 
 int cacao_img_shift_left_u16(int device, const void* src, void* dst, uint64_t samples, uint32_t shift, int mem, void* stream) {
@@ -917,15 +945,12 @@ int cacao_img_shift_left_u16(int device, const void* src, void* dst, uint64_t sa
 		g_launches.fetch_add(n_launch, std::memory_order_relaxed);
 		return CACAO_OK;
 	}
-	std::lock_guard<std::mutex> lock(c->pipe_mutex);
-	rc = ensure_stage(c, samples * 2, 0, 1);
-	if(rc) return rc;
-	rc = upload_any(c, c->stage_in[0], static_cast<const uint8_t*>(src), samples * 2, c->s_run);
-	if(rc) return rc;
-	cudaError_t e = shift_left_u16_launch(c->stage_in[0], c->stage_in[0], samples, shift, c->s_run);
-	if(e != cudaSuccess) return fail_cuda(e, "shift kernel launch");
-	g_launches.fetch_add(n_launch, std::memory_order_relaxed);
-	return download_any(c, static_cast<uint8_t*>(dst), c->stage_in[0], samples * 2, c->s_run);
+	return run_host_op(c, src, samples * 2, dst, samples * 2, [&](uint8_t* s, uint8_t* d, cudaStream_t q) -> int {
+		cudaError_t e = shift_left_u16_launch(s, d, samples, shift, q);
+		if(e != cudaSuccess) return fail_cuda(e, "shift kernel launch");
+		g_launches.fetch_add(n_launch, std::memory_order_relaxed);
+		return CACAO_OK;
+	});
 }
 
 int cacao_img_downsample2x(int device, const void* src, void* dst, uint32_t w, uint32_t h, int ch, int fmt, int mem, void* stream) {
@@ -947,15 +972,12 @@ int cacao_img_downsample2x(int device, const void* src, void* dst, uint32_t w, u
 		if(e != cudaSuccess) return fail_cuda(e, "downsample kernel launch");
 		return CACAO_OK;
 	}
-	std::lock_guard<std::mutex> lock(c->pipe_mutex);
-	rc = ensure_stage(c, in_bytes, out_bytes, 1);
-	if(rc) return rc;
-	rc = upload_any(c, c->stage_in[0], static_cast<const uint8_t*>(src), in_bytes, c->s_run);
-	if(rc) return rc;
-	cudaError_t e = downsample2x_launch(c->stage_in[0], c->stage_out[0], w, h, ch, fmt, c->s_run, &launches);
-	g_launches.fetch_add(launches, std::memory_order_relaxed);
-	if(e != cudaSuccess) return fail_cuda(e, "downsample kernel launch");
-	return download_any(c, static_cast<uint8_t*>(dst), c->stage_out[0], out_bytes, c->s_run);
+	return run_host_op(c, src, in_bytes, dst, out_bytes, [&](uint8_t* s, uint8_t* d, cudaStream_t q) -> int {
+		cudaError_t e = downsample2x_launch(s, d, w, h, ch, fmt, q, &launches);
+		g_launches.fetch_add(launches, std::memory_order_relaxed);
+		if(e != cudaSuccess) return fail_cuda(e, "downsample kernel launch");
+		return CACAO_OK;
+	});
 }
 
 int cacao_img_unpack_texels(int device, const void* src, void* dst, uint64_t texels, const char* hint, int* out_channels, int mem, void* stream) {
@@ -1002,15 +1024,12 @@ int cacao_img_unpack_texels(int device, const void* src, void* dst, uint64_t tex
 		if(e != cudaSuccess) return fail_cuda(e, "texel unpack kernel launch");
 		return CACAO_OK;
 	}
-	std::lock_guard<std::mutex> lock(c->pipe_mutex);
-	rc = ensure_stage(c, texels * 4, texels * plan.out_ch, 1);
-	if(rc) return rc;
-	rc = upload_any(c, c->stage_in[0], static_cast<const uint8_t*>(src), texels * 4, c->s_run);
-	if(rc) return rc;
-	cudaError_t e = unpack_texels_launch(c->stage_in[0], c->stage_out[0], texels, plan, c->s_run, &launches);
-	g_launches.fetch_add(launches, std::memory_order_relaxed);
-	if(e != cudaSuccess) return fail_cuda(e, "texel unpack kernel launch");
-	return download_any(c, static_cast<uint8_t*>(dst), c->stage_out[0], texels * plan.out_ch, c->s_run);
+	return run_host_op(c, src, texels * 4, dst, texels * plan.out_ch, [&](uint8_t* s, uint8_t* d, cudaStream_t q) -> int {
+		cudaError_t e = unpack_texels_launch(s, d, texels, plan, q, &launches);
+		g_launches.fetch_add(launches, std::memory_order_relaxed);
+		if(e != cudaSuccess) return fail_cuda(e, "texel unpack kernel launch");
+		return CACAO_OK;
+	});
 }
 
 int cacao_img_equirect_src_window(uint32_t W, uint32_t H, uint32_t N, uint32_t face_mask, uint32_t row_begin, uint32_t row_end, uint32_t* src_row0, uint32_t* src_rows) {
