@@ -52,6 +52,16 @@ def hbm_peak() -> tuple[float, str]:
 	return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def cpu_model() -> str:
+	try:
+		for line in open("/proc/cpuinfo"):
+			if line.startswith("model name"):
+				return line.split(":", 1)[1].strip()
+	except OSError:
+		pass
+	return "unknown"
+
+
 def traffic_for(kernel_key: str):
 	"""DRAM bytes per launch from the committed `ncu --set full` capture (profiles/traffic.json)."""
 	p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -145,7 +155,7 @@ def cpu_baseline_block():
 		po.convert(src, 4, 4, po.U8, po.F16, threads=0)
 	secs = time.perf_counter() - t0
 	rate = passes * frames * PPI / secs / 1e9
-	return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{frames} of 256 frames (1920x1080 RGBA8 -> RGBA16F) x {passes} passes, oracle/cacao_oracle.c orc_convert_mt, OpenMP x{threads}, {secs:.2f} s wall = {secs * threads:.0f} core-seconds; single-thread {rate1:.4f} {UNIT}", "single_thread_value": rate1}
+	return {"value": rate, "unit": UNIT, "cpu_model": cpu_model(), "cores": threads, "kind": "port", "sample": f"{frames} of 256 frames (1920x1080 RGBA8 -> RGBA16F) x {passes} passes, oracle/cacao_oracle.c orc_convert_mt, OpenMP x{threads}, {secs:.2f} s wall = {secs * threads:.0f} core-seconds; single-thread {rate1:.4f} {UNIT}", "single_thread_value": rate1}
 
 
 def cpu_restatement_cfg1():
@@ -163,7 +173,7 @@ def cpu_restatement_cfg1():
 		for _ in range(reps):
 			po.equirect_to_cube(src, W, H, 4, po.U8, N, threads=th)
 		out[label] = reps * 6 * N * N / (time.perf_counter() - t0) / 1e9
-	out.update({"unit": UNIT, "cores": threads, "kind": "port", "sample": "whole config, oracle/cacao_oracle.c orc_equirect_to_cube (CPU restatement; no reference implementation exists)"})
+	out.update({"unit": UNIT, "cpu_model": cpu_model(), "cores": threads, "kind": "port", "sample": "whole config, oracle/cacao_oracle.c orc_equirect_to_cube (CPU restatement; no reference implementation exists)"})
 	return out
 
 
@@ -186,7 +196,7 @@ def cpu_reference_cfg4a():
 	lib.ref_batch_change_layout(src.ctypes.data, None, w, h, 3, 4, 8, 1, 1, C.byref(secs))
 	single = w * h / secs.value / 1e9
 	lib.ref_batch_change_layout(src.ctypes.data, None, w, h, 3, 4, 8, images, threads, C.byref(secs))
-	return {"value": images * w * h / secs.value / 1e9, "unit": UNIT, "cores": threads, "kind": "reference", "single_thread_value": single,
+	return {"value": images * w * h / secs.value / 1e9, "unit": UNIT, "cpu_model": cpu_model(), "cores": threads, "kind": "reference", "single_thread_value": single,
 			"sample": f"{images} of 4096 images (4096x4096 RGB8 -> RGBA8), libcacaoimage::ChangeChannelLayout as shipped, one call per image, OpenMP x{threads} over images, {secs.value:.2f} s"}
 
 
@@ -213,7 +223,7 @@ def run_reference_arm(args):
 		"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
 		"ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8->f16", "data": "synthetic",
 		"config": {"workload": WORKLOAD, "frames_per_step": frames},
-		"cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+		"cpu_baseline": {"value": value, "unit": UNIT, "cpu_model": cpu_model(), "cores": threads, "kind": "port", "sample": sample},
 		"e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
 		"gpu_launches": 0,
 	}))
