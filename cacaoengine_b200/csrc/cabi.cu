@@ -5,6 +5,7 @@
 // library: without a CUDA device every compute entry point returns CACAO_E_NO_DEVICE.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <thread>
 #include <cstdarg>
@@ -40,6 +41,27 @@ namespace {
 		t_last_error = buf;
 		return status;
 	}
+
+	// CACAO_TRACE=1: one line on stderr per host-memory call -- what ran, how many bytes went each way,
+	// which path it took and how long it blocked the caller.  (Device-memory calls only enqueue; time
+	// those with CUDA events on your stream, or with nsys / ncu.)
+	struct HostTrace {
+		const char* what;
+		const char* path = "";
+		uint64_t in_bytes = 0, out_bytes = 0;
+		std::chrono::steady_clock::time_point t0;
+		bool on;
+		explicit HostTrace(const char* w) : what(w), t0(std::chrono::steady_clock::now()) {
+			static const bool enabled = getenv("CACAO_TRACE") && getenv("CACAO_TRACE")[0] == '1';
+			on = enabled;
+		}
+		~HostTrace() {
+			if(!on) return;
+			const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+			std::fprintf(stderr, "[cacao_img] %-18s %-22s up %10llu B  down %10llu B  %9.3f ms  (%.2f GB/s through the call)\n", what, path, static_cast<unsigned long long>(in_bytes), static_cast<unsigned long long>(out_bytes), ms,
+						 ms > 0 ? static_cast<double>(in_bytes + out_bytes) / ms / 1e6 : 0.0);
+		}
+	};
 
 	int fail_cuda(cudaError_t e, const char* what) {
 		// "no device" style failures get their own status so callers can tell them from kernel faults
@@ -538,12 +560,16 @@ namespace {
 		if(sixth < chunk_px) chunk_px = sixth < 131072 ? 131072 : sixth;
 		chunk_px = ((chunk_px + 8191) / 8192) * 8192;
 		if(quirk || chunk_px > pixels) chunk_px = pixels; // the pixel-0 quirk needs each image whole
+		HostTrace trace("convert");
+		trace.in_bytes = pixels * sbpp;
+		trace.out_bytes = pixels * dbpp;
 		std::lock_guard<std::mutex> lock(c->pipe_mutex);
 		// Small images (icons, 64x64 textures): two DMA copies and their stream hops cost more than the
 		// data.  The kernel reads and writes the pinned staging slots directly over PCIe instead
 		// (host memory from cudaHostAlloc is device-addressable under unified addressing): one memcpy
 		// in, ONE stream operation, one synchronize, one memcpy out.
 		if(pixels * (sbpp + dbpp) <= zero_copy_limit()) {
+			trace.path = "zero-copy";
 			int rc0 = ensure_pinned(c, std::max<uint64_t>(pixels * sbpp, 64u << 10), std::max<uint64_t>(pixels * dbpp, 64u << 10));
 			if(rc0) return rc0;
 			std::memcpy(c->pin_in[0], src, pixels * sbpp);
@@ -557,6 +583,7 @@ namespace {
 		if(rc) return rc;
 		// pageable buffers (std::vector, numpy) travel through the pinned ring; pinned ones are DMA'd directly
 		const bool src_pg = is_pageable(src), dst_pg = is_pageable(dst);
+		trace.path = (src_pg || dst_pg) ? "pipeline, pageable" : "pipeline, pinned";
 		if(src_pg || dst_pg) {
 			rc = ensure_pinned(c, src_pg ? chunk_px * sbpp : 0, dst_pg ? chunk_px * dbpp : 0);
 			if(rc) return rc;
@@ -651,6 +678,8 @@ namespace {
 		hi = std::min<uint64_t>(hi, static_cast<uint64_t>(src_row0) + src_rows);
 		std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& a, const Piece& b) { return a.w1 != b.w1 ? a.w1 < b.w1 : a.w0 < b.w0; });
 
+		HostTrace trace("equirect_to_cube");
+		trace.in_bytes = static_cast<uint64_t>(hi - lo) * pitch;
 		std::lock_guard<std::mutex> lock(c->pipe_mutex);
 		int rc = ensure_stage(c, static_cast<uint64_t>(hi - lo) * pitch, 6 * face_bytes, 1);
 		if(rc) return rc;
@@ -665,6 +694,8 @@ namespace {
 		// download_any, with whole-face units kept whole for the four-fold kernel.
 		uint64_t out_bytes = 0;
 		for(const Piece& p : pieces) out_bytes += static_cast<uint64_t>(p.u.row_end - p.u.row_begin) * row_bytes;
+		trace.out_bytes = out_bytes;
+		trace.path = (src_pg || dst_pg) ? "sequential, pageable" : (static_cast<uint64_t>(hi - lo) * pitch + out_bytes < (32ull << 20) ? "sequential, small" : "pipelined, pinned");
 		if(src_pg || dst_pg || static_cast<uint64_t>(hi - lo) * pitch + out_bytes < (32ull << 20)) {
 			rc = upload_any(c, c->stage_in[0], up_base, static_cast<uint64_t>(hi - lo) * pitch, c->s_run);
 			if(rc) return rc;
@@ -732,7 +763,11 @@ namespace {
 	}
 
 	template<class Launch>
-	int run_host_op(DeviceCtx* c, const void* src, uint64_t in_bytes, void* dst, uint64_t out_bytes, Launch launch) {
+	int run_host_op(DeviceCtx* c, const char* what, const void* src, uint64_t in_bytes, void* dst, uint64_t out_bytes, Launch launch) {
+		HostTrace trace(what);
+		trace.in_bytes = in_bytes;
+		trace.out_bytes = out_bytes;
+		trace.path = in_bytes + out_bytes <= zero_copy_limit() ? "zero-copy" : "sequential";
 		std::lock_guard<std::mutex> lock(c->pipe_mutex);
 		if(in_bytes + out_bytes <= zero_copy_limit()) {
 			int rc = ensure_pinned(c, std::max<uint64_t>(in_bytes, 64u << 10), std::max<uint64_t>(out_bytes, 64u << 10));
@@ -921,7 +956,7 @@ int cacao_img_flip_rows(int device, const void* src, void* dst, uint32_t w, uint
 		return CACAO_OK;
 	}
 	const uint64_t bytes = pitch * h;
-	return run_host_op(c, src, bytes, dst, bytes, [&](uint8_t* s, uint8_t* d, cudaStream_t q) -> int {
+	return run_host_op(c, "flip_rows", src, bytes, dst, bytes, [&](uint8_t* s, uint8_t* d, cudaStream_t q) -> int {
 		cudaError_t e = flip_rows_launch(s, d, pitch, h, c->sm_count, q);
 		if(e != cudaSuccess) return fail_cuda(e, "flip kernel launch");
 		g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -945,7 +980,7 @@ int cacao_img_shift_left_u16(int device, const void* src, void* dst, uint64_t sa
 		g_launches.fetch_add(n_launch, std::memory_order_relaxed);
 		return CACAO_OK;
 	}
-	return run_host_op(c, src, samples * 2, dst, samples * 2, [&](uint8_t* s, uint8_t* d, cudaStream_t q) -> int {
+	return run_host_op(c, "shift_left_u16", src, samples * 2, dst, samples * 2, [&](uint8_t* s, uint8_t* d, cudaStream_t q) -> int {
 		cudaError_t e = shift_left_u16_launch(s, d, samples, shift, q);
 		if(e != cudaSuccess) return fail_cuda(e, "shift kernel launch");
 		g_launches.fetch_add(n_launch, std::memory_order_relaxed);
@@ -972,7 +1007,7 @@ int cacao_img_downsample2x(int device, const void* src, void* dst, uint32_t w, u
 		if(e != cudaSuccess) return fail_cuda(e, "downsample kernel launch");
 		return CACAO_OK;
 	}
-	return run_host_op(c, src, in_bytes, dst, out_bytes, [&](uint8_t* s, uint8_t* d, cudaStream_t q) -> int {
+	return run_host_op(c, "downsample2x", src, in_bytes, dst, out_bytes, [&](uint8_t* s, uint8_t* d, cudaStream_t q) -> int {
 		cudaError_t e = downsample2x_launch(s, d, w, h, ch, fmt, q, &launches);
 		g_launches.fetch_add(launches, std::memory_order_relaxed);
 		if(e != cudaSuccess) return fail_cuda(e, "downsample kernel launch");
@@ -1024,7 +1059,7 @@ int cacao_img_unpack_texels(int device, const void* src, void* dst, uint64_t tex
 		if(e != cudaSuccess) return fail_cuda(e, "texel unpack kernel launch");
 		return CACAO_OK;
 	}
-	return run_host_op(c, src, texels * 4, dst, texels * plan.out_ch, [&](uint8_t* s, uint8_t* d, cudaStream_t q) -> int {
+	return run_host_op(c, "unpack_texels", src, texels * 4, dst, texels * plan.out_ch, [&](uint8_t* s, uint8_t* d, cudaStream_t q) -> int {
 		cudaError_t e = unpack_texels_launch(s, d, texels, plan, q, &launches);
 		g_launches.fetch_add(launches, std::memory_order_relaxed);
 		if(e != cudaSuccess) return fail_cuda(e, "texel unpack kernel launch");
