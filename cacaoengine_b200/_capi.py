@@ -48,6 +48,7 @@ SIGNATURES = {
 	"cacao_img_equirect_to_cube_units": (_i, [_i, _vp, _u32, _u32, _u32, _u32, _i, _i, _vp, _u32, _vp, _u32, _vp]),
 	"cacao_img_equirect_to_cube_units_host": (_i, [_i, _vp, _u32, _u32, _u32, _u32, _i, _i, C.POINTER(_vp), _u32, _vp, _u32]),
 	"cacao_img_equirect_src_window": (_i, [_u32, _u32, _u32, _u32, _u32, _u32, C.POINTER(_u32), C.POINTER(_u32)]),
+	"cacao_img_equirect_fold_units": (_i, [_u32, _vp, _u32, _vp, _u32, C.POINTER(_u32)]),
 	"cacao_img_synth": (_i, [_i, _vp, _u64, _u64, _i, _i, _u32, _vp]),
 	"cacao_img_checksum": (_i, [_i, _vp, _u64, C.POINTER(_u64), _vp]),
 	"cacao_img_get_lut": (_i, [_vp]),

@@ -1074,6 +1074,20 @@ int cacao_img_equirect_src_window(uint32_t W, uint32_t H, uint32_t N, uint32_t f
 	return CACAO_OK;
 }
 
+int cacao_img_equirect_fold_units(uint32_t N, const cacao_cube_unit* units, uint32_t n_units, cacao_cube_unit* out, uint32_t cap, uint32_t* n_out) {
+	if(!n_out || (n_units && !units) || (cap && !out)) return fail(CACAO_E_BAD_ARG, "null pointer");
+	if(N == 0) return fail(CACAO_E_ZERO_DIM, "equirect: zero-sized face");
+	std::vector<CubeUnit> in;
+	for(uint32_t k = 0; k < n_units; ++k) {
+		CubeUnit u = {units[k].face, units[k].row_begin, std::min(units[k].row_end, N)};
+		if(u.face <= 5 && u.row_begin < u.row_end) in.push_back(u);
+	}
+	const std::vector<CubeUnit> folded = pair_mirror_units(in, N);
+	for(size_t k = 0; k < folded.size() && k < cap; ++k) out[k] = {folded[k].face, folded[k].row_begin, folded[k].row_end};
+	*n_out = static_cast<uint32_t>(folded.size());
+	return CACAO_OK;
+}
+
 int cacao_img_equirect_to_cube(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, uint32_t face_mask, uint32_t row_begin, uint32_t row_end, int mem, void* stream) {
 	if(!ch_ok(ch) || !fmt_ok(fmt)) return fail(CACAO_E_BAD_ARG, "equirect: bad channel count %d or format %d", ch, fmt);
 	if(W == 0 || H == 0 || N == 0) return fail(CACAO_E_ZERO_DIM, "equirect: zero-sized image or face");

@@ -11,7 +11,9 @@
 #include "equirect.cuh"
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdlib>
+#include <utility>
 #include <vector>
 
 #include "cacao_device.cuh"
@@ -307,7 +309,9 @@ namespace cacao {
 		// direction's x / z components (face_coord is bit-exactly antisymmetric), so the pair shares
 		// |x|, |z| and y: the two divisions, two polynomials and the square root of the projection are
 		// computed ONCE, the latitude (source rows, fy) is common, and only the longitude's quadrant
-		// placement differs.  With QUAD (launches whose units are whole faces) the thread also owns the
+		// placement differs.  With QUAD (launches with units that come as a band of the upper half plus
+		// its mirror band: whole faces, or the two halves of a mirror pair that a sharded rank was
+		// dealt -- pair_mirror_units() below finds them) the thread also owns the
 		// row mirror j -> N-1-j: on the side faces that negates y, hence theta exactly (atan2 is odd in
 		// y by construction) while the longitudes stay; on the +-Y faces it negates z, so the latitude
 		// stays and only the quadrant changes again.  Four pixels per projection; every value is the
@@ -321,9 +325,11 @@ namespace cacao {
 			const CubeUnit unit = prm.units[blockIdx.z];
 			const uint32_t i = blockIdx.x * WX + (threadIdx.x % WX);
 			const uint32_t j = unit.row_begin + (blockIdx.y * 4u + threadIdx.y) * RY + threadIdx.x / WX;
-			const uint32_t face = unit.face;
+			const uint32_t face = unit.face & 7u;
 			const uint32_t half = (prm.N + 1u) >> 1;
-			if(i >= half || j >= (QUAD ? half : unit.row_end)) return;
+			// a unit flagged kUnitMirror lies in the upper half of the face (row_end <= half, the launcher
+			// sees to that) and stands for its rows AND their mirror rows N-1-j
+			if(i >= half || j >= unit.row_end) return;
 			const uint32_t im = prm.N - 1u - i;
 
 			const float sc = face_coord(i, prm.pc);
@@ -349,7 +355,7 @@ namespace cacao {
 			if(im != i) sample_and_store<F, CH, IDX>(src, orow + static_cast<size_t>(im) * bpp, xs_b, W, rt, total_px);
 			if constexpr(QUAD) {
 				const uint32_t jm = prm.N - 1u - j;
-				if(jm == j) return;
+				if(!(unit.face & kUnitMirror) || jm == j) return; // uniform per block: units are indexed by blockIdx.z
 				uint8_t* mrow = dst + (static_cast<size_t>(face) * prm.N + jm) * prm.N * bpp;
 				const bool polar = (face & 6u) == 2u; // +-Y: the row mirror negates z, theta stays
 				const RowTaps<IDX> rm = polar ? rt : row_taps<IDX>(fmaf(theta, prm.pc.ky, prm.pc.cy), prm);
@@ -555,12 +561,11 @@ namespace cacao {
 			// wide enough for a warp's store to fill whole 32-byte sectors.
 			constexpr int WX = bpp >= 4 ? 8 : (bpp >= 2 ? 16 : 32);
 			block = dim3(32, 4, 1);
-			// whole faces: a thread also takes the row mirror, so only the upper half of the rows is launched
-			bool quad = true;
-			for(uint32_t u = 0; u < prm.n_units; ++u) quad = quad && prm.units[u].row_begin == 0 && prm.units[u].row_end == prm.N;
-			const char* qe = getenv("CACAO_EQUIRECT_NO_QUAD"); // test / A-B switch
-			if(qe && qe[0] == '1') quad = false;
-			const uint32_t rows = quad ? half : max_rows;
+			// units that stand for a band and its mirror band (flagged by pair_mirror_units) need the
+			// four-fold kernel; it also serves unflagged units of the same launch two-fold
+			bool quad = false;
+			for(uint32_t u = 0; u < prm.n_units; ++u) quad = quad || (prm.units[u].face & kUnitMirror) != 0;
+			const uint32_t rows = max_rows;
 			constexpr uint32_t bh = 4 * (32 / WX);
 			const dim3 ggrid((half + WX - 1) / WX, (rows + bh - 1) / bh, prm.n_units);
 			const uint8_t* s8 = static_cast<const uint8_t*>(src);
@@ -590,6 +595,84 @@ namespace cacao {
 		}
 	}
 
+	// Rows j and N-1-j of a face share their whole projection (equirect_kernel), so a band that arrives
+	// together with its mirror band -- a whole face, a band around the centre row, the two units of a
+	// mirror pair in a sharded rank's list, the two polar bands with the same source window in the host
+	// pipeline -- is folded into ONE unit of the upper half flagged kUnitMirror.  Rows whose mirror is
+	// not in the list stay plain units, and so do overlaps of fewer than 16 rows (one block's height):
+	// a sliver would only add a launch.  Every (face, row) of the input is covered exactly as often as
+	// before; only who computes it changes, and the values are bit-identical either way.
+	std::vector<CubeUnit> pair_mirror_units(const std::vector<CubeUnit>& in, uint32_t N) {
+		using Iv = std::pair<uint32_t, uint32_t>;
+		const uint32_t half = (N + 1u) >> 1; // upper half incl. the centre row of an odd face
+		const uint32_t min_fold = std::min(16u, half);
+		// sort by first row, then join intervals that touch (never ones that overlap: rows the caller
+		// names twice are computed twice, as before)
+		auto join = [](std::vector<Iv>& v) {
+			std::sort(v.begin(), v.end());
+			std::vector<Iv> r;
+			for(const Iv& iv : v) {
+				bool done = false;
+				for(Iv& q : r)
+					if(q.second == iv.first) {
+						q.second = iv.second;
+						done = true;
+						break;
+					}
+				if(!done) r.push_back(iv);
+			}
+			v.swap(r);
+		};
+		std::vector<CubeUnit> out;
+		for(uint32_t f = 0; f < 6; ++f) {
+			// per face: intervals of upper rows present as themselves (A) and as mirror images of present
+			// lower rows (B), both in upper-half coordinates
+			std::vector<Iv> A, B;
+			std::vector<uint32_t> cuts;
+			for(const CubeUnit& u : in) {
+				if(u.face != f || u.row_begin >= u.row_end) continue;
+				if(u.row_begin < half) A.push_back({u.row_begin, std::min(u.row_end, half)});
+				// the centre row of an odd face is its own mirror: N - half == half - 1 puts it in B as well
+				const uint32_t lb = std::max(u.row_begin, N - half);
+				if(u.row_end > lb) B.push_back({N - u.row_end, N - lb});
+			}
+			for(const Iv& iv : A) cuts.push_back(iv.first), cuts.push_back(iv.second);
+			for(const Iv& iv : B) cuts.push_back(iv.first), cuts.push_back(iv.second);
+			std::sort(cuts.begin(), cuts.end());
+			cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+			auto count = [](const std::vector<Iv>& v, uint32_t s) {
+				uint32_t n = 0;
+				for(const Iv& iv : v) n += (iv.first <= s && s < iv.second) ? 1u : 0u;
+				return n;
+			};
+			std::vector<Iv> both, upper, lower; // all in upper-half coordinates
+			for(size_t k = 0; k + 1 < cuts.size(); ++k) {
+				const Iv seg{cuts[k], cuts[k + 1]};
+				uint32_t a = count(A, seg.first), b = count(B, seg.first);
+				for(; a > 0 && b > 0; --a, --b) both.push_back(seg);
+				for(; a > 0; --a) upper.push_back(seg);
+				for(; b > 0; --b) lower.push_back(seg);
+			}
+			join(both);
+			for(size_t k = 0; k < both.size();) {
+				if(both[k].second - both[k].first < min_fold) {
+					upper.push_back(both[k]);
+					// an odd face's centre row was listed on both sides only as its own mirror
+					const uint32_t e = ((N & 1u) && both[k].second == half) ? half - 1u : both[k].second;
+					if(e > both[k].first) lower.push_back({both[k].first, e});
+					both.erase(both.begin() + static_cast<std::ptrdiff_t>(k));
+				} else
+					++k;
+			}
+			// plain rows in face coordinates, joined across the centre line
+			for(const Iv& iv : lower) upper.push_back({N - iv.second, N - iv.first});
+			join(upper);
+			for(const Iv& iv : both) out.push_back({f | kUnitMirror, iv.first, iv.second});
+			for(const Iv& iv : upper) out.push_back({f, iv.first, iv.second});
+		}
+		return out;
+	}
+
 	cudaError_t equirect_launch_units(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, const CubeUnit* units, uint32_t n_units, cudaStream_t stream, unsigned* launches) {
 		if(launches) *launches = 0;
 		EquirectParams prm;
@@ -607,14 +690,20 @@ namespace cacao {
 		// of its first one.  A rank's mixed list of side-face and half-height polar bands then still is
 		// ONE launch without empty blocks.
 		std::vector<CubeUnit> todo;
-		uint32_t hmin = 0xFFFFFFFFu, hmax = 0;
 		for(uint32_t k = 0; k < n_units; ++k) {
 			CubeUnit u = units[k];
 			if(u.row_end > N) u.row_end = N;
 			if(u.face > 5 || u.row_begin >= u.row_end) continue;
+			todo.push_back(u);
+		}
+		// test / A-B switches: two-fold sharing only; the staged experiment knows plain units only
+		const char* qe = getenv("CACAO_EQUIRECT_NO_QUAD");
+		const char* se = getenv("CACAO_EQUIRECT_STAGED");
+		if(!(qe && qe[0] == '1') && !(se && se[0] == '1')) todo = pair_mirror_units(todo, N);
+		uint32_t hmin = 0xFFFFFFFFu, hmax = 0;
+		for(const CubeUnit& u : todo) {
 			hmin = std::min(hmin, u.row_end - u.row_begin);
 			hmax = std::max(hmax, u.row_end - u.row_begin);
-			todo.push_back(u);
 		}
 		// gridDim.y is limited to 65535 blocks of at least 4 rows
 		constexpr uint32_t kMaxRows = 65535u * 4u;

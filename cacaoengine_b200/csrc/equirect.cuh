@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <vector>
 
 #include "projection.cuh"
 
@@ -15,6 +16,9 @@ namespace cacao {
 	struct CubeUnit {
 		uint32_t face, row_begin, row_end;
 	};
+	// Internal to the launcher and the kernel (callers' units have face 0..5): the unit lies in the upper
+	// half of its face and stands for its rows and their mirror rows N-1-j.
+	constexpr uint32_t kUnitMirror = 8u;
 
 	struct EquirectParams {
 		uint32_t W, H;               // source size in pixels
@@ -28,6 +32,10 @@ namespace cacao {
 	// Enqueue the resampling of a list of (face, row band) units in as few launches as their heights allow
 	// (normally one), *launches gets the count.
 	cudaError_t equirect_launch_units(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, const CubeUnit* units, uint32_t n_units, cudaStream_t stream, unsigned* launches);
+
+	// The folding step of equirect_launch_units on its own (host only): mirror bands of the input become
+	// single units flagged kUnitMirror; units with face > 5 or no rows are dropped.
+	std::vector<CubeUnit> pair_mirror_units(const std::vector<CubeUnit>& in, uint32_t N);
 
 	// Enqueue the resampling of rows [row_begin,row_end) of every face in face_mask (one launch).
 	cudaError_t equirect_launch(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, uint32_t face_mask, uint32_t row_begin, uint32_t row_end, cudaStream_t stream);

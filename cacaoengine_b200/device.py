@@ -116,6 +116,20 @@ def equirect_src_window(W: int, H: int, N: int, face_mask: int, row_begin: int, 
 	return int(r0.value), int(n.value)
 
 
+UNIT_MIRROR = 8
+
+
+def equirect_fold_units(N: int, units) -> list[tuple[int, int, int]]:
+	"""The launcher's folding of a unit list (host only): (face | UNIT_MIRROR, r0, r1) stands for rows
+	[r0, r1) of the upper half and their mirror rows N-1-j, plain (face, r0, r1) for the rest."""
+	flat = np.array([(u.face, u.row_begin, u.row_end) if hasattr(u, "face") else tuple(u) for u in units], np.uint32).reshape(-1, 3)
+	n = C.c_uint32()
+	capi.check(capi.lib().cacao_img_equirect_fold_units(N, flat.ctypes.data, len(flat), None, 0, C.byref(n)))
+	out = np.zeros((max(1, n.value), 3), np.uint32)
+	capi.check(capi.lib().cacao_img_equirect_fold_units(N, flat.ctypes.data, len(flat), out.ctypes.data, n.value, C.byref(n)))
+	return [tuple(int(v) for v in row) for row in out[: n.value]]
+
+
 def synth(dst: int, samples: int, fmt: int, ch: int, seed: int, first_sample: int = 0, device: int = -1, stream=None) -> None:
 	capi.check(capi.lib().cacao_img_synth(device, dst, first_sample, samples, fmt, ch, seed, stream))
 

@@ -194,6 +194,16 @@ int cacao_img_equirect_to_cube_units_host(int device, const void* src, uint32_t 
 int cacao_img_equirect_src_window(uint32_t W, uint32_t H, uint32_t N, uint32_t face_mask, uint32_t row_begin,
 								  uint32_t row_end, uint32_t* src_row0, uint32_t* src_rows);
 
+/* Host-side planning: how the launcher folds a unit list before it goes to the device.  A band that is
+ * listed together with its mirror band on the same face (rows j and N-1-j: a whole face, the two
+ * units of a mirror pair dealt by sharding.py, ...) becomes ONE unit of the upper half whose face has
+ * CACAO_UNIT_MIRROR set -- the kernel then computes one projection per four pixels instead of per
+ * two.  Rows without a listed mirror stay plain units.  Writes at most `cap` units to `out`
+ * and the full count to *n_out (call with cap = 0 to size the buffer). */
+#define CACAO_UNIT_MIRROR 8u
+int cacao_img_equirect_fold_units(uint32_t N, const cacao_cube_unit* units, uint32_t n_units, cacao_cube_unit* out,
+								  uint32_t cap, uint32_t* n_out);
+
 /* ---- support for measurement and verification (device-side, deterministic) ---------------- */
 
 /* Fill dst_dev with the counter-hash synthetic samples [first_sample, first_sample+samples)

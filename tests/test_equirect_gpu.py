@@ -163,7 +163,8 @@ def test_unit_list_launch_matches_per_unit_calls(oracle):
 	device.download(got, b.ptr)
 	assert same_bits(got, want)
 	# a launch's grid is as tall as its tallest unit, so very different heights go to separate launches
-	# (70 | 35, 34 | 10 rows -> three); heights within a factor of eight are cut to a common height instead
+	# (the whole face folds onto its upper 35 rows: 35, 35, 34 | 10 rows -> two); heights within a factor
+	# of eight are cut to a common height instead
 	mixed = [(0, 0, 70), (3, 10, 20), (1, 0, 35), (2, 36, 70)]
 	want2 = np.zeros_like(want)
 	for f, r0, r1 in mixed:
@@ -171,7 +172,7 @@ def test_unit_list_launch_matches_per_unit_calls(oracle):
 	device.upload(b.ptr, np.zeros_like(want))
 	before = device.launch_count()
 	device.equirect_to_cube_units(a.ptr, W, H, ch, fmt, b.ptr, N, mixed)
-	assert device.launch_count() - before == 3
+	assert device.launch_count() - before == 2
 	device.download(got, b.ptr)
 	assert same_bits(got, want2)
 	similar = [(0, 0, 70), (1, 0, 35), (2, 36, 70), (4, 3, 40)]  # 70 -> 2 x 35: one launch of five pieces
@@ -187,6 +188,48 @@ def test_unit_list_launch_matches_per_unit_calls(oracle):
 	assert same_bits(got, want3)
 	with pytest.raises(c.CacaoError):
 		device.equirect_to_cube_units(1, W, H, ch, fmt, 1, N, [(7, 0, 1)])
+
+
+@pytest.mark.parametrize("fmt,ch,N", [(3, 4, 70), (0, 4, 71), (2, 3, 45), (1, 1, 96), (0, 3, 33)], ids=["f32x4-70", "u8x4-71", "f16x3-45", "u16x1-96", "u8x3-33"])
+def test_mirror_folded_unit_lists_match_the_oracle(oracle, fmt, ch, N):
+	"""Lists in which bands meet their mirror bands (folded by the launcher into four-fold units), meet
+	them partly, or not at all -- odd and even faces, rows named twice, one-row bands at the centre:
+	exactly the listed rows are written and they equal the oracle's."""
+	from cacaoengine_b200 import device
+
+	W, H = 4 * N + 3, 2 * N + 1
+	src = oracle.synth(W * H * ch, fmt, ch, 40 + N)
+	full = oracle.equirect_to_cube(src, W, H, ch, fmt, N)
+	a, b = DevBuf(src.nbytes), DevBuf(full.nbytes)
+	device.upload(a.ptr, src)
+	c0, q = (N - 1) // 2, N // 4
+	lists = [
+		[(f, 0, N) for f in range(6)],
+		[(0, 0, q), (0, N - q, N), (2, q, N - q), (3, 0, c0), (3, c0, c0 + 1), (3, c0 + 1, N)],
+		[(1, 0, N // 2 + 5), (1, N // 2 - 7, N), (4, 3, N - 20), (5, c0, c0 + 1), (2, N - 18, N), (2, 0, 17)],
+		[(4, 0, q), (4, N - q, N - 1), (5, 1, q + 20), (5, N - q - 20, N), (0, N // 2, N)],
+	]
+	rng = np.random.default_rng(N)
+	for _ in range(4):
+		units = []
+		for _ in range(int(rng.integers(2, 9))):
+			r0, r1 = sorted(int(v) for v in rng.integers(0, N + 1, 2))
+			f = int(rng.integers(0, 6))
+			units.append((f, r0, r1))
+			if rng.random() < 0.6:
+				units.append((f, N - r1, N - r0))
+		lists.append(units)
+	for units in lists:
+		want = np.zeros_like(full)
+		for f, r0, r1 in units:
+			sl = slice((f * N + r0) * N * ch, (f * N + r1) * N * ch)
+			want[sl] = full[sl]
+		device.upload(b.ptr, np.zeros_like(full))
+		device.equirect_to_cube_units(a.ptr, W, H, ch, fmt, b.ptr, N, units)
+		got = np.empty_like(full)
+		device.download(got, b.ptr)
+		assert same_bits(got, want), (units, device.equirect_fold_units(N, units))
+	a.free(), b.free()
 
 
 @pytest.mark.parametrize("fmt,ch", [(3, 4), (2, 4), (0, 4), (3, 1), (1, 4)], ids=["f32x4", "f16x4", "u8x4", "f32x1", "u16x4"])

@@ -119,9 +119,83 @@ def test_cube_units_deal_evenly():
 				owner[u.face, u.row_begin:u.row_end] += 1
 		assert (owner == 1).all()
 		costs = [sum(sharding.unit_cost(u, N) for u in us) for us in per_rank]
-		assert max(costs) <= 1.05 * sum(costs) / world, (world, costs)
-		assert all(len(us) <= 8 for us in per_rank) or world < 4  # fits one kernel launch per rank
+		assert max(costs) <= 1.03 * sum(costs) / world, (world, costs)
+		# a band always travels with its mirror band (the launcher folds the two into one four-fold unit)
+		for us in per_rank:
+			have = {(u.face, u.row_begin, u.row_end) for u in us}
+			assert all((u.face, N - u.row_end, N - u.row_begin) in have for u in us)
+		assert all(len(us) <= 32 for us in per_rank) or world < 4  # fits one kernel launch per rank
 	# determinism: every rank derives the same global plan
 	assert sharding.units_for_rank(3, 8, 4096) == sharding.units_for_rank(3, 8, 4096)
 	polar = sharding.CubeUnit(2, 1792, 2304)
 	assert sharding.unit_cost(polar, 4096) > 2.0 * sharding.unit_cost(sharding.CubeUnit(0, 1792, 2304), 4096)
+
+
+def test_band_edges_are_mirror_symmetric():
+	from cacaoengine_b200 import sharding
+
+	for N in (1, 2, 5, 40, 41, 70, 4096):
+		for n in (1, 2, 3, 4, 5, 8, 16):
+			e = sharding.band_edges(N, n)
+			assert e[0] == 0 and e[-1] == N and all(a <= b for a, b in zip(e, e[1:]))
+			# band k mirrors band n-1-k, up to the centre row of an odd face (kept by the upper band)
+			for k in range(len(e) - 1):
+				lo, hi = N - e[len(e) - 1 - k], N - e[len(e) - 2 - k]
+				assert abs(lo - e[k]) <= (N & 1) and abs(hi - e[k + 1]) <= (N & 1)
+		units = sharding.cube_units(N, 4, 2)
+		owner = np.zeros((6, N), np.int32)
+		for u in units:
+			owner[u.face, u.row_begin:u.row_end] += 1
+		assert (owner == 1).all()
+
+
+def test_fold_units_keeps_the_cover(built_lib):
+	"""cacao_img_equirect_fold_units (the launcher's planning step, host only): whatever the list --
+	whole faces, mirror pairs, partial overlaps, odd faces, rows named twice -- every (face, row) is
+	computed exactly as often as the caller listed it, mirror units stay inside the upper half, and
+	slivers are not folded."""
+	from cacaoengine_b200 import device, sharding
+
+	M = device.UNIT_MIRROR
+
+	def cover(N, units, folded=False):
+		own = np.zeros((6, N), np.int32)
+		for f, r0, r1 in units:
+			if folded and f & M:
+				assert r1 <= (N + 1) // 2 and r1 - r0 >= min(16, (N + 1) // 2)
+				own[f & 7, r0:r1] += 1
+				for j in range(r0, r1):
+					if N - 1 - j != j:
+						own[f & 7, N - 1 - j] += 1
+			else:
+				assert f <= 5
+				own[f, r0:min(r1, N)] += 1
+		return own
+
+	for N in (1, 2, 9, 64, 70, 71):
+		whole = [(f, 0, N) for f in range(6)]
+		folded = device.equirect_fold_units(N, whole)
+		assert folded == [(f | M, 0, (N + 1) // 2) for f in range(6)]
+		assert (cover(N, folded, True) == 1).all()
+	assert device.equirect_fold_units(70, [(0, 0, 70), (1, 0, 35), (2, 36, 70), (4, 3, 40)]) == [(M, 0, 35), (1, 0, 35), (2, 36, 70), (4, 3, 40)]
+	assert device.equirect_fold_units(71, [(2, 30, 40), (3, 35, 36)]) == [(2, 30, 40), (3, 35, 36)]
+	assert device.equirect_fold_units(64, [(7, 0, 3), (1, 5, 5), (9, 0, 64)]) == []
+	# a sharded rank's list folds completely: half as many units, all mirrored
+	for world in (2, 4, 8):
+		for rank in range(world):
+			us = sharding.units_for_rank(rank, world, 4096)
+			folded = device.equirect_fold_units(4096, us)
+			assert all(f & M for f, _, _ in folded) and sum(r1 - r0 for _, r0, r1 in folded) * 2 == sum(u.rows for u in us)
+			assert (cover(4096, folded, True) == cover(4096, [(u.face, u.row_begin, u.row_end) for u in us])).all()
+	rng = np.random.default_rng(7)
+	for trial in range(300):
+		N = int(rng.choice([1, 2, 3, 17, 40, 41, 100, 129]))
+		units = []
+		for _ in range(int(rng.integers(0, 9))):
+			a, b = sorted(int(v) for v in rng.integers(0, N + 1, 2))
+			units.append((int(rng.integers(0, 6)), a, b + int(rng.integers(0, 2)) * (b == N)))  # now and then past the face's end
+		if rng.random() < 0.3 and units:  # mirror of an existing unit
+			f, a, b = units[0]
+			units.append((f, N - min(b, N), N - a))
+		folded = device.equirect_fold_units(N, units)
+		assert (cover(N, folded, True) == cover(N, [u for u in units if u[1] < min(u[2], N)])).all(), (N, units, folded)
