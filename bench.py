@@ -135,24 +135,33 @@ def cpu_convert_rate(frames: int, threads: int, repeats: int = 1):
 	return frames * PPI / best / 1e9, best
 
 
+def host_threads():
+	"""All the host cores this process may run on.  Not omp_get_max_threads(): torchrun exports
+	OMP_NUM_THREADS=1 to every rank, which would turn the CPU arm into a single-thread run."""
+	try:
+		return max(1, len(os.sched_getaffinity(0)))
+	except AttributeError:
+		return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline_block():
 	"""The CPU oracle on a bounded sample of the same workload: 64 of the 256 frames, converted
 	repeatedly until about 15 core-seconds of CPU work have been spent; mean rate over the passes."""
 	from oracle import pyoracle as po
 
 	po.build()
-	threads = po.port().orc_max_threads()
+	threads = host_threads()
 	rate1, _ = cpu_convert_rate(2, 1, repeats=3)
 	frames = 64
 	src = po.synth(frames * PPI * 4, po.U8, 4, 0xC0FFEE + 2)
-	po.convert(src, 4, 4, po.U8, po.F16, threads=0)  # warm: page in the output pool, spin up the team
+	po.convert(src, 4, 4, po.U8, po.F16, threads=threads)  # warm: page in the output pool, spin up the team
 	t0 = time.perf_counter()
-	po.convert(src, 4, 4, po.U8, po.F16, threads=0)
+	po.convert(src, 4, 4, po.U8, po.F16, threads=threads)
 	once = time.perf_counter() - t0
 	passes = int(max(3, min(200, 15.0 / max(once * threads, 1e-6))))
 	t0 = time.perf_counter()
 	for _ in range(passes):
-		po.convert(src, 4, 4, po.U8, po.F16, threads=0)
+		po.convert(src, 4, 4, po.U8, po.F16, threads=threads)
 	secs = time.perf_counter() - t0
 	rate = passes * frames * PPI / secs / 1e9
 	return {"value": rate, "unit": UNIT, "cpu_model": cpu_model(), "cores": threads, "kind": "port", "sample": f"{frames} of 256 frames (1920x1080 RGBA8 -> RGBA16F) x {passes} passes, oracle/cacao_oracle.c orc_convert_mt, OpenMP x{threads}, {secs:.2f} s wall = {secs * threads:.0f} core-seconds; single-thread {rate1:.4f} {UNIT}", "single_thread_value": rate1}
@@ -165,9 +174,9 @@ def cpu_restatement_cfg1():
 
 	W, H, N = 2048, 1024, 512
 	src = po.synth(W * H * 4, po.U8, 4, 0xC0FFEE)
-	threads = po.port().orc_max_threads()
+	threads = host_threads()
 	out = {}
-	for label, th, reps in (("single_thread_value", 1, 2), ("value", 0, 5)):
+	for label, th, reps in (("single_thread_value", 1, 2), ("value", threads, 5)):
 		po.equirect_to_cube(src, W, H, 4, po.U8, N, threads=th)
 		t0 = time.perf_counter()
 		for _ in range(reps):
@@ -188,7 +197,7 @@ def cpu_reference_cfg4a():
 	if not po.have_ref():
 		return {"unavailable": "oracle/_ref/libcacaoimage_ref.so was not built (no /root/reference at build time)"}
 	lib = po.ref()
-	threads = lib.ref_max_threads()
+	threads = host_threads()
 	w = h = 4096
 	images = max(4, min(16, threads))
 	src = po.synth(images * w * h * 3, po.U8, 3, 0xC0FFEE + 4)
@@ -208,14 +217,14 @@ def run_reference_arm(args):
 	from oracle import pyoracle as po
 
 	po.build()
-	threads = po.port().orc_max_threads()
+	threads = host_threads()
 	frames = 64
 	src = po.synth(frames * PPI * 4, po.U8, 4, 0xC0FFEE + 2)
 	for _ in range(max(args.warmup, 1)):
-		po.convert(src, 4, 4, po.U8, po.F16, threads=0)
+		po.convert(src, 4, 4, po.U8, po.F16, threads=threads)
 	t0 = time.perf_counter()
 	for _ in range(args.steps):
-		po.convert(src, 4, 4, po.U8, po.F16, threads=0)
+		po.convert(src, 4, 4, po.U8, po.F16, threads=threads)
 	dt = time.perf_counter() - t0
 	value = frames * PPI * args.steps / dt / 1e9
 	sample = f"each step = {frames} of 256 frames, oracle/cacao_oracle.c orc_convert_mt with {threads} OpenMP threads (the reference has no RGBA8->RGBA16F: libcacaoimage.hpp:20)"
