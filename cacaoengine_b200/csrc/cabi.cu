@@ -305,45 +305,6 @@ namespace {
 		return CACAO_OK;
 	}
 
-	// Returns the context for `device` (creating it on first use) with the device made current.
-	int get_ctx(int device, DeviceCtx** out, DeviceGuard& guard) {
-		int dev = 0;
-		int rc = resolve_device(device, &dev);
-		if(rc) return rc;
-		rc = guard.enter(dev);
-		if(rc) return rc;
-		std::lock_guard<std::mutex> lock(g_ctx_mutex);
-		if(!g_ctx[dev]) {
-			DeviceCtx* c = new DeviceCtx();
-			c->device = dev;
-			cudaDeviceProp prop;
-			CU_TRY(cudaGetDeviceProperties(&prop, dev));
-			if(prop.major < 10) {
-				delete c;
-				return fail(CACAO_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
-			}
-			c->sm_count = prop.multiProcessorCount;
-			c->smem_optin = prop.sharedMemPerBlockOptin;
-			CU_TRY(cudaMalloc(&c->lut_dev, 65536));
-			CU_TRY(cudaMemcpy(c->lut_dev, host_lut().table, 65536, cudaMemcpyHostToDevice));
-			if(!host_lut().two_level_ok) return fail(CACAO_E_BAD_ARG, "internal: two-level 16->8 table does not reproduce the reference table");
-			CU_TRY(cudaMalloc(&c->lut2_dev, sizeof(host_lut().two_level)));
-			CU_TRY(cudaMemcpy(c->lut2_dev, host_lut().two_level, sizeof(host_lut().two_level), cudaMemcpyHostToDevice));
-			CU_TRY(cudaMalloc(&c->checksum_dev, sizeof(unsigned long long)));
-			CU_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
-			CU_TRY(cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking));
-			CU_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-			for(int s = 0; s < kSlots; ++s) {
-				CU_TRY(cudaEventCreateWithFlags(&c->ev_in[s], cudaEventDisableTiming));
-				CU_TRY(cudaEventCreateWithFlags(&c->ev_run[s], cudaEventDisableTiming));
-				CU_TRY(cudaEventCreateWithFlags(&c->ev_out[s], cudaEventDisableTiming));
-			}
-			g_ctx[dev] = c;
-		}
-		*out = g_ctx[dev];
-		return CACAO_OK;
-	}
-
 	void destroy_ctx(DeviceCtx* c) {
 		int prev = 0;
 		cudaGetDevice(&prev);
@@ -366,6 +327,54 @@ namespace {
 		if(c->checksum_dev) cudaFree(c->checksum_dev);
 		cudaSetDevice(prev);
 		delete c;
+	}
+
+	// Creates everything a device context owns; on failure the caller destroys the partial context.
+	int init_ctx(DeviceCtx* c, int dev) {
+		c->device = dev;
+		cudaDeviceProp prop;
+		CU_TRY(cudaGetDeviceProperties(&prop, dev));
+		if(prop.major < 10) return fail(CACAO_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+		c->sm_count = prop.multiProcessorCount;
+		c->smem_optin = prop.sharedMemPerBlockOptin;
+		if(!host_lut().two_level_ok) return fail(CACAO_E_BAD_ARG, "internal: two-level 16->8 table does not reproduce the reference table");
+		CU_TRY(cudaMalloc(&c->lut_dev, 65536));
+		CU_TRY(cudaMemcpy(c->lut_dev, host_lut().table, 65536, cudaMemcpyHostToDevice));
+		CU_TRY(cudaMalloc(&c->lut2_dev, sizeof(host_lut().two_level)));
+		CU_TRY(cudaMemcpy(c->lut2_dev, host_lut().two_level, sizeof(host_lut().two_level), cudaMemcpyHostToDevice));
+		CU_TRY(cudaMalloc(&c->checksum_dev, sizeof(unsigned long long)));
+		CU_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+		CU_TRY(cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking));
+		CU_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+		for(int s = 0; s < kSlots; ++s) {
+			CU_TRY(cudaEventCreateWithFlags(&c->ev_in[s], cudaEventDisableTiming));
+			CU_TRY(cudaEventCreateWithFlags(&c->ev_run[s], cudaEventDisableTiming));
+			CU_TRY(cudaEventCreateWithFlags(&c->ev_out[s], cudaEventDisableTiming));
+		}
+		return CACAO_OK;
+	}
+
+	// Returns the context for `device` (creating it on first use) with the device made current.
+	int get_ctx(int device, DeviceCtx** out, DeviceGuard& guard) {
+		int dev = 0;
+		int rc = resolve_device(device, &dev);
+		if(rc) return rc;
+		rc = guard.enter(dev);
+		if(rc) return rc;
+		std::lock_guard<std::mutex> lock(g_ctx_mutex);
+		if(!g_ctx[dev]) {
+			DeviceCtx* c = new DeviceCtx();
+			rc = init_ctx(c, dev);
+			if(rc) {
+				const std::string why = t_last_error; // destroy_ctx makes CUDA calls of its own
+				destroy_ctx(c);
+				t_last_error = why;
+				return rc;
+			}
+			g_ctx[dev] = c;
+		}
+		*out = g_ctx[dev];
+		return CACAO_OK;
 	}
 
 	// Device staging buffers of the host-memory paths.  The chunked conversion pipeline uses all kSlots
