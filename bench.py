@@ -311,15 +311,17 @@ def verify_ring(device, dev, src, dst, px, ring, dfmt, dbytes):
 def extra_configs(torch, dist, world, rank, dev, stream, peak):
 	"""The other BASELINE configs, device-resident, sharded over the ranks exactly as DESIGN.md
 	"Multi-GPU" says (images by index, cube by face/row band); rooflines are per GPU (x world)."""
-	from cacaoengine_b200 import FMT_F32, FMT_U8, MEM_HOST, device, sharding
+	from cacaoengine_b200 import FMT_F16, FMT_F32, FMT_U8, MEM_HOST, device, sharding
 
 	out = {}
 
 	def alloc(n):
 		return torch.empty(max(n, 16), dtype=torch.uint8, device=f"cuda:{dev}")
 
-	def equirect(key, W, H, N, ch, fmt, bps, steps, note=None, e2e=False):
+	def equirect(key, W, H, N, ch, fmt, bps, steps, note=None, e2e=False, dst=None):
 		bpp = ch * bps
+		if dst is not None:
+			return equirect_fused(key, W, H, N, ch, fmt, bps, steps, note, *dst)
 		units = sharding.units_for_rank(rank, world, N) if world > 1 else [sharding.CubeUnit(-1, 0, N)]
 		if world > 1:
 			w0, wn = sharding.source_window(units, W, H, N)
@@ -360,7 +362,29 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 			device.host_free(sp), device.host_free(dp)
 		del src, dst
 
+	def equirect_fused(key, W, H, N, ch, fmt, bps, steps, note, dch, dfmt, dbps):
+		"""Resample + convert in one pass (Spec B.4) against the same job as two passes on the device."""
+		sbpp, dbpp = ch * bps, dch * dbps
+		src, mid, dst2, dst = alloc(W * H * sbpp), alloc(6 * N * N * sbpp), alloc(6 * N * N * dbpp), alloc(6 * N * N * dbpp)
+		device.synth(src.data_ptr(), W * H * ch, fmt, ch, 0xC0FFEE + 3, device=dev, stream=stream)
+
+		def fused():
+			device.equirect_to_cube_cvt(src.data_ptr(), W, H, ch, fmt, dst.data_ptr(), N, dch, dfmt, device=dev, stream=stream)
+
+		def two_pass():
+			device.equirect_to_cube(src.data_ptr(), W, H, ch, fmt, mid.data_ptr(), N, 0x3F, 0, N, device=dev, stream=stream)
+			device.convert(mid.data_ptr(), dst2.data_ptr(), 6 * N * N, ch, dch, fmt, dfmt, device=dev, stream=stream)
+
+		ms2 = timed_region(torch, dist, 1, two_pass, steps, 3)
+		ms = timed_region(torch, dist, 1, fused, steps, 3)
+		same = device.checksum(dst.data_ptr(), 6 * N * N * dbpp, device=dev, stream=stream) == device.checksum(dst2.data_ptr(), 6 * N * N * dbpp, device=dev, stream=stream)
+		alg = W * H * sbpp + 6 * N * N * dbpp
+		out[key] = {"value": 6 * N * N / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "n_gpus": 1, "roofline": roof(alg, ms, peak, traffic_for(key)),
+					"two_pass": {"value": 6 * N * N / ms2 / 1e6, "ms_per_step": ms2, "note": "cacao_img_equirect_to_cube then cacao_img_convert on the device"}, "equals_two_pass": bool(same), "note": note}
+		del src, mid, dst2, dst
+
 	if world == 1:
+		equirect("cfg3_fused_rgba32f_to_rgba16f_cube", 8192, 4096, 2048, 4, FMT_F32, 4, 20, "config 3 with the cube written as RGBA16F in the same pass (Spec B.4): resample + format convert", dst=(4, FMT_F16, 2))
 		equirect("cfg1_equirect_2048x1024_rgba8_to_6x512", 2048, 1024, 512, 4, FMT_U8, 1, 50, "14.7 MB problem: fits L2, launch-latency bound")
 		equirect("cfg3_equirect_8192x4096_rgba32f_to_6x2048", 8192, 4096, 2048, 4, FMT_F32, 4, 20, e2e=True)
 	# sharded, a step is one ~0.1 ms launch per rank: more of them, so that the Python call ahead of the

@@ -652,16 +652,17 @@ namespace {
 	// directions at once and the call costs about max(upload, readback) instead of their sum.
 	// Pinned buffers only; pageable ones and small jobs take the sequential form below.
 	// faces[f] = host base of face f (N x N pixels), only needed for faces that units name.
-	int equirect_host_pipeline(DeviceCtx* c, const uint8_t* hsrc, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, uint8_t* const* faces, uint32_t N, const CubeUnit* units_in, uint32_t n_units_in) {
-		const uint64_t bpp = static_cast<uint64_t>(ch) * fmt_bytes(fmt);
+	int equirect_host_pipeline(DeviceCtx* c, const uint8_t* hsrc, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, uint8_t* const* faces, uint32_t N, const CubeUnit* units_in, uint32_t n_units_in, int dst_ch, int dst_fmt) {
+		const uint64_t bpp = static_cast<uint64_t>(ch) * fmt_bytes(fmt);             // source texel
+		const uint64_t dbpp = static_cast<uint64_t>(dst_ch) * fmt_bytes(dst_fmt);    // face texel (fused conversion: may differ)
 		const uint64_t pitch = static_cast<uint64_t>(W) * bpp;
-		const uint64_t face_bytes = static_cast<uint64_t>(N) * N * bpp;
+		const uint64_t face_bytes = static_cast<uint64_t>(N) * N * dbpp;
 		struct Piece {
 			CubeUnit u;
 			uint32_t w0, w1; // source rows [w0, w1) it reads
 		};
 		std::vector<Piece> pieces;
-		const uint64_t row_bytes = static_cast<uint64_t>(N) * bpp;
+		const uint64_t row_bytes = static_cast<uint64_t>(N) * dbpp;
 		const uint32_t band_rows = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(N, (16ull << 20) / row_bytes)));
 		uint32_t lo = UINT32_MAX, hi = 0;
 		for(uint32_t k = 0; k < n_units_in; ++k) {
@@ -709,7 +710,7 @@ namespace {
 			rc = upload_any(c, c->stage_in[0], up_base, static_cast<uint64_t>(hi - lo) * pitch, c->s_run);
 			if(rc) return rc;
 			unsigned launches = 0;
-			cudaError_t e = equirect_launch_units(c->stage_in[0], c->stage_out[0], ch, fmt, W, H, lo, hi - lo, N, units_in, n_units_in, c->s_run, &launches);
+			cudaError_t e = equirect_launch_units(c->stage_in[0], c->stage_out[0], ch, fmt, W, H, lo, hi - lo, N, units_in, n_units_in, c->s_run, &launches, dst_ch, dst_fmt);
 			g_launches.fetch_add(launches, std::memory_order_relaxed);
 			if(e != cudaSuccess) return fail_cuda(e, "equirect kernel launch");
 			std::vector<Segment> segs;
@@ -747,7 +748,7 @@ namespace {
 				std::vector<CubeUnit> batch;
 				for(size_t q = next; q < ready_end; ++q) batch.push_back(pieces[q].u);
 				unsigned launches = 0;
-				cudaError_t e = equirect_launch_units(c->stage_in[0], c->stage_out[0], ch, fmt, W, H, lo, hi - lo, N, batch.data(), static_cast<uint32_t>(batch.size()), c->s_run, &launches);
+				cudaError_t e = equirect_launch_units(c->stage_in[0], c->stage_out[0], ch, fmt, W, H, lo, hi - lo, N, batch.data(), static_cast<uint32_t>(batch.size()), c->s_run, &launches, dst_ch, dst_fmt);
 				g_launches.fetch_add(launches, std::memory_order_relaxed);
 				if(e != cudaSuccess) return fail_cuda(e, "equirect kernel launch");
 				CU_TRY(cudaEventRecord(c->ev_run[0], c->s_run));
@@ -1128,46 +1129,74 @@ int cacao_img_equirect_to_cube(int device, const void* src, uint32_t W, uint32_t
 		faces[f] = static_cast<uint8_t*>(dst) + static_cast<uint64_t>(f) * N * N * bpp;
 		if(face_mask & (1u << f)) units[n++] = {f, row_begin, row_end};
 	}
-	return equirect_host_pipeline(c, static_cast<const uint8_t*>(src), W, H, src_row0, src_rows, ch, fmt, faces, N, units, n);
+	return equirect_host_pipeline(c, static_cast<const uint8_t*>(src), W, H, src_row0, src_rows, ch, fmt, faces, N, units, n, ch, fmt);
+}
+
+namespace {
+	int check_equirect_cvt(int ch, int fmt, int dst_ch, int dst_fmt, uint32_t W, uint32_t H, uint32_t N, uint32_t src_row0, uint32_t src_rows, const cacao_cube_unit* units, uint32_t n_units) {
+		if(!ch_ok(ch) || !fmt_ok(fmt)) return fail(CACAO_E_BAD_ARG, "equirect: bad channel count %d or format %d", ch, fmt);
+		if(!ch_ok(dst_ch) || !fmt_ok(dst_fmt)) return fail(CACAO_E_BAD_ARG, "equirect: bad destination channel count %d or format %d", dst_ch, dst_fmt);
+		if(!equirect_cvt_supported(ch, fmt, dst_ch, dst_fmt))
+			return fail(CACAO_E_BAD_ARG, "equirect: fused conversion %d ch fmt %d -> %d ch fmt %d is not defined (float sources only; same channels or RGB -> RGBA): resample, then cacao_img_convert", ch, fmt, dst_ch, dst_fmt);
+		if(W == 0 || H == 0 || N == 0) return fail(CACAO_E_ZERO_DIM, "equirect: zero-sized image or face");
+		if(W > (1u << 24) || H > (1u << 24) || N > (1u << 23)) return fail(CACAO_E_BAD_ARG, "equirect: dimensions beyond exact float range");
+		if(src_rows == 0 || src_row0 + static_cast<uint64_t>(src_rows) > H) return fail(CACAO_E_BAD_ARG, "equirect: source window [%u,+%u) outside the image (H=%u)", src_row0, src_rows, H);
+		for(uint32_t u = 0; u < n_units; ++u)
+			if(units[u].face > 5) return fail(CACAO_E_BAD_ARG, "equirect: unit %u names face %u", u, units[u].face);
+		return CACAO_OK;
+	}
+	static_assert(sizeof(cacao_cube_unit) == sizeof(CubeUnit), "unit layouts must match");
+	// a NULL unit list means the whole cube
+	const CubeUnit* units_or_whole_cube(const cacao_cube_unit* units, uint32_t& n_units, uint32_t N, CubeUnit (&whole)[6]) {
+		if(units) return reinterpret_cast<const CubeUnit*>(units);
+		for(uint32_t f = 0; f < 6; ++f) whole[f] = {f, 0, N};
+		n_units = 6;
+		return whole;
+	}
+}
+
+int cacao_img_equirect_to_cube_units_host_cvt(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* const* faces, uint32_t N, int dst_ch, int dst_fmt, const cacao_cube_unit* units, uint32_t n_units) {
+	if(!src || !faces || (!units && n_units)) return fail(CACAO_E_BAD_ARG, "null pointer");
+	int rc = check_equirect_cvt(ch, fmt, dst_ch, dst_fmt, W, H, N, src_row0, src_rows, units, n_units);
+	if(rc) return rc;
+	if(units && n_units == 0) return CACAO_OK;
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	CubeUnit whole[6];
+	const CubeUnit* list = units_or_whole_cube(units, n_units, N, whole);
+	return equirect_host_pipeline(c, static_cast<const uint8_t*>(src), W, H, src_row0, src_rows, ch, fmt, reinterpret_cast<uint8_t* const*>(faces), N, list, n_units, dst_ch, dst_fmt);
 }
 
 int cacao_img_equirect_to_cube_units_host(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* const* faces, uint32_t N, const cacao_cube_unit* units, uint32_t n_units) {
-	if(!ch_ok(ch) || !fmt_ok(fmt)) return fail(CACAO_E_BAD_ARG, "equirect: bad channel count %d or format %d", ch, fmt);
-	if(W == 0 || H == 0 || N == 0) return fail(CACAO_E_ZERO_DIM, "equirect: zero-sized image or face");
-	if(!src || !faces || (!units && n_units)) return fail(CACAO_E_BAD_ARG, "null pointer");
-	if(W > (1u << 24) || H > (1u << 24) || N > (1u << 23)) return fail(CACAO_E_BAD_ARG, "equirect: dimensions beyond exact float range");
-	if(src_rows == 0 || src_row0 + static_cast<uint64_t>(src_rows) > H) return fail(CACAO_E_BAD_ARG, "equirect: source window [%u,+%u) outside the image (H=%u)", src_row0, src_rows, H);
-	for(uint32_t u = 0; u < n_units; ++u)
-		if(units[u].face > 5) return fail(CACAO_E_BAD_ARG, "equirect: unit %u names face %u", u, units[u].face);
-	if(n_units == 0) return CACAO_OK;
-	DeviceGuard g;
-	DeviceCtx* c = nullptr;
-	int rc = get_ctx(device, &c, g);
-	if(rc) return rc;
-	static_assert(sizeof(cacao_cube_unit) == sizeof(CubeUnit), "unit layouts must match");
-	return equirect_host_pipeline(c, static_cast<const uint8_t*>(src), W, H, src_row0, src_rows, ch, fmt, reinterpret_cast<uint8_t* const*>(faces), N, reinterpret_cast<const CubeUnit*>(units), n_units);
+	// here an empty list means "nothing to do" (the _cvt form reads a NULL list as the whole cube)
+	static const cacao_cube_unit none = {0, 0, 0};
+	return cacao_img_equirect_to_cube_units_host_cvt(device, src, W, H, src_row0, src_rows, ch, fmt, faces, N, ch, fmt, (units || n_units) ? units : &none, n_units);
 }
 
-int cacao_img_equirect_to_cube_units(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, const cacao_cube_unit* units, uint32_t n_units, void* stream) {
-	if(!ch_ok(ch) || !fmt_ok(fmt)) return fail(CACAO_E_BAD_ARG, "equirect: bad channel count %d or format %d", ch, fmt);
-	if(W == 0 || H == 0 || N == 0) return fail(CACAO_E_ZERO_DIM, "equirect: zero-sized image or face");
+int cacao_img_equirect_to_cube_units_cvt(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, int dst_ch, int dst_fmt, const cacao_cube_unit* units, uint32_t n_units, void* stream) {
 	if(!src || !dst || (!units && n_units)) return fail(CACAO_E_BAD_ARG, "null pointer");
-	if(W > (1u << 24) || H > (1u << 24) || N > (1u << 23)) return fail(CACAO_E_BAD_ARG, "equirect: dimensions beyond exact float range");
-	if(src_rows == 0 || src_row0 + static_cast<uint64_t>(src_rows) > H) return fail(CACAO_E_BAD_ARG, "equirect: source window [%u,+%u) outside the image (H=%u)", src_row0, src_rows, H);
+	int rc = check_equirect_cvt(ch, fmt, dst_ch, dst_fmt, W, H, N, src_row0, src_rows, units, n_units);
+	if(rc) return rc;
 	if(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) != 0) return fail(CACAO_E_BAD_ARG, "equirect: device buffers must be 16-byte aligned");
-	for(uint32_t u = 0; u < n_units; ++u)
-		if(units[u].face > 5) return fail(CACAO_E_BAD_ARG, "equirect: unit %u names face %u", u, units[u].face);
-	if(n_units == 0) return CACAO_OK;
+	if(units && n_units == 0) return CACAO_OK;
 	DeviceGuard g;
 	DeviceCtx* c = nullptr;
-	int rc = get_ctx(device, &c, g);
+	rc = get_ctx(device, &c, g);
 	if(rc) return rc;
-	static_assert(sizeof(cacao_cube_unit) == sizeof(CubeUnit), "unit layouts must match");
+	CubeUnit whole[6];
+	const CubeUnit* list = units_or_whole_cube(units, n_units, N, whole);
 	unsigned launches = 0;
-	cudaError_t e = equirect_launch_units(src, dst, ch, fmt, W, H, src_row0, src_rows, N, reinterpret_cast<const CubeUnit*>(units), n_units, static_cast<cudaStream_t>(stream), &launches);
+	cudaError_t e = equirect_launch_units(src, dst, ch, fmt, W, H, src_row0, src_rows, N, list, n_units, static_cast<cudaStream_t>(stream), &launches, dst_ch, dst_fmt);
 	g_launches.fetch_add(launches, std::memory_order_relaxed);
 	if(e != cudaSuccess) return fail_cuda(e, "equirect kernel launch");
 	return CACAO_OK;
+}
+
+int cacao_img_equirect_to_cube_units(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, const cacao_cube_unit* units, uint32_t n_units, void* stream) {
+	static const cacao_cube_unit none = {0, 0, 0};
+	return cacao_img_equirect_to_cube_units_cvt(device, src, W, H, src_row0, src_rows, ch, fmt, dst, N, ch, fmt, (units || n_units) ? units : &none, n_units, stream);
 }
 
 int cacao_img_synth(int device, void* dst_dev, uint64_t first_sample, uint64_t samples, int fmt, int ch, uint32_t seed, void* stream) {

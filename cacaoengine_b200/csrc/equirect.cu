@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "cacao_device.cuh"
+#include "convert_pixel.cuh"
 #include "projection.cuh"
 
 namespace cacao {
@@ -155,7 +156,9 @@ namespace cacao {
 		// between p and q and the (monotone) rounding keeps it there; the filtered value of integer
 		// texels is therefore already inside [0, M] and never NaN.  The clamp is dropped here, not in
 		// the spec (oracle/cacao_oracle.c keeps it), and the GPU tests compare the two bit for bit.
-		template<int F, int CH>
+		// NORM (fused format conversion, Spec B.4): v is a normalised float sample and an integer store
+		// quantises it as Spec B.1 does -- (x != x) ? 0 : uintN(min(max(x,0),1)*M + 0.5f).
+		template<int F, int CH, bool NORM = false>
 		__device__ __forceinline__ void store_texel(uint8_t* __restrict__ p, const float (&v)[CH]) {
 			constexpr int sb = FmtTraits<F>::bytes;
 			constexpr int bpp = sb * CH;
@@ -169,7 +172,12 @@ namespace cacao {
 			} else {
 				uint32_t s[CH];
 #pragma unroll
-				for(int c = 0; c < CH; ++c) s[c] = __float2uint_rz(v[c] + 0.5f);
+				for(int c = 0; c < CH; ++c) {
+					if constexpr(NORM)
+						s[c] = f32_to_unorm<(F == CACAO_FMT_U8) ? 255 : 65535>(v[c]);
+					else
+						s[c] = __float2uint_rz(v[c] + 0.5f);
+				}
 				if constexpr(sb == 2) {
 #pragma unroll
 					for(int c = 0; c < CH; c += 2) w[c >> 1] = (c + 1 < CH) ? __byte_perm(s[c], s[(c + 1 < CH) ? c + 1 : c], 0x5410u) : s[c];
@@ -260,7 +268,10 @@ namespace cacao {
 
 		// Bilinear fetch + store of one output pixel whose source rows are already known.
 		// IDX is uint32_t when the source window has < 2^32 pixels (cheaper address arithmetic).
-		template<int F, int CH, typename IDX>
+		// DF / DC = F / CH: the filtered texel is stored in the source's format (Spec B.2).  Anything
+		// else (float sources only): the fp32 result goes through Spec B.1's float -> DF conversion and,
+		// for RGB -> RGBA, gains alpha 1 on its way out -- resampling and conversion in one pass (Spec B.4).
+		template<int F, int CH, typename IDX, int DF = F, int DC = CH>
 		__device__ __forceinline__ void sample_and_store(const uint8_t* __restrict__ src, uint8_t* __restrict__ out_px, float xs, int W, const RowTaps<IDX>& rt, IDX total_px) {
 			constexpr int bpp = FmtTraits<F>::bytes * CH;
 			const float fx0 = floorf(xs);
@@ -300,7 +311,16 @@ namespace cacao {
 				const float bot = fmaf(fx, d[k] - c[k], c[k] - kOff);
 				out[k] = fmaf(rt.fy, bot - top, top);
 			}
-			store_texel<F, CH>(out_px, out);
+			if constexpr(DF == F && DC == CH) {
+				store_texel<F, CH>(out_px, out);
+			} else {
+				static_assert(!FmtTraits<F>::is_int, "fused format conversion is defined for float sources");
+				static_assert(DC == CH || (CH == 3 && DC == 4), "fused layout change: RGB -> RGBA only");
+				float o[DC];
+#pragma unroll
+				for(int c = 0; c < DC; ++c) o[c] = c < CH ? out[c < CH ? c : 0] : 1.0f;
+				store_texel<DF, DC, FmtTraits<DF>::is_int>(out_px, o);
+			}
 		}
 
 		// One thread = the pixel (i, j) and its mirror images.
@@ -318,9 +338,9 @@ namespace cacao {
 		// one the per-pixel spec computes, bit for bit.
 		// 32 registers (16 blocks/SM) everywhere except the three-channel shapes, whose window realignment
 		// needs 40 (12 blocks/SM measured 7 % ahead of spilling at 32: rgb8 0.165 -> 0.154 ms).
-		template<int F, int CH, typename IDX, bool QUAD, int WX>
+		template<int F, int CH, typename IDX, bool QUAD, int WX, int DF = F, int DC = CH>
 		__global__ void __launch_bounds__(128, CH == 3 ? 12 : 16) equirect_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, EquirectParams prm) {
-			constexpr int bpp = FmtTraits<F>::bytes * CH;
+			constexpr int bpp = FmtTraits<DF>::bytes * DC; // of the output; the taps know the source's
 			constexpr int RY = 32 / WX; // a warp covers WX columns x RY rows, a block WX x 4*RY
 			const CubeUnit unit = prm.units[blockIdx.z];
 			const uint32_t i = blockIdx.x * WX + (threadIdx.x % WX);
@@ -351,8 +371,8 @@ namespace cacao {
 			uint8_t* orow = dst + (static_cast<size_t>(face) * prm.N + j) * prm.N * bpp;
 			const float xs_a = fmaf(atan2_quadrant(rphi, xa, za), prm.pc.kx, prm.pc.cx);
 			const float xs_b = fmaf(atan2_quadrant(rphi, xb, zb), prm.pc.kx, prm.pc.cx);
-			sample_and_store<F, CH, IDX>(src, orow + static_cast<size_t>(i) * bpp, xs_a, W, rt, total_px);
-			if(im != i) sample_and_store<F, CH, IDX>(src, orow + static_cast<size_t>(im) * bpp, xs_b, W, rt, total_px);
+			sample_and_store<F, CH, IDX, DF, DC>(src, orow + static_cast<size_t>(i) * bpp, xs_a, W, rt, total_px);
+			if(im != i) sample_and_store<F, CH, IDX, DF, DC>(src, orow + static_cast<size_t>(im) * bpp, xs_b, W, rt, total_px);
 			if constexpr(QUAD) {
 				const uint32_t jm = prm.N - 1u - j;
 				if(!(unit.face & kUnitMirror) || jm == j) return; // uniform per block: units are indexed by blockIdx.z
@@ -361,8 +381,8 @@ namespace cacao {
 				const RowTaps<IDX> rm = polar ? rt : row_taps<IDX>(fmaf(theta, prm.pc.ky, prm.pc.cy), prm);
 				const float xs_c = polar ? fmaf(atan2_quadrant(rphi, xa, -za), prm.pc.kx, prm.pc.cx) : xs_a;
 				const float xs_d = polar ? fmaf(atan2_quadrant(rphi, xb, -zb), prm.pc.kx, prm.pc.cx) : xs_b;
-				sample_and_store<F, CH, IDX>(src, mrow + static_cast<size_t>(i) * bpp, xs_c, W, rm, total_px);
-				if(im != i) sample_and_store<F, CH, IDX>(src, mrow + static_cast<size_t>(im) * bpp, xs_d, W, rm, total_px);
+				sample_and_store<F, CH, IDX, DF, DC>(src, mrow + static_cast<size_t>(i) * bpp, xs_c, W, rm, total_px);
+				if(im != i) sample_and_store<F, CH, IDX, DF, DC>(src, mrow + static_cast<size_t>(im) * bpp, xs_d, W, rm, total_px);
 			}
 		}
 
@@ -536,15 +556,16 @@ namespace cacao {
 			}
 		}
 
-		template<int F, int CH>
+		template<int F, int CH, int DF = F, int DC = CH>
 		cudaError_t launch(const void* src, void* dst, const EquirectParams& prm, cudaStream_t stream) {
+			constexpr bool fused = DF != F || DC != CH;
 			dim3 block(32, 8, 1); // the staged experiment needs 32 x 8; the gather kernel re-shapes below
 			const uint32_t half = (prm.N + 1u) >> 1;
 			uint32_t max_rows = 0;
 			for(uint32_t u = 0; u < prm.n_units; ++u) max_rows = std::max(max_rows, prm.units[u].row_end - prm.units[u].row_begin);
 			const dim3 grid((half + 31) / 32, (max_rows + 7) / 8, prm.n_units);
 			constexpr int bpp = FmtTraits<F>::bytes * CH;
-			if constexpr(bpp == 4 || bpp == 8 || bpp == 16) {
+			if constexpr(!fused && (bpp == 4 || bpp == 8 || bpp == 16)) {
 				const char* e = getenv("CACAO_EQUIRECT_STAGED");
 				const bool staged = e && e[0] == '1' && (static_cast<uint64_t>(prm.W) * bpp) % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
 				if(staged) {
@@ -570,7 +591,13 @@ namespace cacao {
 			const dim3 ggrid((half + WX - 1) / WX, (rows + bh - 1) / bh, prm.n_units);
 			const uint8_t* s8 = static_cast<const uint8_t*>(src);
 			uint8_t* d8 = static_cast<uint8_t*>(dst);
-			if(small) {
+			if constexpr(fused) {
+				// one instantiation per index width: the four-fold kernel serves unflagged units two-fold
+				if(small)
+					equirect_kernel<F, CH, uint32_t, true, WX, DF, DC><<<ggrid, block, 0, stream>>>(s8, d8, prm);
+				else
+					equirect_kernel<F, CH, uint64_t, true, WX, DF, DC><<<ggrid, block, 0, stream>>>(s8, d8, prm);
+			} else if(small) {
 				if(quad)
 					equirect_kernel<F, CH, uint32_t, true, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
 				else
@@ -582,6 +609,27 @@ namespace cacao {
 					equirect_kernel<F, CH, uint64_t, false, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
 			}
 			return cudaGetLastError();
+		}
+
+		// Fused resample + convert (Spec B.4): float sources, any destination format, same channels or
+		// RGB -> RGBA.
+		template<int F, int CH, int DC>
+		cudaError_t launch_cvt_fmt(const void* src, void* dst, int dst_fmt, const EquirectParams& prm, cudaStream_t stream) {
+			switch(dst_fmt) {
+				case CACAO_FMT_U8: return launch<F, CH, CACAO_FMT_U8, DC>(src, dst, prm, stream);
+				case CACAO_FMT_U16: return launch<F, CH, CACAO_FMT_U16, DC>(src, dst, prm, stream);
+				case CACAO_FMT_F16: return launch<F, CH, CACAO_FMT_F16, DC>(src, dst, prm, stream);
+				case CACAO_FMT_F32: return launch<F, CH, CACAO_FMT_F32, DC>(src, dst, prm, stream);
+			}
+			return cudaErrorInvalidValue;
+		}
+		template<int F>
+		cudaError_t launch_cvt(const void* src, void* dst, int ch, int dst_ch, int dst_fmt, const EquirectParams& prm, cudaStream_t stream) {
+			if(ch == 1 && dst_ch == 1) return launch_cvt_fmt<F, 1, 1>(src, dst, dst_fmt, prm, stream);
+			if(ch == 3 && dst_ch == 3) return launch_cvt_fmt<F, 3, 3>(src, dst, dst_fmt, prm, stream);
+			if(ch == 3 && dst_ch == 4) return launch_cvt_fmt<F, 3, 4>(src, dst, dst_fmt, prm, stream);
+			if(ch == 4 && dst_ch == 4) return launch_cvt_fmt<F, 4, 4>(src, dst, dst_fmt, prm, stream);
+			return cudaErrorInvalidValue;
 		}
 
 		template<int F>
@@ -673,8 +721,18 @@ namespace cacao {
 		return out;
 	}
 
-	cudaError_t equirect_launch_units(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, const CubeUnit* units, uint32_t n_units, cudaStream_t stream, unsigned* launches) {
+	bool equirect_cvt_supported(int ch, int fmt, int dst_ch, int dst_fmt) {
+		if(dst_ch == ch && dst_fmt == fmt) return true;
+		const bool float_src = fmt == CACAO_FMT_F16 || fmt == CACAO_FMT_F32;
+		return float_src && (dst_ch == ch || (ch == 3 && dst_ch == 4));
+	}
+
+	cudaError_t equirect_launch_units(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, const CubeUnit* units, uint32_t n_units, cudaStream_t stream, unsigned* launches, int dst_ch, int dst_fmt) {
 		if(launches) *launches = 0;
+		if(dst_ch <= 0) dst_ch = ch;
+		if(dst_fmt < 0) dst_fmt = fmt;
+		if(!equirect_cvt_supported(ch, fmt, dst_ch, dst_fmt)) return cudaErrorInvalidValue;
+		const bool fused = dst_ch != ch || dst_fmt != fmt;
 		EquirectParams prm;
 		prm.W = W;
 		prm.H = H;
@@ -699,7 +757,7 @@ namespace cacao {
 		// test / A-B switches: two-fold sharing only; the staged experiment knows plain units only
 		const char* qe = getenv("CACAO_EQUIRECT_NO_QUAD");
 		const char* se = getenv("CACAO_EQUIRECT_STAGED");
-		if(!(qe && qe[0] == '1') && !(se && se[0] == '1')) todo = pair_mirror_units(todo, N);
+		if(!(qe && qe[0] == '1') && (fused || !(se && se[0] == '1'))) todo = pair_mirror_units(todo, N);
 		uint32_t hmin = 0xFFFFFFFFu, hmax = 0;
 		for(const CubeUnit& u : todo) {
 			hmin = std::min(hmin, u.row_end - u.row_begin);
@@ -727,12 +785,16 @@ namespace cacao {
 			const uint64_t tallest = todo[next].row_end - todo[next].row_begin;
 			while(next < todo.size() && prm.n_units < kMaxUnitsPerLaunch && 5ull * (todo[next].row_end - todo[next].row_begin) >= 4ull * tallest) prm.units[prm.n_units++] = todo[next++];
 			cudaError_t e;
-			switch(fmt) {
-				case CACAO_FMT_U8: e = launch_ch<CACAO_FMT_U8>(src, dst, ch, prm, stream); break;
-				case CACAO_FMT_U16: e = launch_ch<CACAO_FMT_U16>(src, dst, ch, prm, stream); break;
-				case CACAO_FMT_F16: e = launch_ch<CACAO_FMT_F16>(src, dst, ch, prm, stream); break;
-				case CACAO_FMT_F32: e = launch_ch<CACAO_FMT_F32>(src, dst, ch, prm, stream); break;
-				default: return cudaErrorInvalidValue;
+			if(fused) {
+				e = fmt == CACAO_FMT_F32 ? launch_cvt<CACAO_FMT_F32>(src, dst, ch, dst_ch, dst_fmt, prm, stream) : launch_cvt<CACAO_FMT_F16>(src, dst, ch, dst_ch, dst_fmt, prm, stream);
+			} else {
+				switch(fmt) {
+					case CACAO_FMT_U8: e = launch_ch<CACAO_FMT_U8>(src, dst, ch, prm, stream); break;
+					case CACAO_FMT_U16: e = launch_ch<CACAO_FMT_U16>(src, dst, ch, prm, stream); break;
+					case CACAO_FMT_F16: e = launch_ch<CACAO_FMT_F16>(src, dst, ch, prm, stream); break;
+					case CACAO_FMT_F32: e = launch_ch<CACAO_FMT_F32>(src, dst, ch, prm, stream); break;
+					default: return cudaErrorInvalidValue;
+				}
 			}
 			if(e != cudaSuccess) return e;
 			if(launches) *launches += 1;
@@ -745,7 +807,7 @@ namespace cacao {
 		uint32_t n = 0;
 		for(uint32_t f = 0; f < 6; ++f)
 			if(face_mask & (1u << f)) units[n++] = {f, row_begin, row_end};
-		return equirect_launch_units(src, dst, ch, fmt, W, H, src_row0, src_rows, N, units, n, stream, nullptr);
+		return equirect_launch_units(src, dst, ch, fmt, W, H, src_row0, src_rows, N, units, n, stream, nullptr, ch, fmt);
 	}
 
 	// Host-side planning with the same arithmetic as the kernel, in O(1) evaluations per face.

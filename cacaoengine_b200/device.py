@@ -110,6 +110,26 @@ def equirect_to_cube_units_host(src: int, W: int, H: int, ch: int, fmt: int, fac
 	capi.check(capi.lib().cacao_img_equirect_to_cube_units_host(device, src, W, H, src_row0, H if src_rows is None else src_rows, ch, fmt, ptrs, N, flat.ctypes.data, len(flat)))
 
 
+def _flat_units(units):
+	if units is None:
+		return None, 0
+	flat = np.array([(u.face, u.row_begin, u.row_end) if hasattr(u, "face") else tuple(u) for u in units], np.uint32).reshape(-1, 3)
+	return flat, len(flat)
+
+
+def equirect_to_cube_cvt(src: int, W: int, H: int, ch: int, fmt: int, dst: int, N: int, dst_ch: int, dst_fmt: int, units=None, src_row0: int = 0, src_rows: int | None = None, device: int = -1, stream=None) -> None:
+	"""Resampling + format / layout conversion in one pass (Spec B.4; float sources).  units=None: whole cube."""
+	flat, n = _flat_units(units)
+	capi.check(capi.lib().cacao_img_equirect_to_cube_units_cvt(device, src, W, H, src_row0, H if src_rows is None else src_rows, ch, fmt, dst, N, dst_ch, dst_fmt, flat.ctypes.data if flat is not None else None, n, stream))
+
+
+def equirect_to_cube_cvt_host(src: int, W: int, H: int, ch: int, fmt: int, faces, N: int, dst_ch: int, dst_fmt: int, units=None, src_row0: int = 0, src_rows: int | None = None, device: int = -1) -> None:
+	"""Host-memory form: faces = six host addresses of N x N x dst_ch faces in dst_fmt."""
+	flat, n = _flat_units(units)
+	ptrs = (C.c_void_p * 6)(*[int(f) if f else None for f in faces])
+	capi.check(capi.lib().cacao_img_equirect_to_cube_units_host_cvt(device, src, W, H, src_row0, H if src_rows is None else src_rows, ch, fmt, ptrs, N, dst_ch, dst_fmt, flat.ctypes.data if flat is not None else None, n))
+
+
 def equirect_src_window(W: int, H: int, N: int, face_mask: int, row_begin: int, row_end: int) -> tuple[int, int]:
 	r0, n = C.c_uint32(), C.c_uint32()
 	capi.check(capi.lib().cacao_img_equirect_src_window(W, H, N, face_mask, row_begin, row_end, C.byref(r0), C.byref(n)))

@@ -189,6 +189,23 @@ int cacao_img_equirect_to_cube_units_host(int device, const void* src, uint32_t 
 											 uint32_t src_rows, int ch, int fmt, void* const* faces, uint32_t N,
 											 const cacao_cube_unit* units, uint32_t n_units);
 
+/* Resampling AND sample-format / layout conversion in one pass (DESIGN.md "Spec B.4"): the filtered
+ * fp32 texel is converted to dst_fmt exactly as cacao_img_convert converts an F32 sample (Spec B.1) and
+ * an RGB source may gain an opaque alpha (dst_ch = 4) on its way out -- e.g. an RGB32F .hdr panorama
+ * straight to an RGBA16F cube, without the F32 cube ever touching memory.  Defined for FLOAT sources
+ * (F16, F32), dst_ch == ch or 3 -> 4; dst_ch == ch && dst_fmt == fmt is the plain resampling of any
+ * format; everything else returns CACAO_E_BAD_ARG (resample, then convert).  dst holds 6 faces of
+ * N x N x dst_ch samples of dst_fmt.  units == NULL && n_units == 0: the whole cube. */
+int cacao_img_equirect_to_cube_units_cvt(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0,
+										 uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, int dst_ch,
+										 int dst_fmt, const cacao_cube_unit* units, uint32_t n_units, void* stream);
+/* Host-memory form (faces[f] = host base of face f in the DESTINATION format), pipelined like
+ * cacao_img_equirect_to_cube_units_host. */
+int cacao_img_equirect_to_cube_units_host_cvt(int device, const void* src, uint32_t W, uint32_t H,
+											  uint32_t src_row0, uint32_t src_rows, int ch, int fmt,
+											  void* const* faces, uint32_t N, int dst_ch, int dst_fmt,
+											  const cacao_cube_unit* units, uint32_t n_units);
+
 /* Host-side planning: the inclusive-exclusive window of source rows that the work unit
  * (face_mask, [row_begin,row_end)) reads, so a shard can upload just that band. */
 int cacao_img_equirect_src_window(uint32_t W, uint32_t H, uint32_t N, uint32_t face_mask, uint32_t row_begin,

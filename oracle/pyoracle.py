@@ -190,6 +190,20 @@ def equirect_to_cube(src: np.ndarray, W: int, H: int, ch: int, fmt: int, N: int,
 	return out
 
 
+def equirect_to_cube_cvt(src: np.ndarray, W: int, H: int, ch: int, fmt: int, N: int, dst_ch: int, dst_fmt: int,
+						 threads: int = 0) -> np.ndarray:
+	"""Spec B.4 (resample + convert in one pass) stated as the composition it is defined to equal: the
+	float source widened to fp32 (exact), Spec B.2 in fp32, then Spec B.1 from F32 to the destination
+	format / layout.  Whole cube; nothing here is new arithmetic."""
+	assert fmt in (F16, F32), "B.4 is defined for float sources"
+	s = np.ascontiguousarray(src).reshape(-1)
+	wide = s if fmt == F32 else convert(s, ch, ch, F16, F32, threads=threads)
+	cube = equirect_to_cube(wide, W, H, ch, F32, N, threads=threads)
+	if dst_ch == ch and dst_fmt == F32:
+		return cube
+	return convert(cube, ch, dst_ch, F32, dst_fmt, threads=threads)
+
+
 def equirect_to_cube_f64(src: np.ndarray, W: int, H: int, ch: int, fmt: int, N: int, face_mask: int = 0x3F) -> np.ndarray:
 	s = np.ascontiguousarray(src).reshape(-1)
 	out = np.zeros(6 * N * N * ch, np.float64)

@@ -232,6 +232,74 @@ def test_mirror_folded_unit_lists_match_the_oracle(oracle, fmt, ch, N):
 	a.free(), b.free()
 
 
+FUSED = [(sf, ch, dc, df) for sf in (2, 3) for (ch, dc) in ((1, 1), (3, 3), (3, 4), (4, 4)) for df in (0, 1, 2, 3) if not (dc == ch and df == sf)]
+
+
+def _float_pano(rng, W, H, ch, fmt, dst_fmt):
+	"""Finite float samples: around [0, 1] with excursions on both sides for the quantising
+	destinations, a wide dynamic range (f16 overflow included for F32 -> F16) for the float ones."""
+	if dst_fmt in (0, 1):
+		v = rng.uniform(-0.25, 1.25, W * H * ch)
+	else:
+		v = np.exp2(rng.uniform(-12, 17 if fmt == 3 else 14, W * H * ch)) * rng.choice([-1.0, 1.0], W * H * ch)
+	return v.astype(NP[fmt])
+
+
+@pytest.mark.parametrize("sf,ch,dc,df", FUSED, ids=[f"{NAME[sf]}x{ch}-{NAME[df]}x{dc}" for sf, ch, dc, df in FUSED])
+def test_fused_resample_and_convert_matches_the_composition(oracle, sf, ch, dc, df):
+	"""Spec B.4: cacao_img_equirect_to_cube_units_cvt == widen (exact) -> Spec B.2 in fp32 -> Spec B.1 to the
+	destination, bit for bit, for every float source and every destination format / RGB -> RGBA."""
+	from cacaoengine_b200 import device
+
+	W, H, N = 93, 47, 29
+	rng = np.random.default_rng(100 * sf + 10 * ch + df)
+	src = _float_pano(rng, W, H, ch, sf, df)
+	want = oracle.equirect_to_cube_cvt(src, W, H, ch, sf, N, dc, df)
+	a, b = DevBuf(src.nbytes), DevBuf(want.nbytes)
+	device.upload(a.ptr, src)
+	device.upload(b.ptr, np.zeros_like(want))
+	device.equirect_to_cube_cvt(a.ptr, W, H, ch, sf, b.ptr, N, dc, df)
+	got = np.empty_like(want)
+	device.download(got, b.ptr)
+	assert same_bits(got, want)
+	# a unit list (mirror pair + a lone band): only those rows are written, with the same values
+	units = [(2, 3, 9), (2, N - 9, N - 3), (5, 11, 20)]
+	device.upload(b.ptr, np.zeros_like(want))
+	device.equirect_to_cube_cvt(a.ptr, W, H, ch, sf, b.ptr, N, dc, df, units=units)
+	device.download(got, b.ptr)
+	part = np.zeros_like(want)
+	for f, r0, r1 in units:
+		sl = slice((f * N + r0) * N * dc, (f * N + r1) * N * dc)
+		part[sl] = want[sl]
+	assert same_bits(got, part)
+	a.free(), b.free()
+
+
+def test_fused_resample_host_path_and_full_size_property(oracle):
+	"""Host-memory form with six separate face buffers (RGB32F panorama -> RGBA16F faces), and at
+	BASELINE config 3's size: the fused RGBA32F -> RGBA16F cube equals resample-then-convert on the
+	device (checksum), which the parity tests pin to the oracle."""
+	from cacaoengine_b200 import _capi as c, device
+
+	W, H, N, ch = 160, 80, 40, 3
+	rng = np.random.default_rng(5)
+	src = _float_pano(rng, W, H, ch, 3, 2)
+	want = oracle.equirect_to_cube_cvt(src, W, H, ch, 3, N, 4, 2).reshape(6, -1)
+	faces = [np.zeros(N * N * 4, np.float16) for _ in range(6)]
+	device.equirect_to_cube_cvt_host(src.ctypes.data, W, H, ch, 3, [f.ctypes.data for f in faces], N, 4, 2)
+	for f in range(6):
+		assert same_bits(faces[f], want[f]), f
+	W, H, N = 8192, 4096, 2048
+	a, cube32, cube16, fused = DevBuf(W * H * 16), DevBuf(6 * N * N * 16), DevBuf(6 * N * N * 8), DevBuf(6 * N * N * 8)
+	device.synth(a.ptr, W * H * 4, c.FMT_F32, 4, 0xC0FFEE + 3)
+	device.equirect_to_cube(a.ptr, W, H, 4, c.FMT_F32, cube32.ptr, N)
+	device.convert(cube32.ptr, cube16.ptr, 6 * N * N, 4, 4, c.FMT_F32, c.FMT_F16)
+	device.equirect_to_cube_cvt(a.ptr, W, H, 4, c.FMT_F32, fused.ptr, N, 4, c.FMT_F16)
+	assert device.checksum(fused.ptr, 6 * N * N * 8) == device.checksum(cube16.ptr, 6 * N * N * 8)
+	for buf in (a, cube32, cube16, fused):
+		buf.free()
+
+
 @pytest.mark.parametrize("fmt,ch", [(3, 4), (2, 4), (0, 4), (3, 1), (1, 4)], ids=["f32x4", "f16x4", "u8x4", "f32x1", "u16x4"])
 def test_tma_staged_variant_is_bit_identical(oracle, monkeypatch, fmt, ch):
 	"""The experimental TMA-staged kernel (CACAO_EQUIRECT_STAGED=1; cp.async.bulk row segments into
