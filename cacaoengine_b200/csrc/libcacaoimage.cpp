@@ -208,17 +208,33 @@ namespace libcacaoimage {
 		return out;
 	}
 
+	bool FusedProjectionDefined(Image::Layout srcLayout, SampleFormat srcFormat, Image::Layout layout, SampleFormat format) {
+		if(srcLayout == layout && srcFormat == format) return true;
+		const bool float_src = srcFormat == SampleFormat::F16 || srcFormat == SampleFormat::F32;
+		return float_src && (layout == srcLayout || (srcLayout == Image::Layout::RGB && layout == Image::Layout::RGBA));
+	}
+
 	std::array<ImageEx, 6> EquirectToCubemap(const ImageEx& src, unsigned int faceSize, const std::vector<int>& devices) {
+		return EquirectToCubemap(src, faceSize, src.layout, src.format, devices);
+	}
+
+	std::array<ImageEx, 6> EquirectToCubemap(const ImageEx& src, unsigned int faceSize, Image::Layout layout, SampleFormat format, const std::vector<int>& devices) {
+		if(!FusedProjectionDefined(src.layout, src.format, layout, format)) {
+			// no one-pass form (integer source, or a layout change other than RGB -> RGBA): two passes
+			std::array<ImageEx, 6> faces = EquirectToCubemap(src, faceSize, src.layout, src.format, devices);
+			for(auto& f : faces) f = Convert(f, layout, format);
+			return faces;
+		}
 		if(src.w == 0 || src.h == 0 || faceSize == 0) check(CACAO_E_ZERO_DIM);
 		const std::size_t bpp = BytesPerPixel(src.layout, src.format);
 		if(src.data.size() < static_cast<std::size_t>(src.w) * src.h * bpp) throw std::runtime_error("equirect source buffer is smaller than w*h*bytes-per-pixel");
-		const std::size_t face_bytes = static_cast<std::size_t>(faceSize) * faceSize * bpp;
+		const std::size_t face_bytes = static_cast<std::size_t>(faceSize) * faceSize * BytesPerPixel(layout, format);
 		// the six results are allocated up front and every device reads its rows back straight into them
 		std::array<ImageEx, 6> faces;
 		for(unsigned f = 0; f < 6; ++f) {
 			faces[f].w = faces[f].h = faceSize;
-			faces[f].layout = src.layout;
-			faces[f].format = src.format;
+			faces[f].layout = layout;
+			faces[f].format = format;
 			faces[f].data.resize(face_bytes);
 		}
 
@@ -282,7 +298,7 @@ namespace libcacaoimage {
 			const std::size_t pitch = static_cast<std::size_t>(src.w) * bpp;
 			void* dst[6];
 			for(unsigned f = 0; f < 6; ++f) dst[f] = faces[f].data.data();
-			if(cacao_img_equirect_to_cube_units_host(devs[k], src.data.data() + static_cast<std::size_t>(lo) * pitch, src.w, src.h, lo, hi - lo, static_cast<int>(src.layout), static_cast<int>(src.format), dst, faceSize, units.data() + u0, static_cast<uint32_t>(u1 - u0)) != CACAO_OK)
+			if(cacao_img_equirect_to_cube_units_host_cvt(devs[k], src.data.data() + static_cast<std::size_t>(lo) * pitch, src.w, src.h, lo, hi - lo, static_cast<int>(src.layout), static_cast<int>(src.format), dst, faceSize, static_cast<int>(layout), static_cast<int>(format), units.data() + u0, static_cast<uint32_t>(u1 - u0)) != CACAO_OK)
 				errors[k] = cacao_img_last_error();
 		};
 		if(devs.size() == 1) {
@@ -414,18 +430,27 @@ namespace libcacaoimage {
 	}
 
 	std::array<DeviceImage, 6> DeviceImage::EquirectToCubemap(unsigned int faceSize) const {
+		return EquirectToCubemap(faceSize, layout_, format_);
+	}
+
+	std::array<DeviceImage, 6> DeviceImage::EquirectToCubemap(unsigned int faceSize, Image::Layout layout, SampleFormat format) const {
 		if(Empty()) check(CACAO_E_EMPTY);
 		if(faceSize == 0) check(CACAO_E_ZERO_DIM);
-		const std::size_t face_bytes = static_cast<std::size_t>(faceSize) * faceSize * BytesPerPixel(layout_, format_);
+		if(!FusedProjectionDefined(layout_, format_, layout, format)) {
+			std::array<DeviceImage, 6> faces = EquirectToCubemap(faceSize, layout_, format_);
+			for(auto& f : faces) f = f.Convert(layout, format);
+			return faces;
+		}
+		const std::size_t face_bytes = static_cast<std::size_t>(faceSize) * faceSize * BytesPerPixel(layout, format);
 		std::shared_ptr<void> cube = device_alloc(device_, 6 * face_bytes);
-		check(cacao_img_equirect_to_cube(device_, ptr_, w_, h_, 0, h_, static_cast<int>(layout_), static_cast<int>(format_), cube.get(), faceSize, 0x3Fu, 0, faceSize, CACAO_MEM_DEVICE, nullptr));
+		check(cacao_img_equirect_to_cube_units_cvt(device_, ptr_, w_, h_, 0, h_, static_cast<int>(layout_), static_cast<int>(format_), cube.get(), faceSize, static_cast<int>(layout), static_cast<int>(format), nullptr, 0, nullptr));
 		std::array<DeviceImage, 6> faces;
 		for(unsigned f = 0; f < 6; ++f) {
 			faces[f].owner_ = cube;
 			faces[f].ptr_ = static_cast<unsigned char*>(cube.get()) + f * face_bytes;
 			faces[f].w_ = faces[f].h_ = faceSize;
-			faces[f].layout_ = layout_;
-			faces[f].format_ = format_;
+			faces[f].layout_ = layout;
+			faces[f].format_ = format;
 			faces[f].device_ = device_;
 		}
 		return faces;

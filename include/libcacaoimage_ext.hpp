@@ -47,6 +47,13 @@ namespace libcacaoimage {
 	// (right,left,up,down,front,back), same layout and sample format as the source.
 	// devices: CUDA ordinals to spread face/row-band work units over (empty = current device).
 	std::array<ImageEx, 6> EquirectToCubemap(const ImageEx& src, unsigned int faceSize, const std::vector<int>& devices = {});
+	// The same with the faces delivered in another layout / sample format.  Float panoramas (F16, F32)
+	// going to any sample format, with the same channels or RGB -> RGBA, are resampled AND converted in
+	// one pass over the pixels (DESIGN.md "Spec B.4": the fp32 filter result is converted as Convert()
+	// converts an F32 sample) -- an RGB32F .hdr panorama becomes an RGBA16F cube without the F32 cube ever
+	// existing.  FusedProjectionDefined() tells; every other pair runs the two passes for you.
+	std::array<ImageEx, 6> EquirectToCubemap(const ImageEx& src, unsigned int faceSize, Image::Layout layout, SampleFormat format, const std::vector<int>& devices = {});
+	bool FusedProjectionDefined(Image::Layout srcLayout, SampleFormat srcFormat, Image::Layout layout, SampleFormat format);
 
 	// Flip for any sample format.
 	ImageEx Flip(const ImageEx& src);
@@ -90,6 +97,8 @@ namespace libcacaoimage {
 		// six faces that are views of ONE contiguous face-major allocation (+X,-X,+Y,-Y,+Z,-Z) -- the
 		// layout the Vulkan backend concatenates by hand (engine/src/vulkan/impls/VulkanCubemap.cpp:30-41)
 		std::array<DeviceImage, 6> EquirectToCubemap(unsigned int faceSize) const;
+		// faces in another layout / format: one fused pass where Spec B.4 defines it, else project + Convert
+		std::array<DeviceImage, 6> EquirectToCubemap(unsigned int faceSize, Image::Layout layout, SampleFormat format) const;
 
 		unsigned int Width() const { return w_; }
 		unsigned int Height() const { return h_; }

@@ -195,6 +195,40 @@ int main(int argc, char** argv) {
 		DeviceImage copy = dfaces[3]; // shares the allocation; the cube outlives the array it came from
 		EXPECT(copy.Data() == dfaces[3].Data() && copy.Download().data == one[3].data);
 	}
+	// ---- resampling and conversion in one pass (Spec B.4): an RGB32F panorama straight to RGBA16F faces
+	// equals project-then-Convert; pairs without a fused form (integer sources) run the two passes inside
+	{
+		ImageEx hdr;
+		hdr.w = 160;
+		hdr.h = 80;
+		hdr.layout = L::RGB;
+		hdr.format = SampleFormat::F32;
+		hdr.data.resize(160 * 80 * 12);
+		float* px = reinterpret_cast<float*>(hdr.data.data());
+		for(std::size_t k = 0; k < 160 * 80 * 3; ++k) px[k] = static_cast<float>((k * 2654435761u) >> 8 & 0xFFFF) / 32768.0f - 0.25f;
+		EXPECT(FusedProjectionDefined(L::RGB, SampleFormat::F32, L::RGBA, SampleFormat::F16));
+		EXPECT(!FusedProjectionDefined(L::RGBA, SampleFormat::U16, L::RGBA, SampleFormat::F16) && !FusedProjectionDefined(L::RGBA, SampleFormat::F32, L::RGB, SampleFormat::F32));
+		const auto plain = EquirectToCubemap(hdr, 24);
+		const auto fused = EquirectToCubemap(hdr, 24, L::RGBA, SampleFormat::F16);
+		const auto quant = EquirectToCubemap(hdr, 24, L::RGB, SampleFormat::U8);
+		const auto dfused = DeviceImage::Upload(hdr).EquirectToCubemap(24, L::RGBA, SampleFormat::F16);
+		for(int f = 0; f < 6; ++f) {
+			EXPECT(fused[f].layout == L::RGBA && fused[f].format == SampleFormat::F16 && fused[f].data.size() == 24 * 24 * 8);
+			EXPECT(fused[f].data == Convert(plain[f], L::RGBA, SampleFormat::F16).data);
+			EXPECT(quant[f].data == Convert(plain[f], L::RGB, SampleFormat::U8).data);
+			EXPECT(dfused[f].Download().data == fused[f].data && dfused[f].Format() == SampleFormat::F16);
+		}
+		ImageEx deep;
+		deep.w = 64;
+		deep.h = 32;
+		deep.layout = L::RGBA;
+		deep.format = SampleFormat::U16;
+		deep.data.resize(64 * 32 * 8);
+		for(std::size_t b = 0; b < deep.data.size(); ++b) deep.data[b] = static_cast<unsigned char>((b * 40503u) >> 7);
+		const auto two = EquirectToCubemap(deep, 12, L::RGB, SampleFormat::U8); // falls back to two passes
+		const auto ref = EquirectToCubemap(deep, 12);
+		for(int f = 0; f < 6; ++f) EXPECT(two[f].data == Convert(ref[f], L::RGB, SampleFormat::U8).data);
+	}
 	std::printf(failures ? "%d FAILURES\n" : "cpp api ok\n", failures);
 	return failures ? 1 : 0;
 }

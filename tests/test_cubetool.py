@@ -107,6 +107,13 @@ def test_project_float_npy_16bit_png_and_options(tool, tmp_path, oracle):
 	want = oracle.equirect_to_cube(pano.reshape(-1), W, H, 4, oracle.F32, N).reshape(6, N, N, 4)
 	got = np.load(tmp_path / "o1" / "hdr_front.npy")
 	assert got.dtype == np.float32 and (got.view(np.uint32) == want[4].view(np.uint32)).all()
+	# float panorama to half-float RGBA faces: one fused pass inside (Spec B.4), same answer as two
+	np.save(tmp_path / "rgb.npy", pano[:, :, :3].copy())
+	r = run(tool, "project", str(tmp_path / "rgb.npy"), "-o", str(tmp_path / "o3"), "-s", str(N), "--layout", "rgba", "--depth", "f16", "--format", "npy")
+	assert r.returncode == 0, r.stderr
+	want16 = oracle.equirect_to_cube_cvt(pano[:, :, :3].reshape(-1), W, H, 3, oracle.F32, N, 4, oracle.F16).reshape(6, N, N, 4)
+	got16 = np.load(tmp_path / "o3" / "rgb_down.npy")
+	assert got16.dtype == np.float16 and (got16.view(np.uint16) == want16[3].view(np.uint16)).all()
 	# 16-bit PNG in, single face out, converted to 8-bit RGB and flipped
 	p16 = oracle.synth(W * H * 4, oracle.U16, 4, 33).reshape(H, W, 4)
 	cv2.imwrite(str(tmp_path / "deep.png"), p16[:, :, [2, 1, 0, 3]])

@@ -53,10 +53,10 @@ int RunProject(const ProjectOptions& opt) {
 	auto run = [&]() {
 		if(opt.gpus == 1 && post) {
 			const DeviceImage dpano = DeviceImage::Upload(pano);
-			const std::array<DeviceImage, 6> dfaces = dpano.EquirectToCubemap(N);
+			//Float panoramas are resampled and converted in one pass where that is defined (Spec B.4)
+			const std::array<DeviceImage, 6> dfaces = dpano.EquirectToCubemap(N, layout, fmt);
 			for(int i = 0; i < 6; ++i) {
 				DeviceImage f = dfaces[i];
-				if(layout != f.Layout() || fmt != f.Format()) f = f.Convert(layout, fmt);
 				if(opt.flip) f = f.Flip();
 				faces[i] = f.Download();
 			}
@@ -65,9 +65,8 @@ int RunProject(const ProjectOptions& opt) {
 		std::vector<int> devices;
 		for(int d = 0; d < opt.gpus; ++d) devices.push_back(d);
 		if(devices.size() == 1) devices.clear(); // current device
-		faces = EquirectToCubemap(pano, N, devices);
+		faces = EquirectToCubemap(pano, N, layout, fmt, devices);
 		for(auto& f : faces) {
-			if(layout != f.layout || fmt != f.format) f = Convert(f, layout, fmt);
 			if(opt.flip) f = Flip(f);
 		}
 	};
