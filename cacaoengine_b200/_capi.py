@@ -47,8 +47,8 @@ SIGNATURES = {
 	"cacao_img_equirect_to_cube": (_i, [_i, _vp, _u32, _u32, _u32, _u32, _i, _i, _vp, _u32, _u32, _u32, _u32, _i, _vp]),
 	"cacao_img_equirect_to_cube_units": (_i, [_i, _vp, _u32, _u32, _u32, _u32, _i, _i, _vp, _u32, _vp, _u32, _vp]),
 	"cacao_img_equirect_to_cube_units_host": (_i, [_i, _vp, _u32, _u32, _u32, _u32, _i, _i, C.POINTER(_vp), _u32, _vp, _u32]),
-	"cacao_img_equirect_to_cube_units_cvt": (_i, [_i, _vp, _u32, _u32, _u32, _u32, _i, _i, _vp, _u32, _i, _i, _vp, _u32, _vp]),
-	"cacao_img_equirect_to_cube_units_host_cvt": (_i, [_i, _vp, _u32, _u32, _u32, _u32, _i, _i, C.POINTER(_vp), _u32, _i, _i, _vp, _u32]),
+	"cacao_img_equirect_to_cube_units_cvt": (_i, [_i, _vp, _u32, _u32, _u32, _u32, _i, _i, _vp, _u32, _i, _i, _u32, _vp, _u32, _vp]),
+	"cacao_img_equirect_to_cube_units_host_cvt": (_i, [_i, _vp, _u32, _u32, _u32, _u32, _i, _i, C.POINTER(_vp), _u32, _i, _i, _u32, _vp, _u32]),
 	"cacao_img_equirect_src_window": (_i, [_u32, _u32, _u32, _u32, _u32, _u32, C.POINTER(_u32), C.POINTER(_u32)]),
 	"cacao_img_equirect_fold_units": (_i, [_u32, _vp, _u32, _vp, _u32, C.POINTER(_u32)]),
 	"cacao_img_synth": (_i, [_i, _vp, _u64, _u64, _i, _i, _u32, _vp]),

@@ -652,7 +652,7 @@ namespace {
 	// directions at once and the call costs about max(upload, readback) instead of their sum.
 	// Pinned buffers only; pageable ones and small jobs take the sequential form below.
 	// faces[f] = host base of face f (N x N pixels), only needed for faces that units name.
-	int equirect_host_pipeline(DeviceCtx* c, const uint8_t* hsrc, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, uint8_t* const* faces, uint32_t N, const CubeUnit* units_in, uint32_t n_units_in, int dst_ch, int dst_fmt) {
+	int equirect_host_pipeline(DeviceCtx* c, const uint8_t* hsrc, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, uint8_t* const* faces, uint32_t N, const CubeUnit* units_in, uint32_t n_units_in, int dst_ch, int dst_fmt, uint32_t flags) {
 		const uint64_t bpp = static_cast<uint64_t>(ch) * fmt_bytes(fmt);             // source texel
 		const uint64_t dbpp = static_cast<uint64_t>(dst_ch) * fmt_bytes(dst_fmt);    // face texel (fused conversion: may differ)
 		const uint64_t pitch = static_cast<uint64_t>(W) * bpp;
@@ -663,6 +663,9 @@ namespace {
 		};
 		std::vector<Piece> pieces;
 		const uint64_t row_bytes = static_cast<uint64_t>(N) * dbpp;
+		// where rows [r0, r1) of a face are stored: mirrored when the faces come out bottom row first
+		const bool flip = (flags & CACAO_EQUIRECT_FLIP_ROWS) != 0;
+		auto stored_at = [&](const CubeUnit& u) { return static_cast<uint64_t>(flip ? N - u.row_end : u.row_begin) * row_bytes; };
 		const uint32_t band_rows = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(N, (16ull << 20) / row_bytes)));
 		uint32_t lo = UINT32_MAX, hi = 0;
 		for(uint32_t k = 0; k < n_units_in; ++k) {
@@ -710,7 +713,7 @@ namespace {
 			rc = upload_any(c, c->stage_in[0], up_base, static_cast<uint64_t>(hi - lo) * pitch, c->s_run);
 			if(rc) return rc;
 			unsigned launches = 0;
-			cudaError_t e = equirect_launch_units(c->stage_in[0], c->stage_out[0], ch, fmt, W, H, lo, hi - lo, N, units_in, n_units_in, c->s_run, &launches, dst_ch, dst_fmt);
+			cudaError_t e = equirect_launch_units(c->stage_in[0], c->stage_out[0], ch, fmt, W, H, lo, hi - lo, N, units_in, n_units_in, c->s_run, &launches, dst_ch, dst_fmt, flags);
 			g_launches.fetch_add(launches, std::memory_order_relaxed);
 			if(e != cudaSuccess) return fail_cuda(e, "equirect kernel launch");
 			std::vector<Segment> segs;
@@ -718,14 +721,14 @@ namespace {
 				CubeUnit u = units_in[k];
 				if(u.row_end > N) u.row_end = N;
 				if(u.face > 5 || u.row_begin >= u.row_end) continue;
-				const uint64_t off = static_cast<uint64_t>(u.row_begin) * row_bytes;
+				const uint64_t off = stored_at(u);
 				segs.push_back({faces[u.face] + off, c->stage_out[0] + u.face * face_bytes + off, static_cast<size_t>(u.row_end - u.row_begin) * row_bytes});
 			}
 			return download_segments(c, segs, c->s_run);
 		}
 		const uint64_t rows_per_chunk = std::max<uint64_t>(1, kXferChunk / pitch);
 		auto read_back = [&](const Piece& p) -> int {
-			const uint64_t off = static_cast<uint64_t>(p.u.row_begin) * row_bytes, n = static_cast<uint64_t>(p.u.row_end - p.u.row_begin) * row_bytes;
+			const uint64_t off = stored_at(p.u), n = static_cast<uint64_t>(p.u.row_end - p.u.row_begin) * row_bytes;
 			CU_TRY(cudaMemcpyAsync(faces[p.u.face] + off, c->stage_out[0] + p.u.face * face_bytes + off, n, cudaMemcpyDeviceToHost, c->s_out));
 			return CACAO_OK;
 		};
@@ -748,7 +751,7 @@ namespace {
 				std::vector<CubeUnit> batch;
 				for(size_t q = next; q < ready_end; ++q) batch.push_back(pieces[q].u);
 				unsigned launches = 0;
-				cudaError_t e = equirect_launch_units(c->stage_in[0], c->stage_out[0], ch, fmt, W, H, lo, hi - lo, N, batch.data(), static_cast<uint32_t>(batch.size()), c->s_run, &launches, dst_ch, dst_fmt);
+				cudaError_t e = equirect_launch_units(c->stage_in[0], c->stage_out[0], ch, fmt, W, H, lo, hi - lo, N, batch.data(), static_cast<uint32_t>(batch.size()), c->s_run, &launches, dst_ch, dst_fmt, flags);
 				g_launches.fetch_add(launches, std::memory_order_relaxed);
 				if(e != cudaSuccess) return fail_cuda(e, "equirect kernel launch");
 				CU_TRY(cudaEventRecord(c->ev_run[0], c->s_run));
@@ -1129,7 +1132,7 @@ int cacao_img_equirect_to_cube(int device, const void* src, uint32_t W, uint32_t
 		faces[f] = static_cast<uint8_t*>(dst) + static_cast<uint64_t>(f) * N * N * bpp;
 		if(face_mask & (1u << f)) units[n++] = {f, row_begin, row_end};
 	}
-	return equirect_host_pipeline(c, static_cast<const uint8_t*>(src), W, H, src_row0, src_rows, ch, fmt, faces, N, units, n, ch, fmt);
+	return equirect_host_pipeline(c, static_cast<const uint8_t*>(src), W, H, src_row0, src_rows, ch, fmt, faces, N, units, n, ch, fmt, 0);
 }
 
 namespace {
@@ -1155,8 +1158,9 @@ namespace {
 	}
 }
 
-int cacao_img_equirect_to_cube_units_host_cvt(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* const* faces, uint32_t N, int dst_ch, int dst_fmt, const cacao_cube_unit* units, uint32_t n_units) {
+int cacao_img_equirect_to_cube_units_host_cvt(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* const* faces, uint32_t N, int dst_ch, int dst_fmt, uint32_t flags, const cacao_cube_unit* units, uint32_t n_units) {
 	if(!src || !faces || (!units && n_units)) return fail(CACAO_E_BAD_ARG, "null pointer");
+	if(flags & ~CACAO_EQUIRECT_FLIP_ROWS) return fail(CACAO_E_BAD_ARG, "equirect: unknown flags 0x%x", flags);
 	int rc = check_equirect_cvt(ch, fmt, dst_ch, dst_fmt, W, H, N, src_row0, src_rows, units, n_units);
 	if(rc) return rc;
 	if(units && n_units == 0) return CACAO_OK;
@@ -1166,17 +1170,18 @@ int cacao_img_equirect_to_cube_units_host_cvt(int device, const void* src, uint3
 	if(rc) return rc;
 	CubeUnit whole[6];
 	const CubeUnit* list = units_or_whole_cube(units, n_units, N, whole);
-	return equirect_host_pipeline(c, static_cast<const uint8_t*>(src), W, H, src_row0, src_rows, ch, fmt, reinterpret_cast<uint8_t* const*>(faces), N, list, n_units, dst_ch, dst_fmt);
+	return equirect_host_pipeline(c, static_cast<const uint8_t*>(src), W, H, src_row0, src_rows, ch, fmt, reinterpret_cast<uint8_t* const*>(faces), N, list, n_units, dst_ch, dst_fmt, flags);
 }
 
 int cacao_img_equirect_to_cube_units_host(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* const* faces, uint32_t N, const cacao_cube_unit* units, uint32_t n_units) {
 	// here an empty list means "nothing to do" (the _cvt form reads a NULL list as the whole cube)
 	static const cacao_cube_unit none = {0, 0, 0};
-	return cacao_img_equirect_to_cube_units_host_cvt(device, src, W, H, src_row0, src_rows, ch, fmt, faces, N, ch, fmt, (units || n_units) ? units : &none, n_units);
+	return cacao_img_equirect_to_cube_units_host_cvt(device, src, W, H, src_row0, src_rows, ch, fmt, faces, N, ch, fmt, 0, (units || n_units) ? units : &none, n_units);
 }
 
-int cacao_img_equirect_to_cube_units_cvt(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, int dst_ch, int dst_fmt, const cacao_cube_unit* units, uint32_t n_units, void* stream) {
+int cacao_img_equirect_to_cube_units_cvt(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, int dst_ch, int dst_fmt, uint32_t flags, const cacao_cube_unit* units, uint32_t n_units, void* stream) {
 	if(!src || !dst || (!units && n_units)) return fail(CACAO_E_BAD_ARG, "null pointer");
+	if(flags & ~CACAO_EQUIRECT_FLIP_ROWS) return fail(CACAO_E_BAD_ARG, "equirect: unknown flags 0x%x", flags);
 	int rc = check_equirect_cvt(ch, fmt, dst_ch, dst_fmt, W, H, N, src_row0, src_rows, units, n_units);
 	if(rc) return rc;
 	if(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) != 0) return fail(CACAO_E_BAD_ARG, "equirect: device buffers must be 16-byte aligned");
@@ -1188,7 +1193,7 @@ int cacao_img_equirect_to_cube_units_cvt(int device, const void* src, uint32_t W
 	CubeUnit whole[6];
 	const CubeUnit* list = units_or_whole_cube(units, n_units, N, whole);
 	unsigned launches = 0;
-	cudaError_t e = equirect_launch_units(src, dst, ch, fmt, W, H, src_row0, src_rows, N, list, n_units, static_cast<cudaStream_t>(stream), &launches, dst_ch, dst_fmt);
+	cudaError_t e = equirect_launch_units(src, dst, ch, fmt, W, H, src_row0, src_rows, N, list, n_units, static_cast<cudaStream_t>(stream), &launches, dst_ch, dst_fmt, flags);
 	g_launches.fetch_add(launches, std::memory_order_relaxed);
 	if(e != cudaSuccess) return fail_cuda(e, "equirect kernel launch");
 	return CACAO_OK;
@@ -1196,7 +1201,7 @@ int cacao_img_equirect_to_cube_units_cvt(int device, const void* src, uint32_t W
 
 int cacao_img_equirect_to_cube_units(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, const cacao_cube_unit* units, uint32_t n_units, void* stream) {
 	static const cacao_cube_unit none = {0, 0, 0};
-	return cacao_img_equirect_to_cube_units_cvt(device, src, W, H, src_row0, src_rows, ch, fmt, dst, N, ch, fmt, (units || n_units) ? units : &none, n_units, stream);
+	return cacao_img_equirect_to_cube_units_cvt(device, src, W, H, src_row0, src_rows, ch, fmt, dst, N, ch, fmt, 0, (units || n_units) ? units : &none, n_units, stream);
 }
 
 int cacao_img_synth(int device, void* dst_dev, uint64_t first_sample, uint64_t samples, int fmt, int ch, uint32_t seed, void* stream) {

@@ -368,15 +368,16 @@ namespace cacao {
 			const IDX total_px = static_cast<IDX>(prm.src_rows) * static_cast<IDX>(prm.W);
 			const RowTaps<IDX> rt = row_taps<IDX>(fmaf(-theta, prm.pc.ky, prm.pc.cy), prm);
 
-			uint8_t* orow = dst + (static_cast<size_t>(face) * prm.N + j) * prm.N * bpp;
+			// flipped output (bottom row first): the pixel is the same, only its row in the face changes
+			const uint32_t jm = prm.N - 1u - j;
+			uint8_t* orow = dst + (static_cast<size_t>(face) * prm.N + (prm.flip ? jm : j)) * prm.N * bpp;
 			const float xs_a = fmaf(atan2_quadrant(rphi, xa, za), prm.pc.kx, prm.pc.cx);
 			const float xs_b = fmaf(atan2_quadrant(rphi, xb, zb), prm.pc.kx, prm.pc.cx);
 			sample_and_store<F, CH, IDX, DF, DC>(src, orow + static_cast<size_t>(i) * bpp, xs_a, W, rt, total_px);
 			if(im != i) sample_and_store<F, CH, IDX, DF, DC>(src, orow + static_cast<size_t>(im) * bpp, xs_b, W, rt, total_px);
 			if constexpr(QUAD) {
-				const uint32_t jm = prm.N - 1u - j;
 				if(!(unit.face & kUnitMirror) || jm == j) return; // uniform per block: units are indexed by blockIdx.z
-				uint8_t* mrow = dst + (static_cast<size_t>(face) * prm.N + jm) * prm.N * bpp;
+				uint8_t* mrow = dst + (static_cast<size_t>(face) * prm.N + (prm.flip ? j : jm)) * prm.N * bpp;
 				const bool polar = (face & 6u) == 2u; // +-Y: the row mirror negates z, theta stays
 				const RowTaps<IDX> rm = polar ? rt : row_taps<IDX>(fmaf(theta, prm.pc.ky, prm.pc.cy), prm);
 				const float xs_c = polar ? fmaf(atan2_quadrant(rphi, xa, -za), prm.pc.kx, prm.pc.cx) : xs_a;
@@ -567,7 +568,7 @@ namespace cacao {
 			constexpr int bpp = FmtTraits<F>::bytes * CH;
 			if constexpr(!fused && (bpp == 4 || bpp == 8 || bpp == 16)) {
 				const char* e = getenv("CACAO_EQUIRECT_STAGED");
-				const bool staged = e && e[0] == '1' && (static_cast<uint64_t>(prm.W) * bpp) % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+				const bool staged = e && e[0] == '1' && !prm.flip && (static_cast<uint64_t>(prm.W) * bpp) % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
 				if(staged) {
 					equirect_staged_kernel<F, CH><<<grid, block, 0, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), prm);
 					return cudaGetLastError();
@@ -727,7 +728,7 @@ namespace cacao {
 		return float_src && (dst_ch == ch || (ch == 3 && dst_ch == 4));
 	}
 
-	cudaError_t equirect_launch_units(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, const CubeUnit* units, uint32_t n_units, cudaStream_t stream, unsigned* launches, int dst_ch, int dst_fmt) {
+	cudaError_t equirect_launch_units(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, const CubeUnit* units, uint32_t n_units, cudaStream_t stream, unsigned* launches, int dst_ch, int dst_fmt, uint32_t flags) {
 		if(launches) *launches = 0;
 		if(dst_ch <= 0) dst_ch = ch;
 		if(dst_fmt < 0) dst_fmt = fmt;
@@ -739,6 +740,7 @@ namespace cacao {
 		prm.N = N;
 		prm.src_row0 = src_row0;
 		prm.src_rows = src_rows;
+		prm.flip = (flags & CACAO_EQUIRECT_FLIP_ROWS) ? 1u : 0u;
 		prm.pc = make_proj_const(N, W, H);
 		// The grid's y extent is that of the tallest unit in a launch, and blocks beyond a shorter unit's
 		// rows exit at once but are not free (a sharded 16384x8192 job whose +-Y bands are half as tall as
@@ -757,7 +759,7 @@ namespace cacao {
 		// test / A-B switches: two-fold sharing only; the staged experiment knows plain units only
 		const char* qe = getenv("CACAO_EQUIRECT_NO_QUAD");
 		const char* se = getenv("CACAO_EQUIRECT_STAGED");
-		if(!(qe && qe[0] == '1') && (fused || !(se && se[0] == '1'))) todo = pair_mirror_units(todo, N);
+		if(!(qe && qe[0] == '1') && (fused || prm.flip || !(se && se[0] == '1'))) todo = pair_mirror_units(todo, N);
 		uint32_t hmin = 0xFFFFFFFFu, hmax = 0;
 		for(const CubeUnit& u : todo) {
 			hmin = std::min(hmin, u.row_end - u.row_begin);

@@ -25,6 +25,7 @@ namespace cacao {
 		uint32_t N;                  // face edge in pixels
 		uint32_t src_row0, src_rows; // window of source rows present in `src`
 		uint32_t n_units;            // blockIdx.z selects the unit
+		uint32_t flip;               // != 0: face row j is stored at row N-1-j (bottom row first, the GL convention)
 		CubeUnit units[kMaxUnitsPerLaunch];
 		ProjConst pc;
 	};
@@ -33,7 +34,9 @@ namespace cacao {
 	// (normally one), *launches gets the count.
 	// dst_ch / dst_fmt other than ch / fmt: resampling and format conversion in one pass (Spec B.4; float
 	// sources, same channels or RGB -> RGBA -- equirect_cvt_supported); <= 0 / < 0 mean "as the source".
-	cudaError_t equirect_launch_units(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, const CubeUnit* units, uint32_t n_units, cudaStream_t stream, unsigned* launches, int dst_ch = 0, int dst_fmt = -1);
+	// flags: CACAO_EQUIRECT_FLIP_ROWS stores every face bottom row first (units still name rows of the
+	// unflipped face: row j lands at N-1-j).
+	cudaError_t equirect_launch_units(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, const CubeUnit* units, uint32_t n_units, cudaStream_t stream, unsigned* launches, int dst_ch = 0, int dst_fmt = -1, uint32_t flags = 0);
 	bool equirect_cvt_supported(int ch, int fmt, int dst_ch, int dst_fmt);
 
 	// The folding step of equirect_launch_units on its own (host only): mirror bands of the input become

@@ -215,13 +215,14 @@ namespace libcacaoimage {
 	}
 
 	std::array<ImageEx, 6> EquirectToCubemap(const ImageEx& src, unsigned int faceSize, const std::vector<int>& devices) {
-		return EquirectToCubemap(src, faceSize, src.layout, src.format, devices);
+		return EquirectToCubemap(src, faceSize, src.layout, src.format, devices, false);
 	}
 
-	std::array<ImageEx, 6> EquirectToCubemap(const ImageEx& src, unsigned int faceSize, Image::Layout layout, SampleFormat format, const std::vector<int>& devices) {
+	std::array<ImageEx, 6> EquirectToCubemap(const ImageEx& src, unsigned int faceSize, Image::Layout layout, SampleFormat format, const std::vector<int>& devices, bool flipRows) {
 		if(!FusedProjectionDefined(src.layout, src.format, layout, format)) {
 			// no one-pass form (integer source, or a layout change other than RGB -> RGBA): two passes
-			std::array<ImageEx, 6> faces = EquirectToCubemap(src, faceSize, src.layout, src.format, devices);
+			// (the row mirror is folded into the first one: conversion does not care about rows)
+			std::array<ImageEx, 6> faces = EquirectToCubemap(src, faceSize, src.layout, src.format, devices, flipRows);
 			for(auto& f : faces) f = Convert(f, layout, format);
 			return faces;
 		}
@@ -298,7 +299,7 @@ namespace libcacaoimage {
 			const std::size_t pitch = static_cast<std::size_t>(src.w) * bpp;
 			void* dst[6];
 			for(unsigned f = 0; f < 6; ++f) dst[f] = faces[f].data.data();
-			if(cacao_img_equirect_to_cube_units_host_cvt(devs[k], src.data.data() + static_cast<std::size_t>(lo) * pitch, src.w, src.h, lo, hi - lo, static_cast<int>(src.layout), static_cast<int>(src.format), dst, faceSize, static_cast<int>(layout), static_cast<int>(format), units.data() + u0, static_cast<uint32_t>(u1 - u0)) != CACAO_OK)
+			if(cacao_img_equirect_to_cube_units_host_cvt(devs[k], src.data.data() + static_cast<std::size_t>(lo) * pitch, src.w, src.h, lo, hi - lo, static_cast<int>(src.layout), static_cast<int>(src.format), dst, faceSize, static_cast<int>(layout), static_cast<int>(format), flipRows ? CACAO_EQUIRECT_FLIP_ROWS : 0u, units.data() + u0, static_cast<uint32_t>(u1 - u0)) != CACAO_OK)
 				errors[k] = cacao_img_last_error();
 		};
 		if(devs.size() == 1) {
@@ -430,20 +431,20 @@ namespace libcacaoimage {
 	}
 
 	std::array<DeviceImage, 6> DeviceImage::EquirectToCubemap(unsigned int faceSize) const {
-		return EquirectToCubemap(faceSize, layout_, format_);
+		return EquirectToCubemap(faceSize, layout_, format_, false);
 	}
 
-	std::array<DeviceImage, 6> DeviceImage::EquirectToCubemap(unsigned int faceSize, Image::Layout layout, SampleFormat format) const {
+	std::array<DeviceImage, 6> DeviceImage::EquirectToCubemap(unsigned int faceSize, Image::Layout layout, SampleFormat format, bool flipRows) const {
 		if(Empty()) check(CACAO_E_EMPTY);
 		if(faceSize == 0) check(CACAO_E_ZERO_DIM);
 		if(!FusedProjectionDefined(layout_, format_, layout, format)) {
-			std::array<DeviceImage, 6> faces = EquirectToCubemap(faceSize, layout_, format_);
+			std::array<DeviceImage, 6> faces = EquirectToCubemap(faceSize, layout_, format_, flipRows);
 			for(auto& f : faces) f = f.Convert(layout, format);
 			return faces;
 		}
 		const std::size_t face_bytes = static_cast<std::size_t>(faceSize) * faceSize * BytesPerPixel(layout, format);
 		std::shared_ptr<void> cube = device_alloc(device_, 6 * face_bytes);
-		check(cacao_img_equirect_to_cube_units_cvt(device_, ptr_, w_, h_, 0, h_, static_cast<int>(layout_), static_cast<int>(format_), cube.get(), faceSize, static_cast<int>(layout), static_cast<int>(format), nullptr, 0, nullptr));
+		check(cacao_img_equirect_to_cube_units_cvt(device_, ptr_, w_, h_, 0, h_, static_cast<int>(layout_), static_cast<int>(format_), cube.get(), faceSize, static_cast<int>(layout), static_cast<int>(format), flipRows ? CACAO_EQUIRECT_FLIP_ROWS : 0u, nullptr, 0, nullptr));
 		std::array<DeviceImage, 6> faces;
 		for(unsigned f = 0; f < 6; ++f) {
 			faces[f].owner_ = cube;

@@ -117,17 +117,21 @@ def _flat_units(units):
 	return flat, len(flat)
 
 
-def equirect_to_cube_cvt(src: int, W: int, H: int, ch: int, fmt: int, dst: int, N: int, dst_ch: int, dst_fmt: int, units=None, src_row0: int = 0, src_rows: int | None = None, device: int = -1, stream=None) -> None:
-	"""Resampling + format / layout conversion in one pass (Spec B.4; float sources).  units=None: whole cube."""
+FLIP_ROWS = 1
+
+
+def equirect_to_cube_cvt(src: int, W: int, H: int, ch: int, fmt: int, dst: int, N: int, dst_ch: int, dst_fmt: int, units=None, flags: int = 0, src_row0: int = 0, src_rows: int | None = None, device: int = -1, stream=None) -> None:
+	"""Resampling + format / layout conversion in one pass (Spec B.4; float sources); flags=FLIP_ROWS
+	stores the faces bottom row first (any format).  units=None: whole cube."""
 	flat, n = _flat_units(units)
-	capi.check(capi.lib().cacao_img_equirect_to_cube_units_cvt(device, src, W, H, src_row0, H if src_rows is None else src_rows, ch, fmt, dst, N, dst_ch, dst_fmt, flat.ctypes.data if flat is not None else None, n, stream))
+	capi.check(capi.lib().cacao_img_equirect_to_cube_units_cvt(device, src, W, H, src_row0, H if src_rows is None else src_rows, ch, fmt, dst, N, dst_ch, dst_fmt, flags, flat.ctypes.data if flat is not None else None, n, stream))
 
 
-def equirect_to_cube_cvt_host(src: int, W: int, H: int, ch: int, fmt: int, faces, N: int, dst_ch: int, dst_fmt: int, units=None, src_row0: int = 0, src_rows: int | None = None, device: int = -1) -> None:
+def equirect_to_cube_cvt_host(src: int, W: int, H: int, ch: int, fmt: int, faces, N: int, dst_ch: int, dst_fmt: int, units=None, flags: int = 0, src_row0: int = 0, src_rows: int | None = None, device: int = -1) -> None:
 	"""Host-memory form: faces = six host addresses of N x N x dst_ch faces in dst_fmt."""
 	flat, n = _flat_units(units)
 	ptrs = (C.c_void_p * 6)(*[int(f) if f else None for f in faces])
-	capi.check(capi.lib().cacao_img_equirect_to_cube_units_host_cvt(device, src, W, H, src_row0, H if src_rows is None else src_rows, ch, fmt, ptrs, N, dst_ch, dst_fmt, flat.ctypes.data if flat is not None else None, n))
+	capi.check(capi.lib().cacao_img_equirect_to_cube_units_host_cvt(device, src, W, H, src_row0, H if src_rows is None else src_rows, ch, fmt, ptrs, N, dst_ch, dst_fmt, flags, flat.ctypes.data if flat is not None else None, n))
 
 
 def equirect_src_window(W: int, H: int, N: int, face_mask: int, row_begin: int, row_end: int) -> tuple[int, int]:

@@ -195,15 +195,20 @@ int cacao_img_equirect_to_cube_units_host(int device, const void* src, uint32_t 
  * straight to an RGBA16F cube, without the F32 cube ever touching memory.  Defined for FLOAT sources
  * (F16, F32), dst_ch == ch or 3 -> 4; dst_ch == ch && dst_fmt == fmt is the plain resampling of any
  * format; everything else returns CACAO_E_BAD_ARG (resample, then convert).  dst holds 6 faces of
- * N x N x dst_ch samples of dst_fmt.  units == NULL && n_units == 0: the whole cube. */
+ * N x N x dst_ch samples of dst_fmt.  units == NULL && n_units == 0: the whole cube.
+ * flags: CACAO_EQUIRECT_FLIP_ROWS stores every face bottom row first -- the vertical mirror the GL
+ * backend applies before upload (engine/src/opengl/impls/OpenGLCubemap.cpp:25), folded into the store
+ * addressing for every format; units keep naming rows of the unflipped face (row j lands at N-1-j). */
+#define CACAO_EQUIRECT_FLIP_ROWS 1u
 int cacao_img_equirect_to_cube_units_cvt(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0,
 										 uint32_t src_rows, int ch, int fmt, void* dst, uint32_t N, int dst_ch,
-										 int dst_fmt, const cacao_cube_unit* units, uint32_t n_units, void* stream);
+										 int dst_fmt, uint32_t flags, const cacao_cube_unit* units, uint32_t n_units,
+										 void* stream);
 /* Host-memory form (faces[f] = host base of face f in the DESTINATION format), pipelined like
  * cacao_img_equirect_to_cube_units_host. */
 int cacao_img_equirect_to_cube_units_host_cvt(int device, const void* src, uint32_t W, uint32_t H,
 											  uint32_t src_row0, uint32_t src_rows, int ch, int fmt,
-											  void* const* faces, uint32_t N, int dst_ch, int dst_fmt,
+											  void* const* faces, uint32_t N, int dst_ch, int dst_fmt, uint32_t flags,
 											  const cacao_cube_unit* units, uint32_t n_units);
 
 /* Host-side planning: the inclusive-exclusive window of source rows that the work unit

@@ -52,7 +52,9 @@ namespace libcacaoimage {
 	// one pass over the pixels (DESIGN.md "Spec B.4": the fp32 filter result is converted as Convert()
 	// converts an F32 sample) -- an RGB32F .hdr panorama becomes an RGBA16F cube without the F32 cube ever
 	// existing.  FusedProjectionDefined() tells; every other pair runs the two passes for you.
-	std::array<ImageEx, 6> EquirectToCubemap(const ImageEx& src, unsigned int faceSize, Image::Layout layout, SampleFormat format, const std::vector<int>& devices = {});
+	// flipRows: every face comes out bottom row first -- the vertical mirror the GL backend applies before
+	// upload (engine/src/opengl/impls/OpenGLCubemap.cpp:25) -- folded into the store addressing (any format).
+	std::array<ImageEx, 6> EquirectToCubemap(const ImageEx& src, unsigned int faceSize, Image::Layout layout, SampleFormat format, const std::vector<int>& devices = {}, bool flipRows = false);
 	bool FusedProjectionDefined(Image::Layout srcLayout, SampleFormat srcFormat, Image::Layout layout, SampleFormat format);
 
 	// Flip for any sample format.
@@ -98,7 +100,7 @@ namespace libcacaoimage {
 		// layout the Vulkan backend concatenates by hand (engine/src/vulkan/impls/VulkanCubemap.cpp:30-41)
 		std::array<DeviceImage, 6> EquirectToCubemap(unsigned int faceSize) const;
 		// faces in another layout / format: one fused pass where Spec B.4 defines it, else project + Convert
-		std::array<DeviceImage, 6> EquirectToCubemap(unsigned int faceSize, Image::Layout layout, SampleFormat format) const;
+		std::array<DeviceImage, 6> EquirectToCubemap(unsigned int faceSize, Image::Layout layout, SampleFormat format, bool flipRows = false) const;
 
 		unsigned int Width() const { return w_; }
 		unsigned int Height() const { return h_; }

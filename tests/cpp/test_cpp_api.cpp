@@ -218,6 +218,13 @@ int main(int argc, char** argv) {
 			EXPECT(quant[f].data == Convert(plain[f], L::RGB, SampleFormat::U8).data);
 			EXPECT(dfused[f].Download().data == fused[f].data && dfused[f].Format() == SampleFormat::F16);
 		}
+		// bottom row first, folded into the same pass
+		const auto flipped = EquirectToCubemap(hdr, 24, L::RGBA, SampleFormat::F16, {}, true);
+		const auto dflipped = DeviceImage::Upload(hdr).EquirectToCubemap(24, L::RGB, SampleFormat::F32, true);
+		for(int f = 0; f < 6; ++f) {
+			EXPECT(flipped[f].data == Flip(fused[f]).data);
+			EXPECT(dflipped[f].Download().data == Flip(plain[f]).data);
+		}
 		ImageEx deep;
 		deep.w = 64;
 		deep.h = 32;

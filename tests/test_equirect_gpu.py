@@ -275,6 +275,45 @@ def test_fused_resample_and_convert_matches_the_composition(oracle, sf, ch, dc, 
 	a.free(), b.free()
 
 
+@pytest.mark.parametrize("fmt,ch,dfmt,dch", [(0, 4, 0, 4), (1, 3, 1, 3), (2, 1, 2, 1), (3, 4, 3, 4), (3, 3, 2, 4), (2, 4, 0, 4)], ids=["u8x4", "u16x3", "f16x1", "f32x4", "f32x3-f16x4", "f16x4-u8x4"])
+@pytest.mark.parametrize("N", [24, 31])
+def test_flipped_faces_bottom_row_first(oracle, fmt, ch, dfmt, dch, N):
+	"""CACAO_EQUIRECT_FLIP_ROWS: every face equals the unflipped face mirrored vertically -- whole cube
+	(four-fold units), a unit list (row j lands at N-1-j, nothing else is written) and the host-memory
+	pipeline with six separate face buffers, for plain and fused-conversion shapes."""
+	from cacaoengine_b200 import device
+
+	W, H = 4 * N + 1, 2 * N + 3
+	rng = np.random.default_rng(N + fmt)
+	if fmt >= 2:
+		src = _float_pano(rng, W, H, ch, fmt, dfmt)
+	else:
+		src = oracle.synth(W * H * ch, fmt, ch, 77 + N)
+	plain = (oracle.equirect_to_cube(src, W, H, ch, fmt, N) if (dfmt, dch) == (fmt, ch) else oracle.equirect_to_cube_cvt(src, W, H, ch, fmt, N, dch, dfmt)).reshape(6, N, N * dch)
+	want = plain[:, ::-1, :].copy()
+	a, b = DevBuf(src.nbytes), DevBuf(want.nbytes)
+	device.upload(a.ptr, src)
+	device.upload(b.ptr, np.zeros_like(want))
+	device.equirect_to_cube_cvt(a.ptr, W, H, ch, fmt, b.ptr, N, dch, dfmt, flags=device.FLIP_ROWS)
+	got = np.empty_like(want)
+	device.download(got, b.ptr)
+	assert same_bits(got, want)
+	units = [(1, 2, 9), (1, N - 9, N - 2), (3, 0, 5), (4, N // 2 - 1, N // 2 + 2)]
+	part = np.zeros_like(want)
+	for f, r0, r1 in units:
+		part[f, N - r1:N - r0] = want[f, N - r1:N - r0]
+	device.upload(b.ptr, np.zeros_like(want))
+	device.equirect_to_cube_cvt(a.ptr, W, H, ch, fmt, b.ptr, N, dch, dfmt, units=units, flags=device.FLIP_ROWS)
+	device.download(got, b.ptr)
+	assert same_bits(got, part)
+	a.free(), b.free()
+	faces = [np.zeros(N * N * dch, want.dtype) for _ in range(6)]
+	device.equirect_to_cube_cvt_host(src.ctypes.data, W, H, ch, fmt, [f.ctypes.data for f in faces], N, dch, dfmt, units=units + [(0, 0, N)], flags=device.FLIP_ROWS)
+	part[0] = want[0]
+	for f in range(6):
+		assert same_bits(faces[f], part[f].reshape(-1)), f
+
+
 def test_fused_resample_host_path_and_full_size_property(oracle):
 	"""Host-memory form with six separate face buffers (RGB32F panorama -> RGBA16F faces), and at
 	BASELINE config 3's size: the fused RGBA32F -> RGBA16F cube equals resample-then-convert on the

@@ -54,10 +54,9 @@ int RunProject(const ProjectOptions& opt) {
 		if(opt.gpus == 1 && post) {
 			const DeviceImage dpano = DeviceImage::Upload(pano);
 			//Float panoramas are resampled and converted in one pass where that is defined (Spec B.4)
-			const std::array<DeviceImage, 6> dfaces = dpano.EquirectToCubemap(N, layout, fmt);
+			const std::array<DeviceImage, 6> dfaces = dpano.EquirectToCubemap(N, layout, fmt, opt.flip);
 			for(int i = 0; i < 6; ++i) {
 				DeviceImage f = dfaces[i];
-				if(opt.flip) f = f.Flip();
 				faces[i] = f.Download();
 			}
 			return;
@@ -65,10 +64,7 @@ int RunProject(const ProjectOptions& opt) {
 		std::vector<int> devices;
 		for(int d = 0; d < opt.gpus; ++d) devices.push_back(d);
 		if(devices.size() == 1) devices.clear(); // current device
-		faces = EquirectToCubemap(pano, N, layout, fmt, devices);
-		for(auto& f : faces) {
-			if(opt.flip) f = Flip(f);
-		}
+		faces = EquirectToCubemap(pano, N, layout, fmt, devices, opt.flip);
 	};
 	VLOG_NONL("Projecting onto 6 faces of " << N << "x" << N << " on " << opt.gpus << " GPU(s)... ")
 	const auto t0 = std::chrono::steady_clock::now();
