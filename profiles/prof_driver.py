@@ -1,7 +1,7 @@
 """Small driver for ncu captures: launches each hot kernel of the BASELINE configs a few times on
 device-resident synthetic data, through the C ABI only (no torch).  Usage:
 
-    python profiles/prof_driver.py [cfg1] [cfg2] [cfg3] [cfg5] [rgb32f] [shard8] [cfg4a] [cfg4b] [lut] [--reps N]
+    python profiles/prof_driver.py [cfg1] [cfg2] [cfg3] [cfg5] [rgb32f] [fused] [shard8] [cfg4a] [cfg4b] [lut] [--reps N]
 """
 import os
 import sys
@@ -41,6 +41,15 @@ def main():
 				device.equirect_to_cube(a, W, H, ch, fmt, b, N)
 			device.sync()
 			device.free(a), device.free(b)
+	if "fused" in which:
+		# config 3 with the cube written as RGBA16F in the same pass (Spec B.4)
+		W, H, N = 8192, 4096, 2048
+		a, b = device.malloc(W * H * 16), device.malloc(6 * N * N * 8)
+		device.synth(a, W * H * 4, FMT_F32, 4, 2)
+		for _ in range(reps):
+			device.equirect_to_cube_cvt(a, W, H, 4, FMT_F32, b, N, 4, FMT_F16)
+		device.sync()
+		device.free(a), device.free(b)
 	if "shard8" in which:
 		# what rank 0 of an 8-GPU config-5 job launches: its mirror-pair unit list, folded into four-fold
 		# units (first `reps` launches), then the same list computed two-fold (next `reps`)

@@ -60,6 +60,10 @@ def main():
 					keys.pop(frag, None)
 					if g == grid:
 						keys[frag] = key
+			# the fused resample + convert instantiations carry the destination format / channels as trailing
+			# template arguments: RGBA32F -> RGBA16F is equirect_kernel<3, 4, unsigned int, 1, 8, 2, 4>
+			if "equirect_kernel<3, 4" in name and ", 2, 4>(" in name:
+				keys = {"equirect_kernel<3, 4": "cfg3_fused_rgba32f_to_rgba16f_cube"} if grid == "(128, 64, 6)" else {}
 			for frag, key in keys.items():
 				if frag in name:
 					rd = float(r[idx["dram__bytes_read.sum"]]) * UNIT_SCALE[units[idx["dram__bytes_read.sum"]]]
