@@ -523,8 +523,10 @@ namespace {
 		return CACAO_OK;
 	}
 
-	int enqueue_convert(DeviceCtx* c, const void* src, void* dst, uint64_t pixels, uint64_t ppi, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, cudaStream_t stream) {
+	int enqueue_convert(DeviceCtx* c, const void* src, void* dst, uint64_t pixels, uint64_t ppi, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, cudaStream_t stream, uint32_t flip_w = 0, uint32_t flip_h = 0) {
 		ConvertJob job;
+		job.flip_w = flip_w;
+		job.flip_h = flip_h;
 		job.src = src;
 		job.dst = dst;
 		job.pixels = pixels;
@@ -946,6 +948,23 @@ int cacao_img_convert_batch(int device, const void* src, void* dst, uint64_t pix
 	if(pixels == 0) return CACAO_OK;
 	if(mem == CACAO_MEM_DEVICE) return enqueue_convert(c, src, dst, pixels, pixels_per_image, src_ch, dst_ch, src_fmt, dst_fmt, mode, static_cast<cudaStream_t>(stream));
 	return convert_host_pipeline(c, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), pixels, pixels_per_image, src_ch, dst_ch, src_fmt, dst_fmt, mode);
+}
+
+int cacao_img_convert_flip(int device, const void* src, void* dst, uint32_t w, uint32_t h, uint64_t count, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, int mem, void* stream) {
+	int rc = check_convert_args(src, dst, src_ch, dst_ch, src_fmt, dst_fmt, mode, mem);
+	if(rc) return rc;
+	if(w == 0 || h == 0) return fail(CACAO_E_ZERO_DIM, "%s", cacao_img_status_string(CACAO_E_ZERO_DIM));
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	const uint64_t ppi = static_cast<uint64_t>(w) * h, pixels = ppi * count;
+	if(pixels == 0) return CACAO_OK;
+	if(mem == CACAO_MEM_DEVICE) return enqueue_convert(c, src, dst, pixels, ppi, src_ch, dst_ch, src_fmt, dst_fmt, mode, static_cast<cudaStream_t>(stream), w, h);
+	// host memory: one upload, the fused kernel, one readback (the chunked pipeline of the unflipped call
+	// cuts the stream at arbitrary pixels; here a row's destination depends on its image)
+	const uint64_t in_bytes = pixels * src_ch * fmt_bytes(src_fmt), out_bytes = pixels * dst_ch * fmt_bytes(dst_fmt);
+	return run_host_op(c, "convert_flip", src, in_bytes, dst, out_bytes, [&](uint8_t* s, uint8_t* d, cudaStream_t q) -> int { return enqueue_convert(c, s, d, pixels, ppi, src_ch, dst_ch, src_fmt, dst_fmt, mode, q, w, h); });
 }
 
 int cacao_img_convert(int device, const void* src, void* dst, uint64_t pixels, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, int mem, void* stream) {

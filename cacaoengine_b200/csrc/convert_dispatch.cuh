@@ -16,6 +16,7 @@ namespace cacao {
 		uint64_t pixels_per_image; // domain of the Gray->RGBA pixel-0 quirk
 		int src_ch, dst_ch, src_fmt, dst_fmt;
 		int mode;
+		uint32_t flip_w = 0, flip_h = 0; // != 0: images are flip_w x flip_h pixels and come out bottom row first
 		const uint8_t* lut_dev;   // 65536-byte table in device global memory
 		const uint16_t* lut2_dev; // its 4096-entry two-level form (convert_pixel.cuh)
 		TileLaunch dev;
@@ -26,8 +27,8 @@ namespace cacao {
 	// One thread per pixel, byte-wise loads and stores: used for the < one-tile tail, for buffers
 	// that are not 16-byte aligned, and for the reference's Gray->RGBA quirk (Layout.cpp:50-51:
 	// the source pointer never advances, so every output pixel repeats pixel 0 of its image).
-	template<int SF, int DF, int SC, int DC>
-	__global__ void __launch_bounds__(256) convert_edge_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t p_begin, uint64_t p_end, uint64_t pixels_per_image, int pixel0_quirk, const uint8_t* __restrict__ lut_global, uint32_t gray16_cap) {
+	template<int SF, int DF, int SC, int DC, bool FLIP = false>
+	__global__ void __launch_bounds__(256) convert_edge_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t p_begin, uint64_t p_end, uint64_t pixels_per_image, int pixel0_quirk, const uint8_t* __restrict__ lut_global, uint32_t gray16_cap, FlipMap flip) {
 		constexpr int sb = FmtTraits<SF>::bytes, db = FmtTraits<DF>::bytes;
 		PixelCtx ctx;
 		ctx.lut = lut_global;
@@ -46,7 +47,7 @@ namespace cacao {
 				in[c] = v;
 			}
 			convert_pixel<SF, DF, SC, DC>(in, out, ctx);
-			uint8_t* d = dst + p * (DC * db);
+			uint8_t* d = dst + (FLIP ? flip(p) : p) * (DC * db);
 #pragma unroll
 			for(int c = 0; c < DC; ++c) {
 #pragma unroll
@@ -65,15 +66,22 @@ namespace cacao {
 		// buffers are 32-byte aligned; otherwise the 128-bit tile kernel (convert_tiles.cuh)
 		uint64_t done = 0;
 		bool wide = false;
+		// Row mirror in the same pass: the kernel whose unit (lane run / tile) divides the image width
+		// stores unit k of row y at row h-1-y; a width no unit divides goes through the byte-wise kernel.
+		const bool flipped = job.flip_w != 0 && job.flip_h > 1;
+		const bool tile_fits = !flipped || job.flip_w % S::tile_pixels == 0;
 		if constexpr(WideShape<SF, DF, SC, DC>::ok) {
 			using WS = WideShape<SF, DF, SC, DC>;
 			const bool aligned32 = ((reinterpret_cast<uintptr_t>(job.src) | reinterpret_cast<uintptr_t>(job.dst)) & 31u) == 0;
 			const char* force = getenv("CACAO_FORCE_WIDE"); // dev/test switch: run every fitting shape on the sector kernel
-			wide = !quirk && aligned32 && !getenv("CACAO_NO_WIDE") && (WS::preferred || (force && force[0] == '1'));
+			const bool wide_fits = !flipped || job.flip_w % WS::G == 0;
+			wide = !quirk && aligned32 && !getenv("CACAO_NO_WIDE") && wide_fits && (WS::preferred || (force && force[0] == '1') || (flipped && !(tile_fits && aligned)));
 			if(wide) {
 				const uint64_t n_runs = job.pixels / WS::G;
 				if(n_runs > 0) {
-					cudaError_t e = launch_convert_wide<SF, DF, SC, DC>(job.src, job.dst, n_runs, job.lut_dev, job.lut2_dev, gray16_cap, job.stream);
+					FlipMap fm;
+					if(flipped) fm.per_row = job.flip_w / WS::G, fm.rows = job.flip_h;
+					cudaError_t e = launch_convert_wide<SF, DF, SC, DC>(job.src, job.dst, n_runs, job.lut_dev, job.lut2_dev, gray16_cap, job.stream, fm);
 					if(e != cudaSuccess) return e;
 					job.launches += 1;
 				}
@@ -81,9 +89,11 @@ namespace cacao {
 			}
 		}
 		if(!wide) {
-			const uint64_t n_tiles = (quirk || !aligned) ? 0 : job.pixels / S::tile_pixels;
+			const uint64_t n_tiles = (quirk || !aligned || !tile_fits) ? 0 : job.pixels / S::tile_pixels;
 			if(n_tiles > 0) {
-				cudaError_t e = launch_convert_tiles<SF, DF, SC, DC>(job.src, job.dst, n_tiles, job.lut2_dev, gray16_cap, job.dev, job.stream);
+				FlipMap fm;
+				if(flipped) fm.per_row = static_cast<uint32_t>(job.flip_w / S::tile_pixels), fm.rows = job.flip_h;
+				cudaError_t e = launch_convert_tiles<SF, DF, SC, DC>(job.src, job.dst, n_tiles, job.lut2_dev, gray16_cap, job.dev, job.stream, fm);
 				if(e != cudaSuccess) return e;
 				job.launches += 1;
 			}
@@ -94,7 +104,10 @@ namespace cacao {
 			uint64_t blocks = (rest + 255) / 256;
 			const uint64_t cap = static_cast<uint64_t>(job.dev.sm_count) * 8;
 			if(blocks > cap) blocks = cap;
-			convert_edge_kernel<SF, DF, SC, DC><<<static_cast<unsigned>(blocks), 256, 0, job.stream>>>(static_cast<const uint8_t*>(job.src), static_cast<uint8_t*>(job.dst), done, job.pixels, job.pixels_per_image, quirk ? 1 : 0, job.lut_dev, gray16_cap);
+			FlipMap fm; // in pixels
+			if(flipped) fm.per_row = job.flip_w, fm.rows = job.flip_h;
+			auto edge = flipped ? convert_edge_kernel<SF, DF, SC, DC, true> : convert_edge_kernel<SF, DF, SC, DC, false>;
+			edge<<<static_cast<unsigned>(blocks), 256, 0, job.stream>>>(static_cast<const uint8_t*>(job.src), static_cast<uint8_t*>(job.dst), done, job.pixels, job.pixels_per_image, quirk ? 1 : 0, job.lut_dev, gray16_cap, fm);
 			cudaError_t e = cudaGetLastError();
 			if(e != cudaSuccess) return e;
 			job.launches += 1;

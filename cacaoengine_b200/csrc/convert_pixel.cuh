@@ -67,6 +67,26 @@ namespace cacao {
 		return __float2uint_rz(__fadd_rn(__fmul_rn(c, static_cast<float>(M)), 0.5f));
 	}
 
+	// Row mirror folded into a conversion's store addressing.  The stream is cut into
+	// equal units (tiles, lane runs or single pixels) that never straddle a row; unit k of row y of
+	// image i is stored where unit k of row rows-1-y of the same image would go.  per_row == 0: identity.
+	struct FlipMap {
+		uint32_t per_row = 0; // units per image row
+		uint32_t rows = 0;    // rows per image
+		__device__ __forceinline__ uint64_t operator()(uint64_t idx) const {
+			if(per_row == 0) return idx;
+			if(idx <= 0xFFFFFFFFull) {
+				const uint32_t i32 = static_cast<uint32_t>(idx);
+				const uint32_t row = i32 / per_row, k = i32 - row * per_row;
+				const uint32_t img = row / rows, y = row - img * rows;
+				return static_cast<uint64_t>(img * rows + (rows - 1u - y)) * per_row + k;
+			}
+			const uint64_t row = idx / per_row, k = idx - row * per_row;
+			const uint64_t img = row / rows, y = row - img * rows;
+			return (img * rows + (rows - 1u - y)) * per_row + k;
+		}
+	};
+
 	struct PixelCtx {
 		const uint8_t* lut;   // 65536-entry table in global memory (edge kernel); only read for U16 -> U8
 		const uint16_t* lut2; // 4096-entry two-level form of the same table in shared memory (tile kernel)

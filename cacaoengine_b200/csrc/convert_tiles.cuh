@@ -65,8 +65,9 @@ namespace cacao {
 			w[k] = v;
 	}
 
-	template<int SF, int DF, int SC, int DC>
-	__global__ void __launch_bounds__(256) convert_tiles_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t n_tiles, uint32_t iters, const uint16_t* __restrict__ lut2_global, uint32_t gray16_cap) {
+	// FLIP: a separate instantiation, so that the plain stream kernel carries none of the index mapping
+	template<int SF, int DF, int SC, int DC, bool FLIP = false>
+	__global__ void __launch_bounds__(256) convert_tiles_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t n_tiles, uint32_t iters, const uint16_t* __restrict__ lut2_global, uint32_t gray16_cap, FlipMap flip) {
 		using S = TileShape<SF, DF, SC, DC>;
 		extern __shared__ __align__(16) uint8_t smem_raw[];
 
@@ -160,7 +161,7 @@ namespace cacao {
 					__syncwarp();
 				}
 				// ---- coalesced stores
-				uint4* tdst = dst + (t0 + u) * (32ull * S::NOUT);
+				uint4* tdst = dst + (FLIP ? flip(t0 + u) : t0 + u) * (32ull * S::NOUT);
 #pragma unroll
 				for(int k = 0; k < S::NOUT; ++k) stg_stream(tdst + k * 32 + lane, ov[k]);
 			}
@@ -174,9 +175,9 @@ namespace cacao {
 	};
 
 	template<int SF, int DF, int SC, int DC>
-	cudaError_t launch_convert_tiles(const void* src, void* dst, uint64_t n_tiles, const uint16_t* lut2_global, uint32_t gray16_cap, const TileLaunch& dev, cudaStream_t stream) {
+	cudaError_t launch_convert_tiles(const void* src, void* dst, uint64_t n_tiles, const uint16_t* lut2_global, uint32_t gray16_cap, const TileLaunch& dev, cudaStream_t stream, FlipMap flip = FlipMap()) {
 		using S = TileShape<SF, DF, SC, DC>;
-		auto kern = convert_tiles_kernel<SF, DF, SC, DC>;
+		auto kern = flip.per_row ? convert_tiles_kernel<SF, DF, SC, DC, true> : convert_tiles_kernel<SF, DF, SC, DC, false>;
 		const size_t stage_per_warp = static_cast<size_t>(S::STAGE_UNITS) * 16;
 		const size_t lut_bytes = S::needs_lut ? kLut2Bytes : 0;
 		const int warps = 8;
@@ -194,7 +195,7 @@ namespace cacao {
 		if(blocks == 0) return cudaSuccess;
 		if(blocks > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
 		(void)dev;
-		kern<<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), n_tiles, iters, lut2_global, gray16_cap);
+		kern<<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), n_tiles, iters, lut2_global, gray16_cap, flip);
 		return cudaGetLastError();
 	}
 

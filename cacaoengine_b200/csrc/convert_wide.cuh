@@ -48,8 +48,8 @@ namespace cacao {
 
 	// LUT_DIRECT: the 16->8 table sits in shared memory in full (64 KiB, one LDS.U8 per sample);
 	// otherwise its 8 KiB two-level form (convert_pixel.cuh).
-	template<int SF, int DF, int SC, int DC, bool LUT_DIRECT>
-	__global__ void __launch_bounds__(LUT_DIRECT ? 1024 : 256) convert_wide_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n_runs, uint32_t iters, const uint8_t* __restrict__ lut_global, const uint16_t* __restrict__ lut2_global, uint32_t gray16_cap) {
+	template<int SF, int DF, int SC, int DC, bool LUT_DIRECT, bool FLIP = false>
+	__global__ void __launch_bounds__(LUT_DIRECT ? 1024 : 256) convert_wide_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t n_runs, uint32_t iters, const uint8_t* __restrict__ lut_global, const uint16_t* __restrict__ lut2_global, uint32_t gray16_cap, FlipMap flip) {
 		using S = WideShape<SF, DF, SC, DC>;
 		extern __shared__ __align__(16) uint8_t smem_raw[];
 		PixelCtx ctx;
@@ -96,7 +96,7 @@ namespace cacao {
 #pragma unroll
 					for(int c = 0; c < DC; ++c) pack_sample<S::db>(o, p * DC + c, out[c]);
 				}
-				uint8_t* q = dst + (r0 + u) * (16ull * S::NOUT16);
+				uint8_t* q = dst + (FLIP ? flip(r0 + u) : r0 + u) * (16ull * S::NOUT16);
 				if constexpr(S::out_sectors) {
 #pragma unroll
 					for(int k = 0; k < S::NOUT16 / 2; ++k) stg256_stream(q + 32 * k, &o[8 * k]);
@@ -109,14 +109,14 @@ namespace cacao {
 	}
 
 	template<int SF, int DF, int SC, int DC>
-	cudaError_t launch_convert_wide(const void* src, void* dst, uint64_t n_runs, const uint8_t* lut_global, const uint16_t* lut2_global, uint32_t gray16_cap, cudaStream_t stream) {
+	cudaError_t launch_convert_wide(const void* src, void* dst, uint64_t n_runs, const uint8_t* lut_global, const uint16_t* lut2_global, uint32_t gray16_cap, cudaStream_t stream, FlipMap flip = FlipMap()) {
 		using S = WideShape<SF, DF, SC, DC>;
 		// table shapes: the 8 KiB two-level form is the default.  The full 64 KiB table (fewest
 		// instructions per sample, but 1024-thread blocks and 3 blocks/SM) is kept selectable: on
 		// uniform-random samples it is 2-15 % behind (RGBA16->RGBA8 5.84 vs 5.93 TB/s, Gray16->Gray8
 		// 4.47 vs 5.23), on smooth images about level (dev/sweep_lut.py).
 		bool direct = false;
-		if(const char* e = getenv("CACAO_LUT_DIRECT")) direct = S::needs_lut && atoi(e) != 0;
+		if(const char* e = getenv("CACAO_LUT_DIRECT")) direct = S::needs_lut && atoi(e) != 0 && !flip.per_row; // test switch; no flipped form
 		uint32_t iters = S::needs_lut ? (direct ? 16u : 4u) : 1u;
 		if(const char* e = getenv("CACAO_TILE_ITERS")) iters = static_cast<uint32_t>(atoi(e) > 0 ? atoi(e) : 1);
 		const int threads = direct ? 1024 : 256;
@@ -130,11 +130,14 @@ namespace cacao {
 				auto kern = convert_wide_kernel<SF, DF, SC, DC, true>;
 				cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
 				if(e != cudaSuccess) return e;
-				kern<<<static_cast<unsigned>(blocks), threads, smem, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lut_global, lut2_global, gray16_cap);
+				kern<<<static_cast<unsigned>(blocks), threads, smem, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lut_global, lut2_global, gray16_cap, flip);
 				return cudaGetLastError();
 			}
 		}
-		convert_wide_kernel<SF, DF, SC, DC, false><<<static_cast<unsigned>(blocks), threads, smem, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lut_global, lut2_global, gray16_cap);
+		if(flip.per_row)
+			convert_wide_kernel<SF, DF, SC, DC, false, true><<<static_cast<unsigned>(blocks), threads, smem, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lut_global, lut2_global, gray16_cap, flip);
+		else
+			convert_wide_kernel<SF, DF, SC, DC, false><<<static_cast<unsigned>(blocks), threads, smem, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lut_global, lut2_global, gray16_cap, flip);
 		return cudaGetLastError();
 	}
 

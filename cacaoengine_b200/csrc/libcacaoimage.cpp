@@ -130,6 +130,10 @@ namespace libcacaoimage {
 	}
 
 	ImageEx Convert(const ImageEx& src, Image::Layout layout, SampleFormat format, ConvertMode mode) {
+		return Convert(src, layout, format, mode, false);
+	}
+
+	ImageEx Convert(const ImageEx& src, Image::Layout layout, SampleFormat format, ConvertMode mode, bool flipRows) {
 		ImageEx out;
 		out.w = src.w;
 		out.h = src.h;
@@ -139,7 +143,10 @@ namespace libcacaoimage {
 		if(src.layout == layout && src.format == format) check(CACAO_E_SAME_LAYOUT);
 		if(src.data.size() < pixels * BytesPerPixel(src.layout, src.format)) throw std::runtime_error("Image data buffer is smaller than w * h * channels * bytes per channel!");
 		out.data.resize(pixels * BytesPerPixel(layout, format));
-		if(pixels) check(cacao_img_convert(-1, src.data.data(), out.data.data(), pixels, static_cast<int>(src.layout), static_cast<int>(layout), static_cast<int>(src.format), static_cast<int>(format), static_cast<int>(mode), CACAO_MEM_HOST, nullptr));
+		if(pixels && flipRows && src.h > 1)
+			check(cacao_img_convert_flip(-1, src.data.data(), out.data.data(), src.w, src.h, 1, static_cast<int>(src.layout), static_cast<int>(layout), static_cast<int>(src.format), static_cast<int>(format), static_cast<int>(mode), CACAO_MEM_HOST, nullptr));
+		else if(pixels)
+			check(cacao_img_convert(-1, src.data.data(), out.data.data(), pixels, static_cast<int>(src.layout), static_cast<int>(layout), static_cast<int>(src.format), static_cast<int>(format), static_cast<int>(mode), CACAO_MEM_HOST, nullptr));
 		return out;
 	}
 
@@ -183,7 +190,11 @@ namespace libcacaoimage {
 	}
 
 	Image ToRGB8(const Image& src) {
-		if(src.bitsPerChannel == 8 && src.layout == Image::Layout::RGB) return src;
+		return ToRGB8(src, false);
+	}
+
+	Image ToRGB8(const Image& src, bool flipRows) {
+		if(src.bitsPerChannel == 8 && src.layout == Image::Layout::RGB) return flipRows ? Flip(src) : src;
 		Image out = {};
 		out.w = src.w;
 		out.h = src.h;
@@ -195,7 +206,10 @@ namespace libcacaoimage {
 		const uint64_t pixels = static_cast<uint64_t>(src.w) * src.h;
 		if(src.data.size() < pixels * static_cast<int>(src.layout) * (src.bitsPerChannel / 8)) throw std::runtime_error("Image data buffer is smaller than w * h * channels * bytes per channel!");
 		out.data.resize(pixels * 3);
-		if(pixels) check(cacao_img_convert(-1, src.data.data(), out.data.data(), pixels, static_cast<int>(src.layout), 3, fmt_of_bits(src.bitsPerChannel), CACAO_FMT_U8, CACAO_MODE_REF_EXACT, CACAO_MEM_HOST, nullptr));
+		if(pixels && flipRows && src.h > 1)
+			check(cacao_img_convert_flip(-1, src.data.data(), out.data.data(), src.w, src.h, 1, static_cast<int>(src.layout), 3, fmt_of_bits(src.bitsPerChannel), CACAO_FMT_U8, CACAO_MODE_REF_EXACT, CACAO_MEM_HOST, nullptr));
+		else if(pixels)
+			check(cacao_img_convert(-1, src.data.data(), out.data.data(), pixels, static_cast<int>(src.layout), 3, fmt_of_bits(src.bitsPerChannel), CACAO_FMT_U8, CACAO_MODE_REF_EXACT, CACAO_MEM_HOST, nullptr));
 		return out;
 	}
 
@@ -402,17 +416,20 @@ namespace libcacaoimage {
 		return out;
 	}
 
-	DeviceImage DeviceImage::Convert(Image::Layout layout, SampleFormat format, ConvertMode mode) const {
+	DeviceImage DeviceImage::Convert(Image::Layout layout, SampleFormat format, ConvertMode mode, bool flipRows) const {
 		if(Empty()) check(CACAO_E_EMPTY);
 		if(layout == layout_ && format == format_) check(CACAO_E_SAME_LAYOUT);
 		DeviceImage out(w_, h_, layout, format, device_);
-		check(cacao_img_convert(device_, ptr_, out.ptr_, static_cast<uint64_t>(w_) * h_, static_cast<int>(layout_), static_cast<int>(layout), static_cast<int>(format_), static_cast<int>(format), static_cast<int>(mode), CACAO_MEM_DEVICE, nullptr));
+		if(flipRows && h_ > 1)
+			check(cacao_img_convert_flip(device_, ptr_, out.ptr_, w_, h_, 1, static_cast<int>(layout_), static_cast<int>(layout), static_cast<int>(format_), static_cast<int>(format), static_cast<int>(mode), CACAO_MEM_DEVICE, nullptr));
+		else
+			check(cacao_img_convert(device_, ptr_, out.ptr_, static_cast<uint64_t>(w_) * h_, static_cast<int>(layout_), static_cast<int>(layout), static_cast<int>(format_), static_cast<int>(format), static_cast<int>(mode), CACAO_MEM_DEVICE, nullptr));
 		return out;
 	}
 
-	DeviceImage DeviceImage::ToRGB8() const {
-		if(layout_ == Image::Layout::RGB && format_ == SampleFormat::U8) return *this;
-		return Convert(Image::Layout::RGB, SampleFormat::U8);
+	DeviceImage DeviceImage::ToRGB8(bool flipRows) const {
+		if(layout_ == Image::Layout::RGB && format_ == SampleFormat::U8) return flipRows ? Flip() : *this;
+		return Convert(Image::Layout::RGB, SampleFormat::U8, ConvertMode::ReferenceExact, flipRows);
 	}
 
 	DeviceImage DeviceImage::Flip() const {

@@ -92,6 +92,11 @@ def flip_rows(src: int, dst: int, w: int, h: int, bytes_per_pixel: int, mem: int
 	capi.check(capi.lib().cacao_img_flip_rows(device, src, dst, w, h, bytes_per_pixel, mem, stream))
 
 
+def convert_flip(src: int, dst: int, w: int, h: int, count: int, src_ch: int, dst_ch: int, src_fmt: int, dst_fmt: int, mode: int = capi.MODE_REF_EXACT, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> None:
+	"""cacao_img_convert_flip: `count` images of w x h pixels converted and written bottom row first in one pass."""
+	capi.check(capi.lib().cacao_img_convert_flip(device, src, dst, w, h, count, src_ch, dst_ch, src_fmt, dst_fmt, mode, mem, stream))
+
+
 def equirect_to_cube(src: int, W: int, H: int, ch: int, fmt: int, dst: int, N: int, face_mask: int = 0x3F, row_begin: int = 0, row_end: int | None = None, src_row0: int = 0, src_rows: int | None = None, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> None:
 	capi.check(capi.lib().cacao_img_equirect_to_cube(device, src, W, H, src_row0, H if src_rows is None else src_rows, ch, fmt, dst, N, face_mask, row_begin, N if row_end is None else row_end, mem, stream))
 

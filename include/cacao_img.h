@@ -105,6 +105,16 @@ int cacao_img_convert(int device, const void* src, void* dst, uint64_t pixels, i
 int cacao_img_convert_batch(int device, const void* src, void* dst, uint64_t pixels_per_image, uint64_t count,
 							int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, int mem, void* stream);
 
+/* The same conversion with the row mirror of cacao_img_flip_rows folded into the store addressing:
+ * `count` images of w x h pixels stored back to back, each written bottom row first -- e.g. the
+ * engine's load-time chain 16 -> 8 bit, -> RGB (engine/src/core/Cubemap.cpp:28-31) and the GL
+ * backend's Flip before upload (engine/src/opengl/impls/OpenGLCubemap.cpp:25, OpenGLTex2D.cpp:16) as ONE
+ * pass instead of three.  Widths that a vector kernel's unit divides (8 ... 64 pixels for the sector
+ * kernel's shapes, 32 x 1 ... 16 pixels for the tile kernel) run at streaming speed; other widths take
+ * the byte-wise kernel.  Same status codes as cacao_img_convert. */
+int cacao_img_convert_flip(int device, const void* src, void* dst, uint32_t w, uint32_t h, uint64_t count,
+						   int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, int mem, void* stream);
+
 /*
  * dst[k] = (uint16_t)(src[k] << shift) over `samples` 16-bit samples, shift in [0,15].
  *   replaces the 12 -> 16 bit widening loop of the JPEG decoder, libs/image/src/JPEG.cpp:79-82

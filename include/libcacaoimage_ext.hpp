@@ -33,6 +33,9 @@ namespace libcacaoimage {
 
 	// Fused layout + format conversion in one pass over the pixels (one upload, one kernel, one readback).
 	ImageEx Convert(const ImageEx& src, Image::Layout layout, SampleFormat format, ConvertMode mode = ConvertMode::ReferenceExact);
+	// flipRows: the result comes out bottom row first -- Convert and Flip (the GL backend's step before
+	// upload, engine/src/opengl/impls/OpenGLTex2D.cpp:16) as one pass over the pixels.
+	ImageEx Convert(const ImageEx& src, Image::Layout layout, SampleFormat format, ConvertMode mode, bool flipRows);
 
 	// The same conversion for a batch of images, sharded by contiguous image-index range over `devices`
 	// (CUDA ordinals; empty = current device), one host thread per device, no cross-device traffic.
@@ -42,6 +45,8 @@ namespace libcacaoimage {
 	// What engine/src/core/Cubemap.cpp:28-31 does per face in two passes and two allocations
 	// (Convert16To8BitColor, then ChangeChannelLayout to RGB), as one kernel.
 	Image ToRGB8(const Image& src);
+	// ... and OpenGLCubemap.cpp:25's Flip in the same kernel: three reference passes, one here
+	Image ToRGB8(const Image& src, bool flipRows);
 
 	// Equirectangular panorama -> six N x N faces in the order +X,-X,+Y,-Y,+Z,-Z
 	// (right,left,up,down,front,back), same layout and sample format as the source.
@@ -92,8 +97,8 @@ namespace libcacaoimage {
 		static DeviceImage Upload(const Image& src, int device = -1);
 		ImageEx Download() const;
 
-		DeviceImage Convert(Image::Layout layout, SampleFormat format, ConvertMode mode = ConvertMode::ReferenceExact) const;
-		DeviceImage ToRGB8() const; // U16 -> U8 through the engine's table, then -> RGB, one kernel
+		DeviceImage Convert(Image::Layout layout, SampleFormat format, ConvertMode mode = ConvertMode::ReferenceExact, bool flipRows = false) const;
+		DeviceImage ToRGB8(bool flipRows = false) const; // U16 -> U8 through the engine's table, then -> RGB (and the row mirror), one kernel
 		DeviceImage Flip() const;
 		DeviceImage Downsample2x() const; // the next mip level
 		// six faces that are views of ONE contiguous face-major allocation (+X,-X,+Y,-Y,+Z,-Z) -- the

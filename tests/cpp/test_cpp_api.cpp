@@ -195,6 +195,24 @@ int main(int argc, char** argv) {
 		DeviceImage copy = dfaces[3]; // shares the allocation; the cube outlives the array it came from
 		EXPECT(copy.Data() == dfaces[3].Data() && copy.Download().data == one[3].data);
 	}
+	// ---- conversion with the row mirror folded in: the engine's three load-time passes as one
+	{
+		Image deep16;
+		deep16.w = 96;
+		deep16.h = 40;
+		deep16.layout = L::RGBA;
+		deep16.bitsPerChannel = 16;
+		deep16.format = Image::Format::PNG;
+		deep16.quality = 100;
+		deep16.lossy = false;
+		deep16.data.resize(96 * 40 * 8);
+		for(std::size_t b = 0; b < deep16.data.size(); ++b) deep16.data[b] = static_cast<unsigned char>((b * 2246822519u) >> 11);
+		const Image three = Flip(ChangeChannelLayout(Convert16To8BitColor(deep16), L::RGB)); // what the reference runs
+		EXPECT(ToRGB8(deep16, true).data == three.data);
+		EXPECT(DeviceImage::Upload(deep16).ToRGB8(true).Download().data == three.data);
+		const ImageEx ex = FromImage(deep16);
+		EXPECT(Convert(ex, L::RGBA, SampleFormat::F16, ConvertMode::ReferenceExact, true).data == Flip(Convert(ex, L::RGBA, SampleFormat::F16)).data);
+	}
 	// ---- resampling and conversion in one pass (Spec B.4): an RGB32F panorama straight to RGBA16F faces
 	// equals project-then-Convert; pairs without a fused form (integer sources) run the two passes inside
 	{

@@ -208,6 +208,59 @@ def test_flip_rows(oracle, w, h, bpp):
 	assert (oracle.flip_rows(out2, w, h, bpp) == src).all()
 
 
+@pytest.mark.parametrize("sf,df,sc,dc", SHAPES, ids=[f"{NAME[a]}x{c}-{NAME[b]}x{d}" for a, b, c, d in SHAPES])
+def test_convert_flip_every_shape(oracle, sf, df, sc, dc):
+	"""cacao_img_convert_flip == convert, then mirror the rows of every image: widths the sector kernel's
+	run divides (64, 96), widths only the tile kernel could take or nothing divides (1024 / 100 -> tile or
+	byte-wise kernel), batches of images, one-row images, device and host memory."""
+	from cacaoengine_b200 import _capi as c, device
+
+	rng = np.random.default_rng(hash((sf, df, sc, dc, 7)) & 0xFFFF)
+	for w, h, count, mode in ((64, 5, 3, 0), (96, 4, 1, 1), (100, 7, 2, 0), (1024, 3, 2, 0), (33, 1, 2, 0)):
+		src = random_samples(rng, w * h * count * sc, sf)
+		plain = oracle.convert(src, sc, dc, sf, df, mode) if not (sc == 1 and dc == 4 and mode == 0 and sf in (0, 1)) else np.concatenate([oracle.convert(src[k * w * h * sc:(k + 1) * w * h * sc], sc, dc, sf, df, mode) for k in range(count)])
+		want = plain.reshape(count, h, w * dc)[:, ::-1, :].copy().reshape(-1)
+		a, b = DevBuf(src.nbytes), DevBuf(want.nbytes)
+		device.upload(a.ptr, src)
+		device.convert_flip(a.ptr, b.ptr, w, h, count, sc, dc, sf, df, mode)
+		got = np.empty_like(want)
+		device.download(got, b.ptr)
+		a.free(), b.free()
+		assert same_bits(got, want), (w, h, count, mode, "device")
+		if w in (64, 1024):
+			got_h = np.empty_like(want)
+			device.convert_flip(src.ctypes.data, got_h.ctypes.data, w, h, count, sc, dc, sf, df, mode, mem=c.MEM_HOST)
+			assert same_bits(got_h, want), (w, h, count, mode, "host")
+
+
+def test_convert_flip_engine_chain_full_size(oracle):
+	"""The engine's three load-time passes -- 16 -> 8 bit, -> RGB (Cubemap.cpp:28-31), Flip (OpenGLCubemap.cpp:25)
+	-- as one kernel on six 2048^2 RGBA16 faces: equals ToRGB8 followed by flip_rows (checksum), and a
+	sampled face equals the oracle's composition."""
+	from cacaoengine_b200 import _capi as c, device
+
+	w = h = 2048
+	px = w * h * 6
+	a, mid, two, one = DevBuf(px * 8), DevBuf(px * 3), DevBuf(px * 3), DevBuf(px * 3)
+	device.synth(a.ptr, px * 4, c.FMT_U16, 4, 0xC0FFEE + 9)
+	before = device.launch_count()
+	device.convert_flip(a.ptr, one.ptr, w, h, 6, 4, 3, c.FMT_U16, c.FMT_U8)
+	assert device.launch_count() - before == 1
+	device.convert_batch(a.ptr, mid.ptr, w * h, 6, 4, 3, c.FMT_U16, c.FMT_U8)
+	for f in range(6):
+		device.flip_rows(mid.ptr + f * w * h * 3, two.ptr + f * w * h * 3, w, h, 3)
+	assert device.checksum(one.ptr, px * 3) == device.checksum(two.ptr, px * 3)
+	rows = 64
+	head = np.empty(rows * w * 4, np.uint16)
+	device.download(head, a.ptr + 2 * w * h * 8)  # first rows of face 2 ...
+	got = np.empty(rows * w * 3, np.uint8)
+	device.download(got, one.ptr + 2 * w * h * 3 + (h - rows) * w * 3)  # ... are its last rows, mirrored
+	want = oracle.convert(head, 4, 3, oracle.U16, oracle.U8).reshape(rows, w * 3)[::-1].reshape(-1)
+	assert same_bits(got, want)
+	for buf in (a, mid, two, one):
+		buf.free()
+
+
 def test_jpeg_12_to_16_bit_widening():
 	"""libs/image/src/JPEG.cpp:79-82: `uint16_t(twelveBit[i]) << 4` over int16 samples -- restated in
 	numpy (the reference loop needs libjpeg-turbo to build, so this row is parity-unpinned)."""
