@@ -383,7 +383,33 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 					"two_pass": {"value": 6 * N * N / ms2 / 1e6, "ms_per_step": ms2, "note": "cacao_img_equirect_to_cube then cacao_img_convert on the device"}, "equals_two_pass": bool(same), "note": note}
 		del src, mid, dst2, dst
 
+	def engine_chain(key, w, h, count, steps):
+		"""The engine's load-time chain on a cubemap's faces -- 16 -> 8 bit, -> RGB (Cubemap.cpp:28-31), Flip
+		(OpenGLCubemap.cpp:25) -- as ONE kernel (cacao_img_convert_flip) against convert + flip_rows."""
+		from cacaoengine_b200 import FMT_U16
+
+		px = w * h * count
+		src, mid, dst2, dst = alloc(px * 8), alloc(px * 3), alloc(px * 3), alloc(px * 3)
+		device.synth(src.data_ptr(), px * 4, FMT_U16, 4, 0xC0FFEE + 9, device=dev, stream=stream)
+
+		def fused():
+			device.convert_flip(src.data_ptr(), dst.data_ptr(), w, h, count, 4, 3, FMT_U16, FMT_U8, device=dev, stream=stream)
+
+		def two_pass():
+			device.convert_batch(src.data_ptr(), mid.data_ptr(), w * h, count, 4, 3, FMT_U16, FMT_U8, device=dev, stream=stream)
+			for f in range(count):
+				device.flip_rows(mid.data_ptr() + f * w * h * 3, dst2.data_ptr() + f * w * h * 3, w, h, 3, device=dev, stream=stream)
+
+		ms2 = timed_region(torch, dist, 1, two_pass, steps, 3)
+		ms = timed_region(torch, dist, 1, fused, steps, 3)
+		same = device.checksum(dst.data_ptr(), px * 3, device=dev, stream=stream) == device.checksum(dst2.data_ptr(), px * 3, device=dev, stream=stream)
+		out[key] = {"value": px / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "n_gpus": 1, "roofline": roof(px * 11, ms, peak, None),
+					"two_pass": {"value": px / ms2 / 1e6, "ms_per_step": ms2, "note": "cacao_img_convert_batch then cacao_img_flip_rows per face"}, "equals_two_pass": bool(same),
+					"note": "uniform-random samples: the 16->8 table gather is at its worst (bank conflicts); 100 MB problem, partly L2-resident"}
+		del src, mid, dst2, dst
+
 	if world == 1:
+		engine_chain("engine_cube_6x2048sq_rgba16_to_rgb8_flipped", 2048, 2048, 6, 50)
 		equirect("cfg3_fused_rgba32f_to_rgba16f_cube", 8192, 4096, 2048, 4, FMT_F32, 4, 20, "config 3 with the cube written as RGBA16F in the same pass (Spec B.4): resample + format convert", dst=(4, FMT_F16, 2))
 		equirect("cfg1_equirect_2048x1024_rgba8_to_6x512", 2048, 1024, 512, 4, FMT_U8, 1, 50, "14.7 MB problem: fits L2, launch-latency bound")
 		equirect("cfg3_equirect_8192x4096_rgba32f_to_6x2048", 8192, 4096, 2048, 4, FMT_F32, 4, 20, e2e=True)
