@@ -558,7 +558,10 @@ namespace {
 
 	// Host-memory conversion: chunks flow upload -> kernel -> readback over three streams, so PCIe
 	// moves in both directions while the SMs convert the chunk in between.
-	int convert_host_pipeline(DeviceCtx* c, const uint8_t* src, uint8_t* dst, uint64_t pixels, uint64_t ppi, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode) {
+	// flip_w x flip_h != 0 (cacao_img_convert_flip): the images are flip_w x flip_h pixels and come out bottom
+	// row first.  Chunks then are bands of whole rows of one image; a band is converted with its own rows
+	// mirrored and lands at the mirrored band of its image, so the pipeline is the same.
+	int convert_host_pipeline(DeviceCtx* c, const uint8_t* src, uint8_t* dst, uint64_t pixels, uint64_t ppi, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, uint32_t flip_w = 0, uint32_t flip_h = 0) {
 		const uint64_t sbpp = static_cast<uint64_t>(src_ch) * fmt_bytes(src_fmt);
 		const uint64_t dbpp = static_cast<uint64_t>(dst_ch) * fmt_bytes(dst_fmt);
 		const bool quirk = (src_fmt == CACAO_FMT_U8 || src_fmt == CACAO_FMT_U16) && src_ch == 1 && dst_ch == 4 && mode == CACAO_MODE_REF_EXACT;
@@ -571,7 +574,27 @@ namespace {
 		if(sixth < chunk_px) chunk_px = sixth < 131072 ? 131072 : sixth;
 		chunk_px = ((chunk_px + 8191) / 8192) * 8192;
 		if(quirk || chunk_px > pixels) chunk_px = pixels; // the pixel-0 quirk needs each image whole
-		HostTrace trace("convert");
+		// chunk k: pixels [src_off, src_off + n) of the source stream go to [dst_off, dst_off + n) of the
+		// result; rows != 0: the chunk is `rows` whole rows that the kernel mirrors among themselves
+		struct Chunk {
+			uint64_t src_off, n, dst_off;
+			uint32_t rows;
+		};
+		const bool flipped = flip_w != 0 && flip_h > 1;
+		const bool banded = flipped && chunk_px < pixels; // else one chunk holds every image whole
+		const uint64_t band_rows = banded ? std::max<uint64_t>(1, std::min<uint64_t>(flip_h, chunk_px / flip_w)) : 0;
+		const uint64_t bands = banded ? (flip_h + band_rows - 1) / band_rows : 0;
+		if(banded) chunk_px = band_rows * flip_w;
+		const uint64_t chunks = banded ? (pixels / ppi) * bands : (pixels + chunk_px - 1) / chunk_px;
+		auto chunk_at = [&](uint64_t k) -> Chunk {
+			if(!banded) {
+				const uint64_t off = k * chunk_px;
+				return {off, (pixels - off < chunk_px) ? pixels - off : chunk_px, off, flipped ? flip_h : 0u};
+			}
+			const uint64_t img = k / bands, y0 = (k % bands) * band_rows, y1 = std::min<uint64_t>(flip_h, y0 + band_rows);
+			return {img * ppi + y0 * flip_w, (y1 - y0) * flip_w, img * ppi + (flip_h - y1) * flip_w, static_cast<uint32_t>(y1 - y0)};
+		};
+		HostTrace trace(flipped ? "convert_flip" : "convert");
 		trace.in_bytes = pixels * sbpp;
 		trace.out_bytes = pixels * dbpp;
 		std::lock_guard<std::mutex> lock(c->pipe_mutex);
@@ -584,7 +607,7 @@ namespace {
 			int rc0 = ensure_pinned(c, std::max<uint64_t>(pixels * sbpp, 64u << 10), std::max<uint64_t>(pixels * dbpp, 64u << 10));
 			if(rc0) return rc0;
 			std::memcpy(c->pin_in[0], src, pixels * sbpp);
-			rc0 = enqueue_convert(c, c->pin_in[0], c->pin_out[0], pixels, ppi, src_ch, dst_ch, src_fmt, dst_fmt, mode, c->s_run);
+			rc0 = enqueue_convert(c, c->pin_in[0], c->pin_out[0], pixels, ppi, src_ch, dst_ch, src_fmt, dst_fmt, mode, c->s_run, flipped ? flip_w : 0, flipped ? flip_h : 0);
 			if(rc0) return rc0;
 			CU_TRY(cudaStreamSynchronize(c->s_run));
 			std::memcpy(dst, c->pin_out[0], pixels * dbpp);
@@ -599,19 +622,18 @@ namespace {
 			rc = ensure_pinned(c, src_pg ? chunk_px * sbpp : 0, dst_pg ? chunk_px * dbpp : 0);
 			if(rc) return rc;
 		}
-		const uint64_t chunks = (pixels + chunk_px - 1) / chunk_px;
 		// a single chunk has nothing to overlap with: keep its three steps on one stream and save the
 		// cross-stream event hops (tens of microseconds matter for a 64x64 texture)
 		cudaStream_t q_in = chunks == 1 ? c->s_run : c->s_in, q_out = chunks == 1 ? c->s_run : c->s_out;
 		for(uint64_t k = 0; k < chunks + (kSlots - 1); ++k) {
 			if(k < chunks) {
 				const int s = static_cast<int>(k % kSlots);
-				const uint64_t off = k * chunk_px;
-				const uint64_t n = (pixels - off < chunk_px) ? pixels - off : chunk_px;
-				const uint8_t* up_from = src + off * sbpp;
+				const Chunk ck = chunk_at(k);
+				const uint64_t n = ck.n;
+				const uint8_t* up_from = src + ck.src_off * sbpp;
 				if(src_pg) {
 					if(k >= kSlots) CU_TRY(cudaEventSynchronize(c->ev_in[s])); // the ring slot's last upload has left
-					CopyPool::get().copy(c->pin_in[s], src + off * sbpp, n * sbpp);
+					CopyPool::get().copy(c->pin_in[s], src + ck.src_off * sbpp, n * sbpp);
 					up_from = c->pin_in[s];
 				}
 				// the device slot is free once its previous readback has finished
@@ -620,11 +642,11 @@ namespace {
 				CU_TRY(cudaEventRecord(c->ev_in[s], q_in));
 				if(chunks > 1) CU_TRY(cudaStreamWaitEvent(c->s_run, c->ev_in[s], 0));
 				if(k >= kSlots) CU_TRY(cudaStreamWaitEvent(c->s_run, c->ev_out[s], 0));
-				rc = enqueue_convert(c, c->stage_in[s], c->stage_out[s], n, quirk ? ppi : n, src_ch, dst_ch, src_fmt, dst_fmt, mode, c->s_run);
+				rc = enqueue_convert(c, c->stage_in[s], c->stage_out[s], n, quirk ? ppi : n, src_ch, dst_ch, src_fmt, dst_fmt, mode, c->s_run, ck.rows ? flip_w : 0, ck.rows);
 				if(rc) return rc;
 				CU_TRY(cudaEventRecord(c->ev_run[s], c->s_run));
 				if(chunks > 1) CU_TRY(cudaStreamWaitEvent(c->s_out, c->ev_run[s], 0));
-				CU_TRY(cudaMemcpyAsync(dst_pg ? c->pin_out[s] : dst + off * dbpp, c->stage_out[s], n * dbpp, cudaMemcpyDeviceToHost, q_out));
+				CU_TRY(cudaMemcpyAsync(dst_pg ? c->pin_out[s] : dst + ck.dst_off * dbpp, c->stage_out[s], n * dbpp, cudaMemcpyDeviceToHost, q_out));
 				CU_TRY(cudaEventRecord(c->ev_out[s], q_out));
 			}
 			// drain the chunk issued kSlots-1 iterations ago (its slot is the next one to be reused)
@@ -632,10 +654,9 @@ namespace {
 				const uint64_t j = k - (kSlots - 1);
 				if(j < chunks) {
 					const int s = static_cast<int>(j % kSlots);
-					const uint64_t off = j * chunk_px;
-					const uint64_t n = (pixels - off < chunk_px) ? pixels - off : chunk_px;
+					const Chunk cj = chunk_at(j);
 					CU_TRY(cudaEventSynchronize(c->ev_out[s]));
-					CopyPool::get().copy(dst + off * dbpp, c->pin_out[s], n * dbpp);
+					CopyPool::get().copy(dst + cj.dst_off * dbpp, c->pin_out[s], cj.n * dbpp);
 				}
 			}
 		}
@@ -961,10 +982,8 @@ int cacao_img_convert_flip(int device, const void* src, void* dst, uint32_t w, u
 	const uint64_t ppi = static_cast<uint64_t>(w) * h, pixels = ppi * count;
 	if(pixels == 0) return CACAO_OK;
 	if(mem == CACAO_MEM_DEVICE) return enqueue_convert(c, src, dst, pixels, ppi, src_ch, dst_ch, src_fmt, dst_fmt, mode, static_cast<cudaStream_t>(stream), w, h);
-	// host memory: one upload, the fused kernel, one readback (the chunked pipeline of the unflipped call
-	// cuts the stream at arbitrary pixels; here a row's destination depends on its image)
-	const uint64_t in_bytes = pixels * src_ch * fmt_bytes(src_fmt), out_bytes = pixels * dst_ch * fmt_bytes(dst_fmt);
-	return run_host_op(c, "convert_flip", src, in_bytes, dst, out_bytes, [&](uint8_t* s, uint8_t* d, cudaStream_t q) -> int { return enqueue_convert(c, s, d, pixels, ppi, src_ch, dst_ch, src_fmt, dst_fmt, mode, q, w, h); });
+	// host memory: the same chunked upload / kernel / readback pipeline, cut into bands of whole rows
+	return convert_host_pipeline(c, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), pixels, ppi, src_ch, dst_ch, src_fmt, dst_fmt, mode, w, h);
 }
 
 int cacao_img_convert(int device, const void* src, void* dst, uint64_t pixels, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, int mem, void* stream) {

@@ -233,6 +233,29 @@ def test_convert_flip_every_shape(oracle, sf, df, sc, dc):
 			assert same_bits(got_h, want), (w, h, count, mode, "host")
 
 
+@pytest.mark.parametrize("w,h,count", [(2048, 1500, 1), (1000, 777, 3), (96, 4000, 2)])
+def test_convert_flip_host_pipeline_in_row_bands(oracle, w, h, count):
+	"""Host-memory cacao_img_convert_flip on images large enough for the chunked pipeline: chunks are bands
+	of whole rows, each mirrored in itself and stored at the mirrored band.  Pageable (numpy) and
+	pinned buffers; RGBA16 -> RGB8 (table shape) and RGB8 -> RGBA32F."""
+	from cacaoengine_b200 import _capi as c, device
+
+	rng = np.random.default_rng(w + h)
+	for sc, dc, sf, df in ((4, 3, 1, 0), (3, 4, 0, 3)):
+		src = random_samples(rng, w * h * count * sc, sf)
+		want = oracle.convert(src, sc, dc, sf, df).reshape(count, h, w * dc)[:, ::-1, :].copy().reshape(-1)
+		got = np.empty_like(want)
+		device.convert_flip(src.ctypes.data, got.ctypes.data, w, h, count, sc, dc, sf, df, mem=c.MEM_HOST)
+		assert same_bits(got, want), ("pageable", sc, dc)
+		sp, s_host = device.host_alloc(src.nbytes)
+		dp, d_host = device.host_alloc(want.nbytes)
+		s_host[:] = src.view(np.uint8)
+		d_host[:] = 0
+		device.convert_flip(sp, dp, w, h, count, sc, dc, sf, df, mem=c.MEM_HOST)
+		assert same_bits(d_host.view(want.dtype), want), ("pinned", sc, dc)
+		device.host_free(sp), device.host_free(dp)
+
+
 def test_convert_flip_engine_chain_full_size(oracle):
 	"""The engine's three load-time passes -- 16 -> 8 bit, -> RGB (Cubemap.cpp:28-31), Flip (OpenGLCubemap.cpp:25)
 	-- as one kernel on six 2048^2 RGBA16 faces: equals ToRGB8 followed by flip_rows (checksum), and a
