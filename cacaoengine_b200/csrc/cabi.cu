@@ -1178,7 +1178,7 @@ namespace {
 		if(!ch_ok(ch) || !fmt_ok(fmt)) return fail(CACAO_E_BAD_ARG, "equirect: bad channel count %d or format %d", ch, fmt);
 		if(!ch_ok(dst_ch) || !fmt_ok(dst_fmt)) return fail(CACAO_E_BAD_ARG, "equirect: bad destination channel count %d or format %d", dst_ch, dst_fmt);
 		if(!equirect_cvt_supported(ch, fmt, dst_ch, dst_fmt))
-			return fail(CACAO_E_BAD_ARG, "equirect: fused conversion %d ch fmt %d -> %d ch fmt %d is not defined (float sources only; same channels or RGB -> RGBA): resample, then cacao_img_convert", ch, fmt, dst_ch, dst_fmt);
+			return fail(CACAO_E_BAD_ARG, "equirect: fused conversion %d ch fmt %d -> %d ch fmt %d is not defined (float sources only; same channels or RGB <-> RGBA): resample, then cacao_img_convert", ch, fmt, dst_ch, dst_fmt);
 		if(W == 0 || H == 0 || N == 0) return fail(CACAO_E_ZERO_DIM, "equirect: zero-sized image or face");
 		if(W > (1u << 24) || H > (1u << 24) || N > (1u << 23)) return fail(CACAO_E_BAD_ARG, "equirect: dimensions beyond exact float range");
 		if(src_rows == 0 || src_row0 + static_cast<uint64_t>(src_rows) > H) return fail(CACAO_E_BAD_ARG, "equirect: source window [%u,+%u) outside the image (H=%u)", src_row0, src_rows, H);

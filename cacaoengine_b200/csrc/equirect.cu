@@ -269,8 +269,9 @@ namespace cacao {
 		// Bilinear fetch + store of one output pixel whose source rows are already known.
 		// IDX is uint32_t when the source window has < 2^32 pixels (cheaper address arithmetic).
 		// DF / DC = F / CH: the filtered texel is stored in the source's format (Spec B.2).  Anything
-		// else (float sources only): the fp32 result goes through Spec B.1's float -> DF conversion and,
-		// for RGB -> RGBA, gains alpha 1 on its way out -- resampling and conversion in one pass (Spec B.4).
+		// else (float sources only): the fp32 result goes through Spec B.1's float -> DF conversion and gains
+		// alpha 1 (RGB -> RGBA) or loses its alpha (RGBA -> RGB) on its way out -- resampling and conversion
+		// in one pass (Spec B.4).
 		template<int F, int CH, typename IDX, int DF = F, int DC = CH>
 		__device__ __forceinline__ void sample_and_store(const uint8_t* __restrict__ src, uint8_t* __restrict__ out_px, float xs, int W, const RowTaps<IDX>& rt, IDX total_px) {
 			constexpr int bpp = FmtTraits<F>::bytes * CH;
@@ -315,7 +316,7 @@ namespace cacao {
 				store_texel<F, CH>(out_px, out);
 			} else {
 				static_assert(!FmtTraits<F>::is_int, "fused format conversion is defined for float sources");
-				static_assert(DC == CH || (CH == 3 && DC == 4), "fused layout change: RGB -> RGBA only");
+				static_assert(DC == CH || (CH == 3 && DC == 4) || (CH == 4 && DC == 3), "fused layout change: RGB <-> RGBA only");
 				float o[DC];
 #pragma unroll
 				for(int c = 0; c < DC; ++c) o[c] = c < CH ? out[c < CH ? c : 0] : 1.0f;
@@ -613,7 +614,7 @@ namespace cacao {
 		}
 
 		// Fused resample + convert (Spec B.4): float sources, any destination format, same channels or
-		// RGB -> RGBA.
+		// RGB <-> RGBA.
 		template<int F, int CH, int DC>
 		cudaError_t launch_cvt_fmt(const void* src, void* dst, int dst_fmt, const EquirectParams& prm, cudaStream_t stream) {
 			switch(dst_fmt) {
@@ -630,6 +631,7 @@ namespace cacao {
 			if(ch == 3 && dst_ch == 3) return launch_cvt_fmt<F, 3, 3>(src, dst, dst_fmt, prm, stream);
 			if(ch == 3 && dst_ch == 4) return launch_cvt_fmt<F, 3, 4>(src, dst, dst_fmt, prm, stream);
 			if(ch == 4 && dst_ch == 4) return launch_cvt_fmt<F, 4, 4>(src, dst, dst_fmt, prm, stream);
+			if(ch == 4 && dst_ch == 3) return launch_cvt_fmt<F, 4, 3>(src, dst, dst_fmt, prm, stream);
 			return cudaErrorInvalidValue;
 		}
 
@@ -725,7 +727,7 @@ namespace cacao {
 	bool equirect_cvt_supported(int ch, int fmt, int dst_ch, int dst_fmt) {
 		if(dst_ch == ch && dst_fmt == fmt) return true;
 		const bool float_src = fmt == CACAO_FMT_F16 || fmt == CACAO_FMT_F32;
-		return float_src && (dst_ch == ch || (ch == 3 && dst_ch == 4));
+		return float_src && (dst_ch == ch || (ch == 3 && dst_ch == 4) || (ch == 4 && dst_ch == 3));
 	}
 
 	cudaError_t equirect_launch_units(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, const CubeUnit* units, uint32_t n_units, cudaStream_t stream, unsigned* launches, int dst_ch, int dst_fmt, uint32_t flags) {

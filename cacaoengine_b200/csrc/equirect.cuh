@@ -33,7 +33,7 @@ namespace cacao {
 	// Enqueue the resampling of a list of (face, row band) units in as few launches as their heights allow
 	// (normally one), *launches gets the count.
 	// dst_ch / dst_fmt other than ch / fmt: resampling and format conversion in one pass (Spec B.4; float
-	// sources, same channels or RGB -> RGBA -- equirect_cvt_supported); <= 0 / < 0 mean "as the source".
+	// sources, same channels or RGB <-> RGBA -- equirect_cvt_supported); <= 0 / < 0 mean "as the source".
 	// flags: CACAO_EQUIRECT_FLIP_ROWS stores every face bottom row first (units still name rows of the
 	// unflipped face: row j lands at N-1-j).
 	cudaError_t equirect_launch_units(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, const CubeUnit* units, uint32_t n_units, cudaStream_t stream, unsigned* launches, int dst_ch = 0, int dst_fmt = -1, uint32_t flags = 0);

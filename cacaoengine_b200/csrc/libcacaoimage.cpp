@@ -225,7 +225,7 @@ namespace libcacaoimage {
 	bool FusedProjectionDefined(Image::Layout srcLayout, SampleFormat srcFormat, Image::Layout layout, SampleFormat format) {
 		if(srcLayout == layout && srcFormat == format) return true;
 		const bool float_src = srcFormat == SampleFormat::F16 || srcFormat == SampleFormat::F32;
-		return float_src && (layout == srcLayout || (srcLayout == Image::Layout::RGB && layout == Image::Layout::RGBA));
+		return float_src && (layout == srcLayout || (srcLayout == Image::Layout::RGB && layout == Image::Layout::RGBA) || (srcLayout == Image::Layout::RGBA && layout == Image::Layout::RGB));
 	}
 
 	std::array<ImageEx, 6> EquirectToCubemap(const ImageEx& src, unsigned int faceSize, const std::vector<int>& devices) {
@@ -234,7 +234,7 @@ namespace libcacaoimage {
 
 	std::array<ImageEx, 6> EquirectToCubemap(const ImageEx& src, unsigned int faceSize, Image::Layout layout, SampleFormat format, const std::vector<int>& devices, bool flipRows) {
 		if(!FusedProjectionDefined(src.layout, src.format, layout, format)) {
-			// no one-pass form (integer source, or a layout change other than RGB -> RGBA): two passes
+			// no one-pass form (integer source, or a layout change other than RGB <-> RGBA): two passes
 			// (the row mirror is folded into the first one: conversion does not care about rows)
 			std::array<ImageEx, 6> faces = EquirectToCubemap(src, faceSize, src.layout, src.format, devices, flipRows);
 			for(auto& f : faces) f = Convert(f, layout, format);

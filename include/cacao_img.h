@@ -203,7 +203,7 @@ int cacao_img_equirect_to_cube_units_host(int device, const void* src, uint32_t 
  * fp32 texel is converted to dst_fmt exactly as cacao_img_convert converts an F32 sample (Spec B.1) and
  * an RGB source may gain an opaque alpha (dst_ch = 4) on its way out -- e.g. an RGB32F .hdr panorama
  * straight to an RGBA16F cube, without the F32 cube ever touching memory.  Defined for FLOAT sources
- * (F16, F32), dst_ch == ch or 3 -> 4; dst_ch == ch && dst_fmt == fmt is the plain resampling of any
+ * (F16, F32), dst_ch == ch, 3 -> 4 or 4 -> 3 (alpha dropped); dst_ch == ch && dst_fmt == fmt is the plain resampling of any
  * format; everything else returns CACAO_E_BAD_ARG (resample, then convert).  dst holds 6 faces of
  * N x N x dst_ch samples of dst_fmt.  units == NULL && n_units == 0: the whole cube.
  * flags: CACAO_EQUIRECT_FLIP_ROWS stores every face bottom row first -- the vertical mirror the GL

@@ -53,7 +53,7 @@ namespace libcacaoimage {
 	// devices: CUDA ordinals to spread face/row-band work units over (empty = current device).
 	std::array<ImageEx, 6> EquirectToCubemap(const ImageEx& src, unsigned int faceSize, const std::vector<int>& devices = {});
 	// The same with the faces delivered in another layout / sample format.  Float panoramas (F16, F32)
-	// going to any sample format, with the same channels or RGB -> RGBA, are resampled AND converted in
+	// going to any sample format, with the same channels or RGB <-> RGBA, are resampled AND converted in
 	// one pass over the pixels (DESIGN.md "Spec B.4": the fp32 filter result is converted as Convert()
 	// converts an F32 sample) -- an RGB32F .hdr panorama becomes an RGBA16F cube without the F32 cube ever
 	// existing.  FusedProjectionDefined() tells; every other pair runs the two passes for you.

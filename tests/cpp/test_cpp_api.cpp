@@ -225,7 +225,7 @@ int main(int argc, char** argv) {
 		float* px = reinterpret_cast<float*>(hdr.data.data());
 		for(std::size_t k = 0; k < 160 * 80 * 3; ++k) px[k] = static_cast<float>((k * 2654435761u) >> 8 & 0xFFFF) / 32768.0f - 0.25f;
 		EXPECT(FusedProjectionDefined(L::RGB, SampleFormat::F32, L::RGBA, SampleFormat::F16));
-		EXPECT(!FusedProjectionDefined(L::RGBA, SampleFormat::U16, L::RGBA, SampleFormat::F16) && !FusedProjectionDefined(L::RGBA, SampleFormat::F32, L::RGB, SampleFormat::F32));
+		EXPECT(!FusedProjectionDefined(L::RGBA, SampleFormat::U16, L::RGBA, SampleFormat::F16) && FusedProjectionDefined(L::RGBA, SampleFormat::F32, L::RGB, SampleFormat::U8) && !FusedProjectionDefined(L::RGBA, SampleFormat::F32, L::Grayscale, SampleFormat::F32));
 		const auto plain = EquirectToCubemap(hdr, 24);
 		const auto fused = EquirectToCubemap(hdr, 24, L::RGBA, SampleFormat::F16);
 		const auto quant = EquirectToCubemap(hdr, 24, L::RGB, SampleFormat::U8);

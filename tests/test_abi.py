@@ -163,7 +163,7 @@ def test_fused_equirect_conversion_rejects_undefined_pairs(built_lib):
 
 	lib = c.lib()
 	call = lambda ch, fmt, dch, dfmt: lib.cacao_img_equirect_to_cube_units_cvt(-1, 16, 8, 4, 0, 4, ch, fmt, 16, 2, dch, dfmt, 0, None, 0, None)
-	for ch, fmt, dch, dfmt in ((4, c.FMT_U8, 4, c.FMT_F16), (4, c.FMT_U16, 4, c.FMT_U8), (4, c.FMT_F32, 3, c.FMT_F32), (1, c.FMT_F32, 4, c.FMT_F16), (4, c.FMT_F32, 1, c.FMT_U8), (3, c.FMT_U8, 4, c.FMT_U8)):
+	for ch, fmt, dch, dfmt in ((4, c.FMT_U8, 4, c.FMT_F16), (4, c.FMT_U16, 4, c.FMT_U8), (3, c.FMT_F32, 1, c.FMT_F32), (1, c.FMT_F32, 4, c.FMT_F16), (4, c.FMT_F32, 1, c.FMT_U8), (3, c.FMT_U8, 4, c.FMT_U8)):
 		assert call(ch, fmt, dch, dfmt) == c.E_BAD_ARG, (ch, fmt, dch, dfmt)
 		assert b"not defined" in lib.cacao_img_last_error()
 	assert call(2, c.FMT_F32, 2, c.FMT_F16) == c.E_BAD_ARG and call(4, c.FMT_F32, 4, 7) == c.E_BAD_ARG

@@ -232,7 +232,7 @@ def test_mirror_folded_unit_lists_match_the_oracle(oracle, fmt, ch, N):
 	a.free(), b.free()
 
 
-FUSED = [(sf, ch, dc, df) for sf in (2, 3) for (ch, dc) in ((1, 1), (3, 3), (3, 4), (4, 4)) for df in (0, 1, 2, 3) if not (dc == ch and df == sf)]
+FUSED = [(sf, ch, dc, df) for sf in (2, 3) for (ch, dc) in ((1, 1), (3, 3), (3, 4), (4, 4), (4, 3)) for df in (0, 1, 2, 3) if not (dc == ch and df == sf)]
 
 
 def _float_pano(rng, W, H, ch, fmt, dst_fmt):
