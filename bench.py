@@ -409,13 +409,14 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 		del src, mid, dst2, dst
 
 	if world == 1:
-		engine_chain("engine_cube_6x2048sq_rgba16_to_rgb8_flipped", 2048, 2048, 6, 50)
-		equirect("cfg3_fused_rgba32f_to_rgba16f_cube", 8192, 4096, 2048, 4, FMT_F32, 4, 20, "config 3 with the cube written as RGBA16F in the same pass (Spec B.4): resample + format convert", dst=(4, FMT_F16, 2))
 		equirect("cfg1_equirect_2048x1024_rgba8_to_6x512", 2048, 1024, 512, 4, FMT_U8, 1, 50, "14.7 MB problem: fits L2, launch-latency bound")
 		equirect("cfg3_equirect_8192x4096_rgba32f_to_6x2048", 8192, 4096, 2048, 4, FMT_F32, 4, 20, e2e=True)
 	# sharded, a step is one ~0.1 ms launch per rank: more of them, so that the Python call ahead of the
 	# first launch does not weigh in the per-step time
 	equirect("cfg5_equirect_16384x8192_rgba32f_to_6x4096", 16384, 8192, 4096, 4, FMT_F32, 4, 10 if world == 1 else 50)
+	if world == 1:  # the fusions, after the BASELINE configs
+		equirect("cfg3_fused_rgba32f_to_rgba16f_cube", 8192, 4096, 2048, 4, FMT_F32, 4, 20, "config 3 with the cube written as RGBA16F in the same pass (Spec B.4): resample + format convert", dst=(4, FMT_F16, 2))
+		engine_chain("engine_cube_6x2048sq_rgba16_to_rgb8_flipped", 2048, 2048, 6, 50)
 
 	# cfg4: 4096 x 4096^2 RGB8 -> RGBA8 / RGBA32F sharded by image index.  206 GB of input and up to
 	# 1.1 TB of output fit nowhere: each rank walks its logical image range over a

@@ -339,18 +339,27 @@ namespace cacao {
 		// one the per-pixel spec computes, bit for bit.
 		// 32 registers (16 blocks/SM) everywhere except the three-channel shapes, whose window realignment
 		// needs 40 (12 blocks/SM measured 7 % ahead of spilling at 32: rgb8 0.165 -> 0.154 ms).
-		template<int F, int CH, typename IDX, bool QUAD, int WX, int DF = F, int DC = CH>
+		// MODE: kPair = two-fold (column mirror); kQuadUnits = four-fold per unit flag, any mix of units,
+		// flipped or converted output; kQuadFaces = every unit a whole face, stored as is -- the case of a
+		// one-GPU cube, kept as its own instantiation so that nothing the other cases need (per-unit row
+		// bounds and flags, the store row map) sits in its 32 registers: the general form measured 1.5 %
+		// behind it on BASELINE configs 3 and 5 (dev/ab_lib_versions.py).
+		constexpr int kPair = 0, kQuadFaces = 1, kQuadUnits = 2;
+		template<int F, int CH, typename IDX, int MODE, int WX, int DF = F, int DC = CH>
 		__global__ void __launch_bounds__(128, CH == 3 ? 12 : 16) equirect_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, EquirectParams prm) {
+			constexpr bool QUAD = MODE != kPair;
+			constexpr bool FACES = MODE == kQuadFaces;
+			static_assert(!FACES || (DF == F && DC == CH), "the whole-face form stores in the source format");
 			constexpr int bpp = FmtTraits<DF>::bytes * DC; // of the output; the taps know the source's
 			constexpr int RY = 32 / WX; // a warp covers WX columns x RY rows, a block WX x 4*RY
 			const CubeUnit unit = prm.units[blockIdx.z];
 			const uint32_t i = blockIdx.x * WX + (threadIdx.x % WX);
 			const uint32_t j = unit.row_begin + (blockIdx.y * 4u + threadIdx.y) * RY + threadIdx.x / WX;
-			const uint32_t face = unit.face & 7u;
+			const uint32_t face = FACES ? unit.face : (unit.face & 7u);
 			const uint32_t half = (prm.N + 1u) >> 1;
 			// a unit flagged kUnitMirror lies in the upper half of the face (row_end <= half, the launcher
 			// sees to that) and stands for its rows AND their mirror rows N-1-j
-			if(i >= half || j >= unit.row_end) return;
+			if(i >= half || j >= (FACES ? half : unit.row_end)) return;
 			const uint32_t im = prm.N - 1u - i;
 
 			const float sc = face_coord(i, prm.pc);
@@ -369,16 +378,22 @@ namespace cacao {
 			const IDX total_px = static_cast<IDX>(prm.src_rows) * static_cast<IDX>(prm.W);
 			const RowTaps<IDX> rt = row_taps<IDX>(fmaf(-theta, prm.pc.ky, prm.pc.cy), prm);
 
-			// flipped output (bottom row first): the pixel is the same, only its row in the face changes
-			const uint32_t jm = prm.N - 1u - j;
-			uint8_t* orow = dst + (static_cast<size_t>(face) * prm.N + (prm.flip ? jm : j)) * prm.N * bpp;
+			// face row j is stored at row row_add + row_mul * j: (0, 1) normally, (N-1, -1) for flipped output
+			// (bottom row first) -- the multiply-add the row address needed anyway, so the mirror is free
+			const uint32_t frow = face * prm.N + (FACES ? 0u : prm.row_add);
+			uint8_t* orow = FACES ? dst + (static_cast<size_t>(face) * prm.N + j) * prm.N * bpp : dst + static_cast<size_t>(frow + j * prm.row_mul) * prm.N * bpp;
 			const float xs_a = fmaf(atan2_quadrant(rphi, xa, za), prm.pc.kx, prm.pc.cx);
 			const float xs_b = fmaf(atan2_quadrant(rphi, xb, zb), prm.pc.kx, prm.pc.cx);
 			sample_and_store<F, CH, IDX, DF, DC>(src, orow + static_cast<size_t>(i) * bpp, xs_a, W, rt, total_px);
 			if(im != i) sample_and_store<F, CH, IDX, DF, DC>(src, orow + static_cast<size_t>(im) * bpp, xs_b, W, rt, total_px);
 			if constexpr(QUAD) {
-				if(!(unit.face & kUnitMirror) || jm == j) return; // uniform per block: units are indexed by blockIdx.z
-				uint8_t* mrow = dst + (static_cast<size_t>(face) * prm.N + (prm.flip ? j : jm)) * prm.N * bpp;
+				const uint32_t jm = prm.N - 1u - j;
+				if constexpr(FACES) {
+					if(jm == j) return;
+				} else {
+					if(!(unit.face & kUnitMirror) || jm == j) return; // uniform per block: units are indexed by blockIdx.z
+				}
+				uint8_t* mrow = FACES ? dst + (static_cast<size_t>(face) * prm.N + jm) * prm.N * bpp : dst + static_cast<size_t>(frow + jm * prm.row_mul) * prm.N * bpp;
 				const bool polar = (face & 6u) == 2u; // +-Y: the row mirror negates z, theta stays
 				const RowTaps<IDX> rm = polar ? rt : row_taps<IDX>(fmaf(theta, prm.pc.ky, prm.pc.cy), prm);
 				const float xs_c = polar ? fmaf(atan2_quadrant(rphi, xa, -za), prm.pc.kx, prm.pc.cx) : xs_a;
@@ -569,7 +584,7 @@ namespace cacao {
 			constexpr int bpp = FmtTraits<F>::bytes * CH;
 			if constexpr(!fused && (bpp == 4 || bpp == 8 || bpp == 16)) {
 				const char* e = getenv("CACAO_EQUIRECT_STAGED");
-				const bool staged = e && e[0] == '1' && !prm.flip && (static_cast<uint64_t>(prm.W) * bpp) % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+				const bool staged = e && e[0] == '1' && prm.row_mul == 1u && (static_cast<uint64_t>(prm.W) * bpp) % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
 				if(staged) {
 					equirect_staged_kernel<F, CH><<<grid, block, 0, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), prm);
 					return cudaGetLastError();
@@ -593,22 +608,32 @@ namespace cacao {
 			const dim3 ggrid((half + WX - 1) / WX, (rows + bh - 1) / bh, prm.n_units);
 			const uint8_t* s8 = static_cast<const uint8_t*>(src);
 			uint8_t* d8 = static_cast<uint8_t*>(dst);
+			// every unit the folded upper half of a whole face, stored unflipped: the dedicated form
+			bool faces = quad && prm.row_mul == 1u;
+			for(uint32_t u = 0; u < prm.n_units; ++u) faces = faces && (prm.units[u].face & kUnitMirror) && prm.units[u].row_begin == 0 && prm.units[u].row_end == half;
 			if constexpr(fused) {
 				// one instantiation per index width: the four-fold kernel serves unflagged units two-fold
 				if(small)
-					equirect_kernel<F, CH, uint32_t, true, WX, DF, DC><<<ggrid, block, 0, stream>>>(s8, d8, prm);
+					equirect_kernel<F, CH, uint32_t, kQuadUnits, WX, DF, DC><<<ggrid, block, 0, stream>>>(s8, d8, prm);
 				else
-					equirect_kernel<F, CH, uint64_t, true, WX, DF, DC><<<ggrid, block, 0, stream>>>(s8, d8, prm);
+					equirect_kernel<F, CH, uint64_t, kQuadUnits, WX, DF, DC><<<ggrid, block, 0, stream>>>(s8, d8, prm);
+			} else if(faces) {
+				EquirectParams whole = prm; // plain face numbers, as that form reads them
+				for(uint32_t u = 0; u < whole.n_units; ++u) whole.units[u].face &= 7u;
+				if(small)
+					equirect_kernel<F, CH, uint32_t, kQuadFaces, WX><<<ggrid, block, 0, stream>>>(s8, d8, whole);
+				else
+					equirect_kernel<F, CH, uint64_t, kQuadFaces, WX><<<ggrid, block, 0, stream>>>(s8, d8, whole);
 			} else if(small) {
 				if(quad)
-					equirect_kernel<F, CH, uint32_t, true, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
+					equirect_kernel<F, CH, uint32_t, kQuadUnits, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
 				else
-					equirect_kernel<F, CH, uint32_t, false, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
+					equirect_kernel<F, CH, uint32_t, kPair, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
 			} else {
 				if(quad)
-					equirect_kernel<F, CH, uint64_t, true, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
+					equirect_kernel<F, CH, uint64_t, kQuadUnits, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
 				else
-					equirect_kernel<F, CH, uint64_t, false, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
+					equirect_kernel<F, CH, uint64_t, kPair, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
 			}
 			return cudaGetLastError();
 		}
@@ -742,7 +767,9 @@ namespace cacao {
 		prm.N = N;
 		prm.src_row0 = src_row0;
 		prm.src_rows = src_rows;
-		prm.flip = (flags & CACAO_EQUIRECT_FLIP_ROWS) ? 1u : 0u;
+		const bool flip_rows = (flags & CACAO_EQUIRECT_FLIP_ROWS) != 0;
+		prm.row_add = flip_rows ? N - 1u : 0u;
+		prm.row_mul = flip_rows ? 0xFFFFFFFFu : 1u; // -1 in the kernel's modular row arithmetic
 		prm.pc = make_proj_const(N, W, H);
 		// The grid's y extent is that of the tallest unit in a launch, and blocks beyond a shorter unit's
 		// rows exit at once but are not free (a sharded 16384x8192 job whose +-Y bands are half as tall as
@@ -761,7 +788,7 @@ namespace cacao {
 		// test / A-B switches: two-fold sharing only; the staged experiment knows plain units only
 		const char* qe = getenv("CACAO_EQUIRECT_NO_QUAD");
 		const char* se = getenv("CACAO_EQUIRECT_STAGED");
-		if(!(qe && qe[0] == '1') && (fused || prm.flip || !(se && se[0] == '1'))) todo = pair_mirror_units(todo, N);
+		if(!(qe && qe[0] == '1') && (fused || flip_rows || !(se && se[0] == '1'))) todo = pair_mirror_units(todo, N);
 		uint32_t hmin = 0xFFFFFFFFu, hmax = 0;
 		for(const CubeUnit& u : todo) {
 			hmin = std::min(hmin, u.row_end - u.row_begin);

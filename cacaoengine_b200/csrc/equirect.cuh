@@ -25,9 +25,9 @@ namespace cacao {
 		uint32_t N;                  // face edge in pixels
 		uint32_t src_row0, src_rows; // window of source rows present in `src`
 		uint32_t n_units;            // blockIdx.z selects the unit
-		uint32_t flip;               // != 0: face row j is stored at row N-1-j (bottom row first, the GL convention)
 		CubeUnit units[kMaxUnitsPerLaunch];
 		ProjConst pc;
+		uint32_t row_add, row_mul;   // face row j is stored at row row_add + row_mul * j: (0, 1), or (N-1, -1) = bottom row first
 	};
 
 	// Enqueue the resampling of a list of (face, row band) units in as few launches as their heights allow
