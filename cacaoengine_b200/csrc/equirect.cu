@@ -344,11 +344,14 @@ namespace cacao {
 		// one-GPU cube, kept as its own instantiation so that nothing the other cases need (per-unit row
 		// bounds and flags, the store row map) sits in its 32 registers: the general form measured 1.5 %
 		// behind it on BASELINE configs 3 and 5 (dev/ab_lib_versions.py).
-		constexpr int kPair = 0, kQuadFaces = 1, kQuadUnits = 2;
+		// kQuadUnitsMapped = kQuadUnits with the store row map (flipped output); the fused-conversion
+		// instantiations always carry the map.
+		constexpr int kPair = 0, kQuadFaces = 1, kQuadUnits = 2, kQuadUnitsMapped = 3;
 		template<int F, int CH, typename IDX, int MODE, int WX, int DF = F, int DC = CH>
 		__global__ void __launch_bounds__(128, CH == 3 ? 12 : 16) equirect_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, EquirectParams prm) {
 			constexpr bool QUAD = MODE != kPair;
 			constexpr bool FACES = MODE == kQuadFaces;
+			constexpr bool MAPPED = MODE == kQuadUnitsMapped || DF != F || DC != CH;
 			static_assert(!FACES || (DF == F && DC == CH), "the whole-face form stores in the source format");
 			constexpr int bpp = FmtTraits<DF>::bytes * DC; // of the output; the taps know the source's
 			constexpr int RY = 32 / WX; // a warp covers WX columns x RY rows, a block WX x 4*RY
@@ -380,8 +383,8 @@ namespace cacao {
 
 			// face row j is stored at row row_add + row_mul * j: (0, 1) normally, (N-1, -1) for flipped output
 			// (bottom row first) -- the multiply-add the row address needed anyway, so the mirror is free
-			const uint32_t frow = face * prm.N + (FACES ? 0u : prm.row_add);
-			uint8_t* orow = FACES ? dst + (static_cast<size_t>(face) * prm.N + j) * prm.N * bpp : dst + static_cast<size_t>(frow + j * prm.row_mul) * prm.N * bpp;
+			const uint32_t frow = face * prm.N + (MAPPED ? prm.row_add : 0u);
+			uint8_t* orow = MAPPED ? dst + static_cast<size_t>(frow + j * prm.row_mul) * prm.N * bpp : dst + (static_cast<size_t>(face) * prm.N + j) * prm.N * bpp;
 			const float xs_a = fmaf(atan2_quadrant(rphi, xa, za), prm.pc.kx, prm.pc.cx);
 			const float xs_b = fmaf(atan2_quadrant(rphi, xb, zb), prm.pc.kx, prm.pc.cx);
 			sample_and_store<F, CH, IDX, DF, DC>(src, orow + static_cast<size_t>(i) * bpp, xs_a, W, rt, total_px);
@@ -393,7 +396,7 @@ namespace cacao {
 				} else {
 					if(!(unit.face & kUnitMirror) || jm == j) return; // uniform per block: units are indexed by blockIdx.z
 				}
-				uint8_t* mrow = FACES ? dst + (static_cast<size_t>(face) * prm.N + jm) * prm.N * bpp : dst + static_cast<size_t>(frow + jm * prm.row_mul) * prm.N * bpp;
+				uint8_t* mrow = MAPPED ? dst + static_cast<size_t>(frow + jm * prm.row_mul) * prm.N * bpp : dst + (static_cast<size_t>(face) * prm.N + jm) * prm.N * bpp;
 				const bool polar = (face & 6u) == 2u; // +-Y: the row mirror negates z, theta stays
 				const RowTaps<IDX> rm = polar ? rt : row_taps<IDX>(fmaf(theta, prm.pc.ky, prm.pc.cy), prm);
 				const float xs_c = polar ? fmaf(atan2_quadrant(rphi, xa, -za), prm.pc.kx, prm.pc.cx) : xs_a;
@@ -624,6 +627,11 @@ namespace cacao {
 					equirect_kernel<F, CH, uint32_t, kQuadFaces, WX><<<ggrid, block, 0, stream>>>(s8, d8, whole);
 				else
 					equirect_kernel<F, CH, uint64_t, kQuadFaces, WX><<<ggrid, block, 0, stream>>>(s8, d8, whole);
+			} else if(prm.row_mul != 1u) { // flipped output: the mapped form (it serves unflagged units two-fold)
+				if(small)
+					equirect_kernel<F, CH, uint32_t, kQuadUnitsMapped, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
+				else
+					equirect_kernel<F, CH, uint64_t, kQuadUnitsMapped, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
 			} else if(small) {
 				if(quad)
 					equirect_kernel<F, CH, uint32_t, kQuadUnits, WX><<<ggrid, block, 0, stream>>>(s8, d8, prm);
