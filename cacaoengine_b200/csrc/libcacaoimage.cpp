@@ -359,7 +359,7 @@ namespace libcacaoimage {
 		out.quality = 0;
 		out.lossy = false;
 		const uint64_t n = static_cast<uint64_t>(w) * h;
-		std::vector<unsigned char> tmp(n * 4 ? n * 4 : 4);
+		std::vector<unsigned char> tmp(n ? n * 4 : 4);
 		int ch = 0;
 		const int rc = cacao_img_unpack_texels(-1, n ? texels : tmp.data(), tmp.data(), n, hint.c_str(), &ch, CACAO_MEM_HOST, nullptr);
 		if(rc == CACAO_E_BAD_ARG) throw std::runtime_error(cacao_img_last_error()); // the reference's texts for rejected hints
