@@ -199,3 +199,37 @@ def test_fold_units_keeps_the_cover(built_lib):
 			units.append((f, N - min(b, N), N - a))
 		folded = device.equirect_fold_units(N, units)
 		assert (cover(N, folded, True) == cover(N, [u for u in units if u[1] < min(u[2], N)])).all(), (N, units, folded)
+
+
+def test_units_for_rank_random_sizes(built_lib):
+	"""Any face size and rank count: the ranks' lists tile the cube exactly once, every band sits with its
+	mirror band on the same rank (up to the centre row of an odd face), the launcher folds a rank's list
+	into four-fold units without changing its cover, and the plan is the same on every rank."""
+	from cacaoengine_b200 import device, sharding
+
+	M = device.UNIT_MIRROR
+	rng = np.random.default_rng(2026)
+	for _ in range(40):
+		N = int(rng.choice([1, 2, 3, 7, 16, 31, 64, 100, 257, 512, 1023, 2048]))
+		world = int(rng.integers(1, 9))
+		owner = np.zeros((6, N), np.int32)
+		for rank in range(world):
+			us = sharding.units_for_rank(rank, world, N)
+			assert us == sharding.units_for_rank(rank, world, N)
+			mine = np.zeros((6, N), np.int32)
+			for u in us:
+				assert 0 <= u.face < 6 and 0 <= u.row_begin < u.row_end <= N
+				mine[u.face, u.row_begin:u.row_end] += 1
+			owner += mine
+			# mirror closure: row j is here iff row N-1-j is
+			assert (mine == mine[:, ::-1]).all(), (N, world, rank)
+			folded = device.equirect_fold_units(N, us)
+			cover = np.zeros((6, N), np.int32)
+			for f, r0, r1 in folded:
+				cover[f & 7, r0:r1] += 1
+				if f & M:
+					for j in range(r0, r1):
+						if N - 1 - j != j:
+							cover[f & 7, N - 1 - j] += 1
+			assert (cover == mine).all(), (N, world, rank, folded)
+		assert (owner == 1).all(), (N, world)
