@@ -21,15 +21,15 @@ LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libcacaoimage_b200.so")
 TOOL = os.path.join(LIBDIR, "ce-cubetool")
 
-CU_SOURCES = ["convert_u8.cu", "convert_u16.cu", "convert_f16.cu", "convert_f32.cu", "equirect.cu", "mip.cu", "misc_kernels.cu", "cabi.cu"]
+CU_SOURCES = ["convert_u8.cu", "convert_u16.cu", "convert_f16.cu", "convert_f32.cu", "equirect.cu", "equirect_rows.cu", "mip.cu", "misc_kernels.cu", "cabi.cu"]
 CXX_SOURCES = ["libcacaoimage.cpp"]
 TOOL_SOURCES = ["tools/cubetool/main.cpp", "tools/cubetool/project.cpp", "tools/cubetool/create.cpp", "tools/cubetool/extract.cpp", "tools/cubetool/imageio.cpp", "tools/cubetool/vp8l.cpp", "tools/cubetool/xjc.cpp"]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: the float spec fixes where FMAs happen (explicit fmaf only).  No --use_fast_math:
 # IEEE division / sqrt and no flush-to-zero are part of the spec.
-NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
-CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
+NVCC_FLAGS = ARCH + (["-DCACAO_ROWS_SWEEP"] if os.environ.get("CACAO_ROWS_SWEEP") else []) + ["-O3", "-std=c++20", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
+CXX_FLAGS = ["-O2", "-std=c++20", "-fPIC", "-ffp-contract=off", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
 
 def _nvcc() -> str:
@@ -97,7 +97,7 @@ def build_tool(force: bool = False, verbose: bool = False) -> str | None:
 		return None
 	tool_hdrs = [os.path.join(ROOT, "tools/cubetool", f) for f in os.listdir(os.path.join(ROOT, "tools/cubetool")) if f.endswith(".hpp")] + [os.path.join(ROOT, "tools/toolutil.hpp")]
 	if force or not _newer(TOOL, srcs + tool_hdrs + [LIB]):
-		_run(["g++", "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "tools")] + srcs + ["-o", TOOL, "-L" + LIBDIR, "-lcacaoimage_b200", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread", "-ldl"], verbose)
+		_run(["g++", "-O2", "-std=c++20", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "tools")] + srcs + ["-o", TOOL, "-L" + LIBDIR, "-lcacaoimage_b200", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread", "-ldl"], verbose)
 	return TOOL
 
 

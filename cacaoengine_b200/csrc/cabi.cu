@@ -513,6 +513,12 @@ namespace {
 		return f >= CACAO_FMT_U8 && f <= CACAO_FMT_F32;
 	}
 
+	// true when [a, a+na) and [b, b+nb) share a byte
+	bool overlaps(const void* a, uint64_t na, const void* b, uint64_t nb) {
+		const uintptr_t x = reinterpret_cast<uintptr_t>(a), y = reinterpret_cast<uintptr_t>(b);
+		return na && nb && x < y + nb && y < x + na;
+	}
+
 	int check_convert_args(const void* src, void* dst, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, int mem) {
 		if(!ch_ok(src_ch) || !ch_ok(dst_ch)) return fail(CACAO_E_BAD_ARG, "channel counts must be 1, 3 or 4 (got %d -> %d)", src_ch, dst_ch);
 		if(!fmt_ok(src_fmt) || !fmt_ok(dst_fmt)) return fail(CACAO_E_BAD_ARG, "unknown sample format (%d -> %d)", src_fmt, dst_fmt);
@@ -702,7 +708,10 @@ namespace {
 				uint32_t w0 = 0, wn = 0;
 				equirect_src_window(W, H, N, 1u << p.u.face, p.u.row_begin, p.u.row_end, &w0, &wn);
 				// clip to the rows the caller holds (the kernel clamps the same way)
-				const uint32_t a = std::max(w0, src_row0), b = std::min<uint64_t>(static_cast<uint64_t>(w0) + wn, static_cast<uint64_t>(src_row0) + src_rows);
+				// (a window that misses the unit's rows altogether is clamped to its nearest row, like the kernel's taps)
+				const uint64_t held_end = static_cast<uint64_t>(src_row0) + src_rows;
+				const uint32_t a = static_cast<uint32_t>(std::min<uint64_t>(std::max(w0, src_row0), held_end - 1));
+				const uint32_t b = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(w0) + wn, held_end));
 				p.w0 = a;
 				p.w1 = b > a ? b : a + 1;
 				lo = std::min(lo, p.w0);
@@ -712,6 +721,7 @@ namespace {
 		}
 		if(pieces.empty()) return CACAO_OK;
 		hi = std::min<uint64_t>(hi, static_cast<uint64_t>(src_row0) + src_rows);
+		if(hi <= lo) return fail(CACAO_E_BAD_ARG, "equirect: the source window [%u,+%u) holds none of the rows the units read", src_row0, src_rows);
 		std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& a, const Piece& b) { return a.w1 != b.w1 ? a.w1 < b.w1 : a.w0 < b.w0; });
 
 		HostTrace trace("equirect_to_cube");
@@ -967,6 +977,8 @@ int cacao_img_convert_batch(int device, const void* src, void* dst, uint64_t pix
 	if(rc) return rc;
 	const uint64_t pixels = pixels_per_image * count;
 	if(pixels == 0) return CACAO_OK;
+	// the kernels read through the non-coherent path and promise the compiler disjoint buffers
+	if(overlaps(src, pixels * src_ch * fmt_bytes(src_fmt), dst, pixels * dst_ch * fmt_bytes(dst_fmt))) return fail(CACAO_E_BAD_ARG, "convert: source and destination overlap (the conversion is not an in-place operation)");
 	if(mem == CACAO_MEM_DEVICE) return enqueue_convert(c, src, dst, pixels, pixels_per_image, src_ch, dst_ch, src_fmt, dst_fmt, mode, static_cast<cudaStream_t>(stream));
 	return convert_host_pipeline(c, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), pixels, pixels_per_image, src_ch, dst_ch, src_fmt, dst_fmt, mode);
 }
@@ -981,6 +993,7 @@ int cacao_img_convert_flip(int device, const void* src, void* dst, uint32_t w, u
 	if(rc) return rc;
 	const uint64_t ppi = static_cast<uint64_t>(w) * h, pixels = ppi * count;
 	if(pixels == 0) return CACAO_OK;
+	if(overlaps(src, pixels * src_ch * fmt_bytes(src_fmt), dst, pixels * dst_ch * fmt_bytes(dst_fmt))) return fail(CACAO_E_BAD_ARG, "convert_flip: source and destination overlap (a row mirror cannot run in place)");
 	if(mem == CACAO_MEM_DEVICE) return enqueue_convert(c, src, dst, pixels, ppi, src_ch, dst_ch, src_fmt, dst_fmt, mode, static_cast<cudaStream_t>(stream), w, h);
 	// host memory: the same chunked upload / kernel / readback pipeline, cut into bands of whole rows
 	return convert_host_pipeline(c, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), pixels, ppi, src_ch, dst_ch, src_fmt, dst_fmt, mode, w, h);
@@ -1000,6 +1013,7 @@ int cacao_img_flip_rows(int device, const void* src, void* dst, uint32_t w, uint
 	int rc = get_ctx(device, &c, g);
 	if(rc) return rc;
 	const uint64_t pitch = static_cast<uint64_t>(w) * bytes_per_pixel;
+	if(overlaps(src, pitch * h, dst, pitch * h)) return fail(CACAO_E_BAD_ARG, "flip_rows: source and destination overlap (rows would be read after they were overwritten)");
 	if(mem == CACAO_MEM_DEVICE) {
 		cudaError_t e = flip_rows_launch(src, dst, pitch, h, c->sm_count, static_cast<cudaStream_t>(stream));
 		if(e != cudaSuccess) return fail_cuda(e, "flip kernel launch");
@@ -1024,6 +1038,7 @@ int cacao_img_shift_left_u16(int device, const void* src, void* dst, uint64_t sa
 	int rc = get_ctx(device, &c, g);
 	if(rc) return rc;
 	if(samples == 0) return CACAO_OK;
+	if(src != dst && overlaps(src, samples * 2, dst, samples * 2)) return fail(CACAO_E_BAD_ARG, "shift_left_u16: buffers may be identical (in place) or disjoint, not partly overlapping");
 	const unsigned n_launch = 1u + ((samples % 8) ? 1u : 0u);
 	if(mem == CACAO_MEM_DEVICE) {
 		cudaError_t e = shift_left_u16_launch(src, dst, samples, shift, static_cast<cudaStream_t>(stream));

@@ -114,7 +114,24 @@ namespace cacao {
 	template<int SF, int DF, int SC, int DC, bool TwoLevelLut = false>
 	__device__ __forceinline__ void convert_pixel(const uint32_t (&in)[SC], uint32_t (&out)[DC], const PixelCtx& ctx) {
 		constexpr bool src_int = FmtTraits<SF>::is_int;
-		if constexpr(src_int) {
+		if constexpr(SF == CACAO_FMT_U16 && DF == CACAO_FMT_U8 && SC != DC) {
+			// ---- 16 -> 8 bit WITH a layout change: the one pair where the depth conversion comes first --
+			// the order of the engine's composition (Convert16To8BitColor, then ChangeChannelLayout:
+			// engine/src/core/Cubemap.cpp:28-31), so the fused call equals the reference's two calls for every
+			// layout pair: an added alpha is 255 (Layout.cpp:57-58), not table[65535] = 254, and gray is the
+			// 8-bit rule on table outputs (Layout.cpp:33-41).  Only the channels that survive are looked up.
+			constexpr int used = SC < 3 ? SC : 3;
+			uint32_t t[used];
+#pragma unroll
+			for(int c = 0; c < used; ++c) t[c] = lut_16to8<TwoLevelLut>(ctx, in[c]);
+			if constexpr(DC == 1) {
+				out[0] = min(trunc_2126(t[0]) + trunc_7152<false>(t[1]) + trunc_0722(t[2]), 255u);
+			} else {
+#pragma unroll
+				for(int c = 0; c < 3; ++c) out[c] = t[SC == 1 ? 0 : c];
+				if constexpr(DC == 4) out[3] = 255u;
+			}
+		} else if constexpr(src_int) {
 			// ---- step 1: layout change in the integer domain
 			uint32_t mid[DC];
 			if constexpr(SC == DC) {

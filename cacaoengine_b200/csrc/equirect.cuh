@@ -39,6 +39,14 @@ namespace cacao {
 	cudaError_t equirect_launch_units(const void* src, void* dst, int ch, int fmt, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, uint32_t N, const CubeUnit* units, uint32_t n_units, cudaStream_t stream, unsigned* launches, int dst_ch = 0, int dst_fmt = -1, uint32_t flags = 0);
 	bool equirect_cvt_supported(int ch, int fmt, int dst_ch, int dst_fmt);
 
+	// The row-strip kernel (equirect_rows.cu): same pixels, fewer instructions -- ahead on the one-channel and
+	// 8-bit shapes, which are bound by instruction issue.
+	// equirect_launch_units routes to it by shape; CACAO_EQUIRECT_ROWS=0 / 1 forces the gather kernel / the
+	// row-strip kernel wherever it is defined (tests, A/B timing).
+	bool equirect_rows_supported(int ch, int fmt, int dst_ch, int dst_fmt, uint32_t W, uint32_t H);
+	bool equirect_rows_preferred(int ch, int fmt);
+	cudaError_t equirect_rows_launch(const void* src, void* dst, int ch, int fmt, const EquirectParams& prm, int sm_count, cudaStream_t stream);
+
 	// The folding step of equirect_launch_units on its own (host only): mirror bands of the input become
 	// single units flagged kUnitMirror; units with face > 5 or no rows are dropped.
 	std::vector<CubeUnit> pair_mirror_units(const std::vector<CubeUnit>& in, uint32_t N);

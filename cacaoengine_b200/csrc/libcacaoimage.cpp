@@ -236,8 +236,11 @@ namespace libcacaoimage {
 		if(!FusedProjectionDefined(src.layout, src.format, layout, format)) {
 			// no one-pass form (integer source, or a layout change other than RGB <-> RGBA): two passes
 			// (the row mirror is folded into the first one: conversion does not care about rows)
+			// ConvertMode::Fixed: this is a new operation, not a replacement of a reference call -- the
+			// reference's Gray -> RGBA pixel-0 repeat and its clamp of 16-bit gray to 255 are bugs to reproduce
+			// where its own functions are replaced, not to spread to faces that never went through them
 			std::array<ImageEx, 6> faces = EquirectToCubemap(src, faceSize, src.layout, src.format, devices, flipRows);
-			for(auto& f : faces) f = Convert(f, layout, format);
+			for(auto& f : faces) f = Convert(f, layout, format, ConvertMode::Fixed);
 			return faces;
 		}
 		if(src.w == 0 || src.h == 0 || faceSize == 0) check(CACAO_E_ZERO_DIM);
@@ -456,7 +459,7 @@ namespace libcacaoimage {
 		if(faceSize == 0) check(CACAO_E_ZERO_DIM);
 		if(!FusedProjectionDefined(layout_, format_, layout, format)) {
 			std::array<DeviceImage, 6> faces = EquirectToCubemap(faceSize, layout_, format_, flipRows);
-			for(auto& f : faces) f = f.Convert(layout, format);
+			for(auto& f : faces) f = f.Convert(layout, format, ConvertMode::Fixed); // see the host form above
 			return faces;
 		}
 		const std::size_t face_bytes = static_cast<std::size_t>(faceSize) * faceSize * BytesPerPixel(layout, format);

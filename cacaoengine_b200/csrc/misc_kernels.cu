@@ -27,6 +27,22 @@ namespace cacao {
 		}
 
 		// 16-bit left shift on packed pairs: (w << s) with the bits that crossed the half-word border masked off
+		// In place (src == dst, which the header allows) nothing may promise the compiler disjoint, read-only
+		// memory: that form has no __restrict__ and loads with plain ld.global instead of ld.global.nc.
+		__global__ void __launch_bounds__(256) shl16_inplace_kernel(uint4* buf, uint64_t units, uint32_t shift, uint32_t mask) {
+			const uint64_t u = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+			if(u >= units) return;
+			uint4 v = buf[u];
+			v.x = (v.x << shift) & mask;
+			v.y = (v.y << shift) & mask;
+			v.z = (v.z << shift) & mask;
+			v.w = (v.w << shift) & mask;
+			buf[u] = v;
+		}
+		__global__ void __launch_bounds__(256) shl16_scalar_inplace_kernel(uint16_t* buf, uint64_t begin, uint64_t end, uint32_t shift) {
+			const uint64_t k = begin + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+			if(k < end) buf[k] = static_cast<uint16_t>(static_cast<uint32_t>(buf[k]) << shift);
+		}
 		__global__ void __launch_bounds__(256) shl16_vec_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t units, uint32_t shift, uint32_t mask) {
 			const uint64_t u = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 			if(u >= units) return;
@@ -153,15 +169,22 @@ namespace cacao {
 	cudaError_t shift_left_u16_launch(const void* src, void* dst, uint64_t samples, uint32_t shift, cudaStream_t stream) {
 		const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
 		const uint64_t units = vec ? samples / 8 : 0;
+		const bool inplace = src == dst; // allowed by the header: no read-only / no-alias promises then
 		if(units) {
 			const uint32_t half = (0xFFFFu << shift) & 0xFFFFu;
-			shl16_vec_kernel<<<static_cast<unsigned>((units + 255) / 256), 256, 0, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), units, shift, half | (half << 16));
+			if(inplace)
+				shl16_inplace_kernel<<<static_cast<unsigned>((units + 255) / 256), 256, 0, stream>>>(static_cast<uint4*>(dst), units, shift, half | (half << 16));
+			else
+				shl16_vec_kernel<<<static_cast<unsigned>((units + 255) / 256), 256, 0, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), units, shift, half | (half << 16));
 			cudaError_t e = cudaGetLastError();
 			if(e != cudaSuccess) return e;
 		}
 		if(units * 8 < samples) {
 			const uint64_t rest = samples - units * 8;
-			shl16_scalar_kernel<<<static_cast<unsigned>((rest + 255) / 256), 256, 0, stream>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), units * 8, samples, shift);
+			if(inplace)
+				shl16_scalar_inplace_kernel<<<static_cast<unsigned>((rest + 255) / 256), 256, 0, stream>>>(static_cast<uint16_t*>(dst), units * 8, samples, shift);
+			else
+				shl16_scalar_kernel<<<static_cast<unsigned>((rest + 255) / 256), 256, 0, stream>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), units * 8, samples, shift);
 			return cudaGetLastError();
 		}
 		return cudaSuccess;

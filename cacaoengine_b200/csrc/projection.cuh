@@ -100,6 +100,18 @@ namespace cacao {
 		}
 	}
 
+	// The same table without a jump: selects on the (warp-uniform) face number and negations only, so
+	// every component has the bits the switch above produces, signed zeros included (equirect_rows.cu).
+	CACAO_HD void face_direction_sel(uint32_t face, float sc, float tc, float& x, float& y, float& z) {
+		const bool odd = (face & 1u) != 0;
+		const uint32_t axis = face >> 1; // 0: +-X, 1: +-Y, 2: +-Z
+		const float one = odd ? -1.0f : 1.0f;
+		const float nsc = -sc, ntc = -tc;
+		x = axis == 0u ? one : (face == 5u ? nsc : sc);
+		y = axis == 1u ? one : ntc;
+		z = axis == 0u ? (odd ? sc : nsc) : (axis == 1u ? (odd ? ntc : tc) : one);
+	}
+
 	// face pixel (column i, row j) -> continuous source position (texel centres at integer + 0.5
 	// already removed: xs, ys index texel centres directly)
 	CACAO_HD void project_pixel(uint32_t face, uint32_t i, uint32_t j, const ProjConst& c, float& xs, float& ys) {

@@ -305,6 +305,20 @@ static void convert_range(const uint8_t* src, uint8_t* dst, uint64_t p0, uint64_
 			/* step 1: layout change in the integer domain (reference rules) */
 			uint32_t in[4] = {0, 0, 0, 0}, mid[4];
 			for(int c = 0; c < src_ch; ++c) in[c] = (uint32_t)load_as_float(sp + (size_t)c * sb, src_fmt);
+			if(src_fmt == ORC_U16 && dst_fmt == ORC_U8 && src_ch != dst_ch) {
+				/* 16 -> 8 bit WITH a layout change: depth first, then the 8-bit layout rules -- the order of
+				 * the engine's composition Convert16To8BitColor, ChangeChannelLayout
+				 * (engine/src/core/Cubemap.cpp:28-31), so that the fused conversion equals the reference's two
+				 * calls for every layout pair (added alpha = 255, Layout.cpp:57-58; gray from table outputs) */
+				uint32_t in8[4] = {0, 0, 0, 0}, first8[4] = {0, 0, 0, 0};
+				for(int c = 0; c < src_ch; ++c) {
+					in8[c] = lut[in[c]];
+					first8[c] = lut[first[c]];
+				}
+				layout_int_px(in8, first8, mid, src_ch, dst_ch, 8, mode);
+				for(int c = 0; c < dst_ch; ++c) dp[c] = (uint8_t)mid[c];
+				continue;
+			}
 			if(src_ch == dst_ch)
 				memcpy(mid, in, sizeof mid);
 			else

@@ -11,7 +11,7 @@ def _compile(tmp_path, built_lib):
 	from cacaoengine_b200 import build as b
 
 	exe = tmp_path / "test_cpp_api"
-	subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests/cpp/test_cpp_api.cpp"), "-o", str(exe), "-L" + b.LIBDIR, "-lcacaoimage_b200", "-Wl,-rpath," + b.LIBDIR, "-lpthread"], check=True)
+	subprocess.run(["g++", "-std=c++20", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests/cpp/test_cpp_api.cpp"), "-o", str(exe), "-L" + b.LIBDIR, "-lcacaoimage_b200", "-Wl,-rpath," + b.LIBDIR, "-lpthread"], check=True)
 	return exe
 
 

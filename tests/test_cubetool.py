@@ -124,3 +124,31 @@ def test_project_float_npy_16bit_png_and_options(tool, tmp_path, oracle):
 	face = cv2.imread(str(tmp_path / "o2" / "deep_up.png"), cv2.IMREAD_UNCHANGED)[:, :, ::-1]
 	assert (face == up8).all()
 	assert sorted(os.listdir(tmp_path / "o2")) == ["deep_up.png"]  # no .ajc for a partial set
+
+
+@pytest.mark.gpu
+def test_project_integer_panoramas_convert_without_the_reference_quirks(tool, tmp_path, oracle):
+	"""`project --layout/--depth` on integer panoramas runs projection, then conversion.  That conversion is
+	part of a NEW operation, so it uses the fixed rules, not the reference's bugs (Layout.cpp:50-51 repeats
+	pixel 0 for Gray -> RGBA, :75 clamps 16-bit gray to 255): a gray panorama with --layout rgba keeps its
+	picture, a 16-bit RGB panorama with --layout gray keeps its range.  One GPU (device-resident chain) and
+	the host-memory path (--gpus semantics of EquirectToCubemap) must agree."""
+	W, H, N = 128, 64, 24
+	gray = oracle.synth(W * H, oracle.U8, 1, 51).reshape(H, W)
+	np.save(tmp_path / "g.npy", gray)
+	r = run(tool, "project", str(tmp_path / "g.npy"), "-o", str(tmp_path / "o1"), "-s", str(N), "--layout", "rgba", "--format", "npy")
+	assert r.returncode == 0, r.stderr
+	cube = oracle.equirect_to_cube(gray.reshape(-1), W, H, 1, oracle.U8, N).reshape(6, N * N)
+	for k, nm in enumerate(["right", "left", "up", "down", "front", "back"]):
+		got = np.load(tmp_path / "o1" / f"g_{nm}.npy")
+		want = oracle.convert(cube[k], 1, 4, oracle.U8, oracle.U8, mode=1).reshape(N, N, 4)
+		assert (got == want).all(), nm
+		assert len(np.unique(got[:, :, 0])) > 16, "faces must not be one flat colour (the pixel-0 quirk)"
+	rgb16 = oracle.synth(W * H * 3, oracle.U16, 3, 52).reshape(H, W, 3)
+	np.save(tmp_path / "c.npy", rgb16)
+	r = run(tool, "project", str(tmp_path / "c.npy"), "-o", str(tmp_path / "o2"), "-s", str(N), "--layout", "gray", "--format", "npy")
+	assert r.returncode == 0, r.stderr
+	cube = oracle.equirect_to_cube(rgb16.reshape(-1), W, H, 3, oracle.U16, N).reshape(6, N * N * 3)
+	got = np.load(tmp_path / "o2" / "c_front.npy")
+	want = oracle.convert(cube[4], 3, 1, oracle.U16, oracle.U16, mode=1).reshape(got.shape)
+	assert got.dtype == np.uint16 and (got == want).all() and got.max() > 255

@@ -361,6 +361,54 @@ def test_tma_staged_variant_is_bit_identical(oracle, monkeypatch, fmt, ch):
 		assert same_bits(part[sl], full[sl]), f
 
 
+@pytest.mark.parametrize("fmt", FMTS, ids=[NAME[f] for f in FMTS])
+@pytest.mark.parametrize("ch", (1, 3, 4))
+@pytest.mark.parametrize("rows", ("0", "1"), ids=["gather", "row-strip"])
+def test_both_resampling_kernels_on_every_shape(oracle, monkeypatch, fmt, ch, rows):
+	"""The gather kernel (equirect.cu) and the row-strip kernel (equirect_rows.cu: FP32-pipe floor and
+	truncation, row pointers, the column part of the projection carried across row steps) are two
+	implementations of Spec B.2; the launcher picks one per shape.  CACAO_EQUIRECT_ROWS forces either on
+	every shape: whole cubes (even, odd, one-pixel and upsampling faces, panoramas one texel wide), unit
+	lists with and without mirror partners, flipped output, row bands with source windows -- bit-exact
+	against the oracle, with 1, 2 and 5 row steps per thread where the shape has a row loop."""
+	from cacaoengine_b200 import device
+
+	monkeypatch.setenv("CACAO_EQUIRECT_ROWS", rows)
+	for steps in (None, "2", "5") if rows == "1" else (None,):
+		if steps:
+			monkeypatch.setenv("CACAO_EQUIRECT_STEPS", steps)
+		for W, H, N in ((96, 48, 36), (130, 70, 37), (16, 8, 1), (1, 1, 5), (3, 2, 7), (64, 32, 130), (257, 129, 64)):
+			src = oracle.synth(W * H * ch, fmt, ch, 5 + N)
+			want = oracle.equirect_to_cube(src, W, H, ch, fmt, N)
+			assert same_bits(gpu_equirect_device(src, W, H, ch, fmt, N), want), (W, H, N, steps)
+	monkeypatch.delenv("CACAO_EQUIRECT_STEPS", raising=False)
+	W, H, N = 301, 150, 75
+	src = oracle.synth(W * H * ch, fmt, ch, 9)
+	full = oracle.equirect_to_cube(src, W, H, ch, fmt, N)
+	a, b = DevBuf(src.nbytes), DevBuf(full.nbytes)
+	device.upload(a.ptr, src)
+	units = [(0, 0, 20), (0, 55, 75), (2, 10, 65), (3, 0, 37), (3, 37, 38), (4, 3, 50), (5, 70, 75), (1, 30, 31)]
+	for flags in (0, device.FLIP_ROWS):
+		want = np.zeros_like(full).reshape(6, N, N * ch)
+		ref = full.reshape(6, N, N * ch)
+		for f, r0, r1 in units:
+			if flags:
+				want[f, N - r1:N - r0] = ref[f, r0:r1][::-1]
+			else:
+				want[f, r0:r1] = ref[f, r0:r1]
+		device.upload(b.ptr, np.zeros_like(full))
+		device.equirect_to_cube_cvt(a.ptr, W, H, ch, fmt, b.ptr, N, ch, fmt, units=units, flags=flags)
+		got = np.empty_like(full)
+		device.download(got, b.ptr)
+		assert same_bits(got, want.reshape(-1)), flags
+	a.free(), b.free()
+	for f in (1, 2, 4):
+		win = device.equirect_src_window(W, H, N, 1 << f, 20, 61)
+		part = gpu_equirect_device(src, W, H, ch, fmt, N, 1 << f, 20, 61, window=win)
+		sl = slice((f * N + 20) * N * ch, (f * N + 61) * N * ch)
+		assert same_bits(part[sl], full[sl]), f
+
+
 def test_seam_and_poles(oracle):
 	"""One-hot panoramas: a texel on the u=0/1 seam and texels in the pole rows land identically."""
 	from cacaoengine_b200 import _capi as c

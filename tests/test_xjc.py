@@ -35,7 +35,7 @@ def tool(built_lib):
 @pytest.fixture(scope="module")
 def codec(tmp_path_factory):
 	exe = tmp_path_factory.mktemp("vp8l") / "vp8l_cli"
-	subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(ROOT, "tools/cubetool"), os.path.join(ROOT, "tests/cpp/vp8l_cli.cpp"), os.path.join(ROOT, "tools/cubetool/vp8l.cpp"), "-o", str(exe)], check=True)
+	subprocess.run(["g++", "-std=c++20", "-O2", "-Wall", "-I" + os.path.join(ROOT, "tools/cubetool"), os.path.join(ROOT, "tests/cpp/vp8l_cli.cpp"), os.path.join(ROOT, "tools/cubetool/vp8l.cpp"), "-o", str(exe)], check=True)
 	return str(exe)
 
 

@@ -57,6 +57,7 @@ namespace {
 			if(pos + 12 + len > f.size()) throw std::runtime_error("PNG chunk runs past the end of the file");
 			const unsigned char* d = &f[pos + 8];
 			if(type == "IHDR") {
+				if(len != 13) throw std::runtime_error("PNG IHDR chunk has the wrong size");
 				w = be32(d);
 				h = be32(d + 4);
 				depth = d[8];
@@ -70,6 +71,7 @@ namespace {
 			pos += 12 + len;
 		}
 		if(w == 0 || h == 0) throw std::runtime_error("PNG has no IHDR");
+		if(w > 65536 || h > 65536) throw std::runtime_error("PNG dimensions beyond 65536 pixels are not supported");
 		if(interlace) throw std::runtime_error("Interlaced PNG files are not supported");
 		if(depth != 8 && depth != 16) throw std::runtime_error("Only 8- and 16-bit PNG files are supported");
 		int ch;

@@ -171,7 +171,7 @@ namespace xjc {
 			vp8l::Decoded d;
 			try {
 				d = vp8l::Decode(b.data(), b.size());
-			} catch(const std::runtime_error& e) {
+			} catch(const std::exception& e) {
 				throw std::runtime_error(std::string("Failed to decode WebP data! (") + e.what() + ")");
 			}
 			// metadata as libs/image/src/WebP.cpp:47-54 sets it
@@ -190,7 +190,7 @@ namespace xjc {
 		libcacaoimage::ImageEx ex;
 		try {
 			ex = cubeio::DecodeImage(b);
-		} catch(const std::runtime_error&) {
+		} catch(const std::exception&) { // malformed input of any kind (length_error / bad_alloc from a hostile header included)
 			throw std::runtime_error("Unknown file type!"); // Forwarding.cpp:66
 		}
 		check(ex.format == libcacaoimage::SampleFormat::U8 || ex.format == libcacaoimage::SampleFormat::U16, "Cubemap faces must have 8 or 16-bit integer samples!");
