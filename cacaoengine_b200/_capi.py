@@ -35,6 +35,8 @@ SIGNATURES = {
 	"cacao_img_free": (_i, [_i, _vp]),
 	"cacao_img_host_alloc": (_i, [C.POINTER(_vp), _u64]),
 	"cacao_img_host_free": (_i, [_vp]),
+	"cacao_img_host_register": (_i, [_vp, _u64]),
+	"cacao_img_host_unregister": (_i, [_vp]),
 	"cacao_img_upload": (_i, [_i, _vp, _vp, _u64, _vp]),
 	"cacao_img_download": (_i, [_i, _vp, _vp, _u64, _vp]),
 	"cacao_img_sync": (_i, [_i, _vp]),

@@ -928,6 +928,18 @@ int cacao_img_host_free(void* host_ptr) {
 	return CACAO_OK;
 }
 
+int cacao_img_host_register(void* host_ptr, uint64_t bytes) {
+	if(!host_ptr || bytes == 0) return fail(CACAO_E_BAD_ARG, "host_register: null pointer or empty range");
+	cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable);
+	if(e != cudaSuccess) return fail_cuda(e, "cudaHostRegister");
+	return CACAO_OK;
+}
+
+int cacao_img_host_unregister(void* host_ptr) {
+	CU_TRY(cudaHostUnregister(host_ptr));
+	return CACAO_OK;
+}
+
 int cacao_img_upload(int device, void* dst_dev, const void* src_host, uint64_t bytes, void* stream) {
 	DeviceGuard g;
 	DeviceCtx* c = nullptr;

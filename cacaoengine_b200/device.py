@@ -46,6 +46,15 @@ def host_free(ptr: int) -> None:
 	capi.check(capi.lib().cacao_img_host_free(ptr))
 
 
+def host_register(ptr: int, nbytes: int) -> None:
+	"""Pin memory the caller owns (numpy array, shared-memory segment) for direct DMA; undo with host_unregister."""
+	capi.check(capi.lib().cacao_img_host_register(ptr, nbytes))
+
+
+def host_unregister(ptr: int) -> None:
+	capi.check(capi.lib().cacao_img_host_unregister(ptr))
+
+
 def upload(dst_dev: int, src: np.ndarray, device: int = -1, stream=None) -> None:
 	s = np.ascontiguousarray(src)
 	capi.check(capi.lib().cacao_img_upload(device, dst_dev, s.ctypes.data, s.nbytes, stream))

@@ -76,6 +76,11 @@ int cacao_img_malloc(int device, void** dev_ptr, uint64_t bytes);
 int cacao_img_free(int device, void* dev_ptr);
 int cacao_img_host_alloc(void** host_ptr, uint64_t bytes); /* pinned, portable across devices */
 int cacao_img_host_free(void* host_ptr);
+/* Pin memory the caller already owns (a std::vector's storage, a shared-memory segment several processes map,
+ * an mmap'ed file) so the host-memory calls DMA it directly instead of staging it: cudaHostRegister, portable
+ * across devices.  The range must stay mapped until cacao_img_host_unregister(host_ptr). */
+int cacao_img_host_register(void* host_ptr, uint64_t bytes);
+int cacao_img_host_unregister(void* host_ptr);
 /* Copies are enqueued on `stream` and asynchronous for pinned host memory.  Pageable host memory
  * (>= 1 MiB) is staged through the library's pinned ring by its host copy threads and the call
  * returns when the bytes have landed. */
@@ -90,6 +95,10 @@ int cacao_img_sync(int device, void* stream); /* stream == NULL: whole device */
  *   replaces  ChangeChannelLayout   (libs/image/src/Layout.cpp:8-103)      src_fmt == dst_fmt in {U8,U16}
  *             Convert16To8BitColor  (libs/image/src/Colordepth.cpp:7-41)   U16 -> U8, src_ch == dst_ch
  *             both in one pass      (engine/src/core/Cubemap.cpp:28-31)    e.g. RGBA16 -> RGB8
+ *                                   U16 -> U8 with a layout change applies the depth table FIRST, then the
+ *                                   8-bit layout rules -- the engine's order, so the fused call equals
+ *                                   ChangeChannelLayout(Convert16To8BitColor(img), layout) for every layout
+ *                                   pair (an added alpha is 255; gray is computed from table outputs)
  *   extends   to F16/F32 per DESIGN.md "Spec B.1" (no reference counterpart).
  * Channel counts are Image::Layout values: 1 (Grayscale), 3 (RGB), 4 (RGBA).
  * src_ch == dst_ch && src_fmt == dst_fmt -> CACAO_E_SAME_LAYOUT (Layout.cpp:9).
@@ -119,7 +128,8 @@ int cacao_img_convert_flip(int device, const void* src, void* dst, uint32_t w, u
  * dst[k] = (uint16_t)(src[k] << shift) over `samples` 16-bit samples, shift in [0,15].
  *   replaces the 12 -> 16 bit widening loop of the JPEG decoder, libs/image/src/JPEG.cpp:79-82
  *   (`imgDataSixteen[i] = uint16_t(twelveBit[i]) << 4`), one of the per-pixel loops next to the
- *   hot path.  In place (src == dst) is allowed.
+ *   hot path.  In place (src == dst) is allowed; partly overlapping buffers are not.
+ *   (Every other call needs disjoint src and dst and returns CACAO_E_BAD_ARG otherwise.)
  */
 int cacao_img_shift_left_u16(int device, const void* src, void* dst, uint64_t samples, uint32_t shift, int mem,
 							 void* stream);

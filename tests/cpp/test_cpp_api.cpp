@@ -1,6 +1,7 @@
 // test_cpp_api.cpp -- the reference's C++ interface (include/libcacaoimage.hpp) exercised the way
 // engine/src/core/Cubemap.cpp:20-32 and Tex2D.cpp:18 use it, against the known-answer vectors
 // extracted from the compiled reference.  Built and run by tests/test_cpp_api.py.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -57,7 +58,10 @@ static std::string thrown(F f) {
 }
 
 int main(int argc, char** argv) {
+	// argv[1] = logical ranks to spread multi-device calls over, argv[2] = devices in the box: the ranks go round
+	// robin over the devices (three ranks on device 0 of a one-GPU box still take the multi-threaded path)
 	const int n_devices = argc > 1 ? std::atoi(argv[1]) : 1;
+	const int n_physical = argc > 2 ? std::max(1, std::atoi(argv[2])) : n_devices;
 	static_assert(sizeof(Image) == 56, "Image layout must match the reference (libstdc++ x86-64)");
 	using L = Image::Layout;
 	// ---- ChangeChannelLayout, 8 bit
@@ -147,7 +151,7 @@ int main(int argc, char** argv) {
 			for(std::size_t b = 0; b < batch[k].data.size(); ++b) batch[k].data[b] = static_cast<unsigned char>((b * 7 + k * 13) & 0xFF);
 		}
 		std::vector<int> devs;
-		for(int d = 0; d < n_devices; ++d) devs.push_back(d);
+		for(int d = 0; d < n_devices; ++d) devs.push_back(d % n_physical);
 		const auto one = ConvertBatch(batch, L::RGBA, SampleFormat::U8);
 		const auto many = ConvertBatch(batch, L::RGBA, SampleFormat::U8, ConvertMode::ReferenceExact, devs);
 		for(std::size_t k = 0; k < batch.size(); ++k) {
@@ -173,7 +177,7 @@ int main(int argc, char** argv) {
 		noisy.data.resize(192 * 96 * 8);
 		for(std::size_t b = 0; b < noisy.data.size(); ++b) noisy.data[b] = static_cast<unsigned char>((b * 2654435761u) >> 13);
 		std::vector<int> devs;
-		for(int d = 0; d < n_devices; ++d) devs.push_back(d);
+		for(int d = 0; d < n_devices; ++d) devs.push_back(d % n_physical);
 		const auto one = EquirectToCubemap(noisy, 40);
 		const auto many = EquirectToCubemap(noisy, 40, devs);
 		for(int f = 0; f < 6; ++f) EXPECT(one[f].data == many[f].data && one[f].data.size() == 40 * 40 * 8);

@@ -28,6 +28,12 @@ def test_reference_arm_line(oracle):
 	assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 	assert "workload" in d["config"] and "model" not in d["config"]
 	assert d["gpu_launches"] == 0
+	# the same config object as the GPU arm prints, and every step the whole 256-frame batch
+	sys.path.insert(0, ROOT)
+	import bench
+
+	assert d["config"] == bench.headline_config(1) and d["config"]["frames_per_gpu"] == 256
+	assert "all 256 frames" in d["cpu_baseline"]["sample"]
 
 
 def test_reference_arm_other_ranks_stay_silent(oracle):
@@ -60,7 +66,13 @@ def test_gpu_arm_line(built_lib, oracle):
 	assert 0.5 < roof["frac"] < 1.3  # a sane fraction of the measured copy peak
 	e2e = d["e2e"]
 	assert e2e["h2d_bytes_per_step"] == 1920 * 1080 * 4 * 256 and e2e["d2h_bytes_per_step"] == 1920 * 1080 * 8 * 256
-	assert 0 < e2e["value"] < d["value"] and e2e["readback_verified"] is True
+	assert 0 < e2e["value"] < d["value"] and e2e["readback_verified"] is True and "oracle" in e2e["verified_against"]
+	pcie = e2e["roofline"]
+	assert pcie["bound"] == "pcie" and 0.5 < pcie["frac"] <= 1.1 and abs(pcie["frac"] - pcie["achieved"] / pcie["peak"]) < 1e-6
+	sys.path.insert(0, ROOT)
+	import bench
+
+	assert d["config"] == bench.headline_config(1)
 	cpu = d["cpu_baseline"]
 	assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] > 0
 	assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

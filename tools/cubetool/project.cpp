@@ -61,8 +61,11 @@ int RunProject(const ProjectOptions& opt) {
 			}
 			return;
 		}
+		// --gpus k deals the work units to k host threads; with fewer than k devices in the box the shares go
+		// round robin over the devices there are (same result, the shares of one device run one after the other)
+		const int have = std::max(1, cacao_img_device_count());
 		std::vector<int> devices;
-		for(int d = 0; d < opt.gpus; ++d) devices.push_back(d);
+		for(int d = 0; d < opt.gpus; ++d) devices.push_back(d % have);
 		if(devices.size() == 1) devices.clear(); // current device
 		faces = EquirectToCubemap(pano, N, layout, fmt, devices, opt.flip);
 	};
