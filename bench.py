@@ -463,7 +463,10 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 			res["verified"] = {"ok": bool(not bad and covered and pinned_ok is not False), "units": n_units, "ranks": world, "rows_cover_every_face_once": covered, "mismatching_units": bad[:8],
 							   "against": "cacao_img_checksum of every unit's rows on its rank == the same rows of a single-GPU whole-cube launch on rank 0, " + pin, "oracle_bands_ok": pinned_ok}
 			del full_src
-		# ---- (2) host -> host with the gather
+		# ---- (2) host -> host with the gather.  Host jobs are dealt by LATITUDE (sharding.units_for_rank_by_latitude,
+		# the plan of libcacaoimage::EquirectToCubemap(..., devices)): a rank pays for the source rows it uploads
+		units_h = sharding.units_for_rank_by_latitude(rank, world, N, W, H)
+		hw0, hwn = sharding.source_window(units_h, W, H, N)
 		pano = shared_host(f"{key[:4]}_src", W * H * bpp)
 		cube = shared_host(f"{key[:4]}_dst", 6 * N * N * bpp) if pano else None
 		if pano and cube:
@@ -474,7 +477,7 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 			faces = [cube_h.ctypes.data + f * N * N * bpp for f in range(6)]
 
 			def step():
-				device.equirect_to_cube_units_host(pano_h.ctypes.data + w0 * row_bytes, W, H, ch, fmt, faces, N, units, src_row0=w0, src_rows=wn, device=dev)
+				device.equirect_to_cube_units_host(pano_h.ctypes.data + hw0 * row_bytes, W, H, ch, fmt, faces, N, units_h, src_row0=hw0, src_rows=hwn, device=dev)
 
 			step()
 			reps = 3
@@ -483,7 +486,7 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 			for _ in range(reps):
 				step()
 			secs = (time.perf_counter() - t0) / reps
-			t = torch.tensor([secs, float(wn * row_bytes)], device=f"cuda:{dev}", dtype=torch.float64)
+			t = torch.tensor([secs, float(hwn * row_bytes)], device=f"cuda:{dev}", dtype=torch.float64)
 			tmax = t.clone()
 			dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
 			dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -494,8 +497,8 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 				ref = np.empty(6 * N * N * bpp, np.uint8)
 				device.download(ref, whole.data_ptr(), device=dev)
 				same = bool(np.array_equal(ref, cube_h))
-			res["e2e"] = {"value": 6 * N * N / secs / 1e9, "unit": UNIT, "ms_per_step": secs * 1e3, "h2d_bytes_per_step": up_bytes, "d2h_bytes_per_step": 6 * N * N * bpp, "gathered_cube_equals_single_gpu_cube": same,
-						  "path": f"{world} ranks: cacao_img_equirect_to_cube_units_host per rank -- source window from a pinned panorama all ranks map (/dev/shm, cudaHostRegister), pipelined upload / resample / readback, bands land in ONE set of six host face buffers; wall clock between barriers, max over ranks"}
+			res["e2e"] = {"value": 6 * N * N / secs / 1e9, "unit": UNIT, "ms_per_step": secs * 1e3, "h2d_bytes_per_step": up_bytes, "d2h_bytes_per_step": 6 * N * N * bpp, "gathered_cube_equals_single_gpu_cube": same, "source_rows_uploaded_by_this_rank": hwn,
+						  "path": f"{world} ranks, (face, row band) units dealt by latitude: cacao_img_equirect_to_cube_units_host per rank -- source window from a pinned panorama all ranks map (/dev/shm, cudaHostRegister), pipelined upload / resample / readback, bands land in ONE set of six host face buffers; wall clock between barriers, max over ranks"}
 			cube_done()
 			pano_done()
 		else:
@@ -544,9 +547,57 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 		ms2 = timed_region(torch, dist, 1, two_pass, steps, 3)
 		ms = timed_region(torch, dist, 1, fused, steps, 3)
 		same = device.checksum(dst.data_ptr(), px * 3, device=dev, stream=stream) == device.checksum(dst2.data_ptr(), px * 3, device=dev, stream=stream)
-		out[key] = {"value": px / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "n_gpus": 1, "roofline": roof(px * 11, ms, peak, None),
+		out[key] = {"value": px / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "n_gpus": 1, "roofline": roof(px * 11, ms, peak, traffic_for(key)),
 					"two_pass": {"value": px / ms2 / 1e6, "ms_per_step": ms2, "note": "cacao_img_convert_batch then cacao_img_flip_rows per face"}, "equals_two_pass": bool(same),
 					"note": "uniform-random samples: the 16->8 table gather is at its worst (bank conflicts); 100 MB problem, partly L2-resident"}
+		# ---- the same chain END TO END as the engine would call it: six host faces in, one contiguous flipped RGB8
+		# cube out (cacao_img_engine_cube, CACAO_MEM_HOST) -- against the UNMODIFIED reference doing the same job on
+		# the host cores: Convert16To8BitColor + ChangeChannelLayout per face (Cubemap.cpp:28-31) from oracle/_ref,
+		# the row mirror and the concatenation (OpenGLCubemap.cpp:25, VulkanCubemap.cpp:30-34) as plain memcpys
+		try:
+			from oracle import pyoracle as po
+
+			po.build()
+			face_in, cube_out = w * h * 8, device.engine_cube_bytes(w, h, device.CUBE_FLIP_ROWS)
+			hp_in, h_in = device.host_alloc(count * face_in)
+			hp_out, h_out = device.host_alloc(cube_out)
+			device.download(h_in, src.data_ptr(), device=dev)
+			ptrs = [hp_in + f * face_in for f in range(6)]
+			device.engine_cube(ptrs, w, h, 4, FMT_U16, hp_out, device.CUBE_FLIP_ROWS, mem=MEM_HOST, device=dev)
+			reps = 5
+			t0 = time.perf_counter()
+			for _ in range(reps):
+				device.engine_cube(ptrs, w, h, 4, FMT_U16, hp_out, device.CUBE_FLIP_ROWS, mem=MEM_HOST, device=dev)
+			dt = (time.perf_counter() - t0) / reps
+			pg_in = np.array(h_in, copy=True)  # ordinary pageable memory: what std::vector-based Images hand over
+			pg_out = np.empty(cube_out, np.uint8)
+			pg_ptrs = [pg_in.ctypes.data + f * face_in for f in range(6)]
+			device.engine_cube(pg_ptrs, w, h, 4, FMT_U16, pg_out.ctypes.data, device.CUBE_FLIP_ROWS, mem=MEM_HOST, device=dev)
+			t0 = time.perf_counter()
+			for _ in range(3):
+				device.engine_cube(pg_ptrs, w, h, 4, FMT_U16, pg_out.ctypes.data, device.CUBE_FLIP_ROWS, mem=MEM_HOST, device=dev)
+			dt_pg = (time.perf_counter() - t0) / 3
+			e2e = {"value": px / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": count * face_in, "d2h_bytes_per_step": cube_out,
+				   "pageable_value": px / dt_pg / 1e9, "pageable_ms_per_step": dt_pg * 1e3,
+				   "path": "cacao_img_engine_cube(CACAO_MEM_HOST, FLIP_ROWS): face k+1 uploads while face k converts and face k-1 reads back; pinned buffers (pageable_*: std::vector-like memory through the pinned ring)"}
+			if po.have_ref():
+				threads = min(6, host_threads())
+				faces16 = np.frombuffer(h_in, np.uint16)
+				want, _ = po.ref_engine_cube(faces16, w, h, 4, flip=True, threads=threads)
+				secs = min(po.ref_engine_cube(faces16, w, h, 4, flip=True, threads=threads)[1] for _ in range(3))
+				one = po.ref_engine_cube(faces16, w, h, 4, flip=True, threads=1)[1]
+				e2e["readback_verified"] = bool(np.array_equal(want, h_out) and np.array_equal(want, pg_out))
+				e2e["verified_against"] = "the compiled reference's own Convert16To8BitColor + ChangeChannelLayout per face (oracle/_ref), rows mirrored, faces concatenated"
+				out[key]["cpu_baseline"] = {"value": px / secs / 1e9, "unit": UNIT, "ms": secs * 1e3, "cores": threads, "kind": "reference", "cpu_model": cpu_model(), "single_thread_value": px / one / 1e9,
+											"sample": f"whole job: 6 faces {w}x{h} RGBA16 -> RGB8, libcacaoimage::Convert16To8BitColor + ChangeChannelLayout as shipped (two passes, two allocations per face), one host thread per face ({threads}); Flip as a row memcpy (the reference's Flip.cpp overruns its buffer) + concatenation; best of 3"}
+			else:
+				want = po.engine_cube(np.frombuffer(h_in, np.uint16), w, h, 4, flip=True)
+				e2e["readback_verified"] = bool(np.array_equal(want, h_out) and np.array_equal(want, pg_out))
+				e2e["verified_against"] = "oracle restatement (oracle/_ref did not travel)"
+			out[key]["e2e"] = e2e
+			device.host_free(hp_in), device.host_free(hp_out)
+		except Exception as e:
+			out[key]["e2e"] = {"error": repr(e)}
 		del src, mid, dst2, dst
 
 	if world == 1:

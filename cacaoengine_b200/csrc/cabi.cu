@@ -1015,6 +1015,162 @@ int cacao_img_convert(int device, const void* src, void* dst, uint64_t pixels, i
 	return cacao_img_convert_batch(device, src, dst, pixels, 1, src_ch, dst_ch, src_fmt, dst_fmt, mode, mem, stream);
 }
 
+namespace {
+	// Mip levels below a face-major cube level of six w x h RGB8 faces at `level` (device memory); the next levels
+	// are written behind it.  Six stacked faces of even height ARE one image of height 6h for a 2x2 box filter
+	// (no box straddles two faces), so such a level is one launch; odd heights go face by face.
+	int enqueue_cube_mips(uint8_t* level, uint32_t w, uint32_t h, cudaStream_t stream) {
+		while(w > 1 || h > 1) {
+			const uint32_t wo = w / 2 ? w / 2 : 1, ho = h / 2 ? h / 2 : 1;
+			uint8_t* next = level + 6ull * w * h * 3;
+			unsigned launches = 0, total = 0;
+			cudaError_t e = cudaSuccess;
+			if(h % 2 == 0) {
+				e = downsample2x_launch(level, next, w, 6 * h, 3, CACAO_FMT_U8, stream, &launches);
+				total = launches;
+			} else {
+				for(uint32_t f = 0; f < 6 && e == cudaSuccess; ++f) {
+					e = downsample2x_launch(level + static_cast<uint64_t>(f) * w * h * 3, next + static_cast<uint64_t>(f) * wo * ho * 3, w, h, 3, CACAO_FMT_U8, stream, &launches);
+					total += launches;
+				}
+			}
+			g_launches.fetch_add(total, std::memory_order_relaxed);
+			if(e != cudaSuccess) return fail_cuda(e, "mip kernel launch");
+			level = next;
+			w = wo;
+			h = ho;
+		}
+		return CACAO_OK;
+	}
+
+	// one face (or six contiguous ones) -> RGB8, optionally bottom row first; RGB8 input is a copy / a row mirror
+	int enqueue_face_to_rgb8(DeviceCtx* c, const void* src, void* dst, uint32_t w, uint32_t h, uint64_t count, int ch, int fmt, bool flip, cudaStream_t stream) {
+		const uint64_t ppi = static_cast<uint64_t>(w) * h;
+		if(ch == 3 && fmt == CACAO_FMT_U8) {
+			if(!flip || h == 1) {
+				CU_TRY(cudaMemcpyAsync(dst, src, ppi * count * 3, cudaMemcpyDefault, stream));
+				return CACAO_OK;
+			}
+			for(uint64_t k = 0; k < count; ++k) {
+				cudaError_t e = flip_rows_launch(static_cast<const uint8_t*>(src) + k * ppi * 3, static_cast<uint8_t*>(dst) + k * ppi * 3, static_cast<uint64_t>(w) * 3, h, c->sm_count, stream);
+				if(e != cudaSuccess) return fail_cuda(e, "flip kernel launch");
+				g_launches.fetch_add(1, std::memory_order_relaxed);
+			}
+			return CACAO_OK;
+		}
+		return enqueue_convert(c, src, dst, ppi * count, ppi, ch, 3, fmt, CACAO_FMT_U8, CACAO_MODE_REF_EXACT, stream, (flip && h > 1) ? w : 0, (flip && h > 1) ? h : 0);
+	}
+}
+
+uint64_t cacao_img_engine_cube_bytes(uint32_t w, uint32_t h, uint32_t flags) {
+	uint64_t total = 6ull * w * h * 3;
+	if((flags & CACAO_CUBE_MIPS) && w && h) {
+		while(w > 1 || h > 1) {
+			w = w / 2 ? w / 2 : 1;
+			h = h / 2 ? h / 2 : 1;
+			total += 6ull * w * h * 3;
+		}
+	}
+	return total;
+}
+
+int cacao_img_engine_cube(int device, const void* const* faces, uint32_t w, uint32_t h, int ch, int fmt, void* dst, uint32_t flags, int mem, void* stream) {
+	if(!faces || !dst) return fail(CACAO_E_BAD_ARG, "null pointer");
+	for(int f = 0; f < 6; ++f)
+		if(!faces[f]) return fail(CACAO_E_BAD_ARG, "engine_cube: face %d is null", f);
+	if(!ch_ok(ch)) return fail(CACAO_E_BAD_ARG, "channel count must be 1, 3 or 4 (got %d)", ch);
+	if(fmt != CACAO_FMT_U8 && fmt != CACAO_FMT_U16) return fail(CACAO_E_BAD_DEPTH, "%s", cacao_img_status_string(CACAO_E_BAD_DEPTH));
+	if(w == 0 || h == 0) return fail(CACAO_E_ZERO_DIM, "%s", cacao_img_status_string(CACAO_E_ZERO_DIM));
+	if(flags & ~(CACAO_CUBE_FLIP_ROWS | CACAO_CUBE_MIPS)) return fail(CACAO_E_BAD_ARG, "engine_cube: unknown flags 0x%x", flags);
+	if(mem != CACAO_MEM_HOST && mem != CACAO_MEM_DEVICE) return fail(CACAO_E_BAD_ARG, "unknown memory kind %d", mem);
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	const bool flip = (flags & CACAO_CUBE_FLIP_ROWS) != 0, mips = (flags & CACAO_CUBE_MIPS) != 0;
+	const uint64_t ppi = static_cast<uint64_t>(w) * h;
+	const uint64_t in_face = ppi * ch * fmt_bytes(fmt), out_face = ppi * 3;
+	const uint64_t out_total = cacao_img_engine_cube_bytes(w, h, flags);
+	for(int f = 0; f < 6; ++f)
+		if(overlaps(faces[f], in_face, dst, out_total)) return fail(CACAO_E_BAD_ARG, "engine_cube: face %d overlaps the destination", f);
+	if(mem == CACAO_MEM_DEVICE) {
+		cudaStream_t s = static_cast<cudaStream_t>(stream);
+		bool contiguous = true;
+		for(int f = 1; f < 6; ++f) contiguous = contiguous && static_cast<const uint8_t*>(faces[f]) == static_cast<const uint8_t*>(faces[0]) + f * in_face;
+		if(contiguous) {
+			rc = enqueue_face_to_rgb8(c, faces[0], dst, w, h, 6, ch, fmt, flip, s);
+			if(rc) return rc;
+		} else {
+			for(int f = 0; f < 6; ++f) {
+				rc = enqueue_face_to_rgb8(c, faces[f], static_cast<uint8_t*>(dst) + f * out_face, w, h, 1, ch, fmt, flip, s);
+				if(rc) return rc;
+			}
+		}
+		return mips ? enqueue_cube_mips(static_cast<uint8_t*>(dst), w, h, s) : CACAO_OK;
+	}
+	// ---- host memory: faces flow upload -> convert -> readback over the three streams
+	HostTrace trace("engine_cube");
+	trace.in_bytes = 6 * in_face;
+	trace.out_bytes = out_total;
+	std::lock_guard<std::mutex> lock(c->pipe_mutex);
+	rc = ensure_stage(c, 6 * in_face, out_total, 1);
+	if(rc) return rc;
+	bool src_pg = false;
+	for(int f = 0; f < 6; ++f) src_pg = src_pg || is_pageable(faces[f]);
+	const bool dst_pg = is_pageable(dst);
+	trace.path = (src_pg || dst_pg) ? "per face, pageable" : "per face, pinned";
+	uint8_t* d_in = c->stage_in[0];
+	uint8_t* d_out = c->stage_out[0];
+	uint8_t* h_out = static_cast<uint8_t*>(dst);
+	// Pageable faces go through the pinned ring in chunks on the upload stream; the copy pool fills slot k+1 while
+	// slot k is on the wire.  A face's kernel waits for its last chunk, its readback for the kernel.
+	uint64_t ring_use = 0; // chunks staged so far (ring slots are reused round robin)
+	if(src_pg || dst_pg) {
+		rc = ensure_pinned(c, src_pg ? kXferChunk : 0, dst_pg ? kXferChunk : 0);
+		if(rc) return rc;
+	}
+	std::vector<Segment> back; // pageable destination: drained after the last face has been issued
+	for(int f = 0; f < 6; ++f) {
+		const uint8_t* from = static_cast<const uint8_t*>(faces[f]);
+		if(is_pageable(from) && in_face >= (1u << 20)) {
+			for(uint64_t off = 0; off < in_face; off += kXferChunk, ++ring_use) {
+				const int sl = static_cast<int>(ring_use % kSlots);
+				const uint64_t n = std::min<uint64_t>(kXferChunk, in_face - off);
+				if(ring_use >= kSlots) CU_TRY(cudaEventSynchronize(c->ev_in[sl]));
+				CopyPool::get().copy(c->pin_in[sl], from + off, n);
+				CU_TRY(cudaMemcpyAsync(d_in + f * in_face + off, c->pin_in[sl], n, cudaMemcpyHostToDevice, c->s_in));
+				CU_TRY(cudaEventRecord(c->ev_in[sl], c->s_in));
+			}
+		} else {
+			CU_TRY(cudaMemcpyAsync(d_in + f * in_face, from, in_face, cudaMemcpyHostToDevice, c->s_in));
+		}
+		CU_TRY(cudaEventRecord(c->ev_run[0], c->s_in)); // "face f has landed"
+		CU_TRY(cudaStreamWaitEvent(c->s_run, c->ev_run[0], 0));
+		rc = enqueue_face_to_rgb8(c, d_in + f * in_face, d_out + f * out_face, w, h, 1, ch, fmt, flip, c->s_run);
+		if(rc) return rc;
+		CU_TRY(cudaEventRecord(c->ev_run[1], c->s_run));
+		CU_TRY(cudaStreamWaitEvent(c->s_out, c->ev_run[1], 0));
+		if(dst_pg)
+			back.push_back({h_out + f * out_face, d_out + f * out_face, static_cast<size_t>(out_face)});
+		else
+			CU_TRY(cudaMemcpyAsync(h_out + f * out_face, d_out + f * out_face, out_face, cudaMemcpyDeviceToHost, c->s_out));
+	}
+	if(mips) {
+		rc = enqueue_cube_mips(d_out, w, h, c->s_run);
+		if(rc) return rc;
+		CU_TRY(cudaEventRecord(c->ev_run[2], c->s_run));
+		CU_TRY(cudaStreamWaitEvent(c->s_out, c->ev_run[2], 0));
+		const uint64_t level0 = 6 * out_face;
+		if(dst_pg)
+			back.push_back({h_out + level0, d_out + level0, static_cast<size_t>(out_total - level0)});
+		else
+			CU_TRY(cudaMemcpyAsync(h_out + level0, d_out + level0, out_total - level0, cudaMemcpyDeviceToHost, c->s_out));
+	}
+	if(dst_pg) return download_segments(c, back, c->s_out);
+	CU_TRY(cudaStreamSynchronize(c->s_out));
+	return CACAO_OK;
+}
+
 int cacao_img_flip_rows(int device, const void* src, void* dst, uint32_t w, uint32_t h, uint32_t bytes_per_pixel, int mem, void* stream) {
 	if(w == 0 || h == 0) return fail(CACAO_E_ZERO_DIM, "%s", cacao_img_status_string(CACAO_E_ZERO_DIM));
 	if(bytes_per_pixel == 0) return fail(CACAO_E_BAD_DEPTH, "%s", cacao_img_status_string(CACAO_E_BAD_DEPTH));

@@ -213,6 +213,50 @@ namespace libcacaoimage {
 		return out;
 	}
 
+	std::size_t CubeRGB8::FaceBytes(unsigned int level) const {
+		unsigned int lw = w, lh = h;
+		for(unsigned int l = 0; l < level; ++l) {
+			lw = lw / 2 ? lw / 2 : 1;
+			lh = lh / 2 ? lh / 2 : 1;
+		}
+		return static_cast<std::size_t>(lw) * lh * 3;
+	}
+
+	CubeRGB8 EngineCube(const std::array<Image, 6>& faces, bool flipRows, bool mips, int device) {
+		CubeRGB8 cube;
+		cube.w = faces[0].w;
+		cube.h = faces[0].h;
+		bool uniform = true;
+		for(const Image& f : faces) {
+			if(f.w != cube.w || f.h != cube.h) throw std::runtime_error("Not all cubemap faces are the same size!"); // Cubemap.cpp:25
+			if(!(f.bitsPerChannel == 8 || f.bitsPerChannel == 16)) check(CACAO_E_BAD_DEPTH);
+			if(f.data.size() < static_cast<std::size_t>(f.w) * f.h * static_cast<int>(f.layout) * (f.bitsPerChannel / 8)) throw std::runtime_error("Image data buffer is smaller than w * h * channels * bytes per channel!");
+			uniform = uniform && f.layout == faces[0].layout && f.bitsPerChannel == faces[0].bitsPerChannel;
+		}
+		if(cube.w == 0 || cube.h == 0) check(CACAO_E_ZERO_DIM);
+		const uint32_t flags = (flipRows ? CACAO_CUBE_FLIP_ROWS : 0u) | (mips ? CACAO_CUBE_MIPS : 0u);
+		cube.data.resize(cacao_img_engine_cube_bytes(cube.w, cube.h, flags));
+		std::size_t off = 0;
+		for(unsigned int lw = cube.w, lh = cube.h;; lw = lw / 2 ? lw / 2 : 1, lh = lh / 2 ? lh / 2 : 1) {
+			cube.levelOffset.push_back(off);
+			off += 6 * static_cast<std::size_t>(lw) * lh * 3;
+			if(!mips || (lw == 1 && lh == 1)) break;
+		}
+		const void* ptrs[6];
+		std::array<Image, 6> converted; // only for mixed sets: each face brought to RGB8 on its own first
+		if(uniform) {
+			for(int f = 0; f < 6; ++f) ptrs[f] = faces[f].data.data();
+			check(cacao_img_engine_cube(device, ptrs, cube.w, cube.h, static_cast<int>(faces[0].layout), fmt_of_bits(faces[0].bitsPerChannel), cube.data.data(), flags, CACAO_MEM_HOST, nullptr));
+		} else {
+			for(int f = 0; f < 6; ++f) {
+				converted[f] = ToRGB8(faces[f]);
+				ptrs[f] = converted[f].data.data();
+			}
+			check(cacao_img_engine_cube(device, ptrs, cube.w, cube.h, 3, CACAO_FMT_U8, cube.data.data(), flags, CACAO_MEM_HOST, nullptr));
+		}
+		return cube;
+	}
+
 	ImageEx Flip(const ImageEx& src) {
 		if(!(src.w > 0 && src.h > 0)) check(CACAO_E_ZERO_DIM);
 		if(src.data.empty()) check(CACAO_E_EMPTY);

@@ -106,6 +106,19 @@ def convert_flip(src: int, dst: int, w: int, h: int, count: int, src_ch: int, ds
 	capi.check(capi.lib().cacao_img_convert_flip(device, src, dst, w, h, count, src_ch, dst_ch, src_fmt, dst_fmt, mode, mem, stream))
 
 
+CUBE_FLIP_ROWS, CUBE_MIPS = 1, 2
+
+
+def engine_cube_bytes(w: int, h: int, flags: int = 0) -> int:
+	return int(capi.lib().cacao_img_engine_cube_bytes(w, h, flags))
+
+
+def engine_cube(faces, w: int, h: int, ch: int, fmt: int, dst: int, flags: int = 0, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> None:
+	"""cacao_img_engine_cube: six faces (addresses) -> one contiguous RGB8 cube (+ flipped rows, + mip chain)."""
+	ptrs = (C.c_void_p * 6)(*[int(f) for f in faces])
+	capi.check(capi.lib().cacao_img_engine_cube(device, ptrs, w, h, ch, fmt, dst, flags, mem, stream))
+
+
 def equirect_to_cube(src: int, W: int, H: int, ch: int, fmt: int, dst: int, N: int, face_mask: int = 0x3F, row_begin: int = 0, row_end: int | None = None, src_row0: int = 0, src_rows: int | None = None, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> None:
 	capi.check(capi.lib().cacao_img_equirect_to_cube(device, src, W, H, src_row0, H if src_rows is None else src_rows, ch, fmt, dst, N, face_mask, row_begin, N if row_end is None else row_end, mem, stream))
 

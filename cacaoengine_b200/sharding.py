@@ -148,6 +148,42 @@ def units_for_rank(rank: int, world: int, face_size: int, bands_per_face: int | 
 	return sorted(mine, key=lambda u: (u.face, u.row_begin))
 
 
+def units_for_rank_by_latitude(rank: int, world: int, face_size: int, W: int, H: int) -> list[CubeUnit]:
+	"""Dealing for HOST-memory jobs, where the upload of the source window is what a rank pays for, not its
+	kernel: 2 x world row bands per face, ordered by the latitude they read (centre of their source-row
+	window) and cut into `world` contiguous runs of equal output rows -- each rank then uploads one band of
+	the panorama (about a quarter of it at 8 ranks) instead of nearly all of it.  The same plan
+	libcacaoimage::EquirectToCubemap(src, N, ..., devices) makes (csrc/libcacaoimage.cpp); the device-resident
+	dealing above balances kernel cost instead and lets windows overlap."""
+	if not (0 <= rank < world):
+		raise ValueError(f"rank {rank} outside world of {world}")
+	if world == 1:
+		return [CubeUnit(f, 0, face_size) for f in range(6)]
+	bands = min(face_size, 2 * world)
+	keyed = []
+	for f in range(6):
+		for b in range(bands):
+			r0, r1 = face_size * b // bands, face_size * (b + 1) // bands
+			if r1 <= r0:
+				continue
+			w0, wn = device.equirect_src_window(W, H, face_size, 1 << f, r0, r1)
+			keyed.append((2 * w0 + wn, len(keyed), CubeUnit(f, r0, r1)))
+	keyed.sort(key=lambda k: (k[0], k[1]))
+	units = [k[2] for k in keyed]
+	total = sum(u.rows for u in units)
+	begin = [len(units)] * (world + 1)
+	begin[0], acc, d = 0, 0, 0
+	for i, u in enumerate(units):
+		while d + 1 < world and acc * world >= (d + 1) * total:
+			d += 1
+			begin[d] = i
+		acc += u.rows
+	while d + 1 < world:
+		d += 1
+		begin[d] = len(units)
+	return units[begin[rank]:begin[rank + 1]]
+
+
 def source_window(units: list[CubeUnit], W: int, H: int, face_size: int) -> tuple[int, int]:
 	"""(first_row, rows): the band of equirect rows that covers every unit in the list
 	(host arithmetic identical to the kernel's, cacao_img_equirect_src_window)."""

@@ -125,6 +125,31 @@ int cacao_img_convert_flip(int device, const void* src, void* dst, uint32_t w, u
 						   int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, int mem, void* stream);
 
 /*
+ * The engine's cubemap load chain as ONE call.  What Cacao::Cubemap::Cubemap does per face in two passes and two
+ * allocations -- Convert16To8BitColor when the face is 16-bit, then ChangeChannelLayout to RGB when it is not
+ * RGB already (engine/src/core/Cubemap.cpp:28-31) -- what the GL backend adds before upload (Flip,
+ * engine/src/opengl/impls/OpenGLCubemap.cpp:25) and what the Vulkan backend adds after it (the six faces copied
+ * into one contiguous buffer, engine/src/vulkan/impls/VulkanCubemap.cpp:30-41), plus, on request, the mip chain
+ * the GL backend asks the driver for (glGenerateMipmap, OpenGLTex2D.cpp:51):
+ *   faces[f]  the six faces +X,-X,+Y,-Y,+Z,-Z, each w x h pixels of `ch` channels (1, 3, 4) of `fmt`
+ *             (CACAO_FMT_U8 or CACAO_FMT_U16); separate allocations are fine
+ *   dst       ONE buffer: level 0 = six RGB8 faces back to back (6*w*h*3 bytes), then -- with
+ *             CACAO_CUBE_MIPS -- level 1 (six faces of max(1,w/2) x max(1,h/2)), level 2, ... down to 1 x 1,
+ *             every level face-major; cacao_img_engine_cube_bytes() says how large it is
+ *   flags     CACAO_CUBE_FLIP_ROWS: every face bottom row first; CACAO_CUBE_MIPS: append the mip chain
+ *             (2x2 box average per level, DESIGN.md "Spec B.3", of the faces as stored)
+ * Values are the reference's, bit for bit (REF_EXACT rules, the Gray -> RGB replicate included).  Host memory:
+ * one pipelined pass -- face k+1 goes up while face k is converted and face k-1 comes back; pinned buffers are
+ * DMA'd directly, pageable ones (std::vector) are staged by the host copy pool.  Device memory: one launch when
+ * the faces are contiguous, six otherwise, plus one per mip level.
+ */
+#define CACAO_CUBE_FLIP_ROWS 1u
+#define CACAO_CUBE_MIPS 2u
+uint64_t cacao_img_engine_cube_bytes(uint32_t w, uint32_t h, uint32_t flags);
+int cacao_img_engine_cube(int device, const void* const* faces, uint32_t w, uint32_t h, int ch, int fmt, void* dst,
+						  uint32_t flags, int mem, void* stream);
+
+/*
  * dst[k] = (uint16_t)(src[k] << shift) over `samples` 16-bit samples, shift in [0,15].
  *   replaces the 12 -> 16 bit widening loop of the JPEG decoder, libs/image/src/JPEG.cpp:79-82
  *   (`imgDataSixteen[i] = uint16_t(twelveBit[i]) << 4`), one of the per-pixel loops next to the

@@ -48,6 +48,22 @@ namespace libcacaoimage {
 	// ... and OpenGLCubemap.cpp:25's Flip in the same kernel: three reference passes, one here
 	Image ToRGB8(const Image& src, bool flipRows);
 
+	// The engine's whole cubemap load chain in one call: what Cacao::Cubemap::Cubemap does per face
+	// (Convert16To8BitColor when 16-bit, ChangeChannelLayout to RGB when not RGB, engine/src/core/Cubemap.cpp:20-32),
+	// the GL backend's Flip before upload (engine/src/opengl/impls/OpenGLCubemap.cpp:25, flipRows) and the Vulkan
+	// backend's copy of the six faces into one contiguous buffer (engine/src/vulkan/impls/VulkanCubemap.cpp:30-41),
+	// optionally with the mip chain behind it (2x2 box per level; the GL path leaves that to glGenerateMipmap).
+	// One upload / kernel / readback pipeline instead of up to eighteen passes over the pixels; values are the
+	// reference's bit for bit.  Throws the engine's message when the faces differ in size.
+	struct CubeRGB8 {
+		unsigned int w = 0, h = 0;            // of a level-0 face
+		std::vector<unsigned char> data;      // level 0: six RGB8 faces back to back (+X,-X,+Y,-Y,+Z,-Z); then the mip levels, each face-major
+		std::vector<std::size_t> levelOffset; // byte offset of every level in data (one entry without mips)
+		std::size_t FaceBytes(unsigned int level = 0) const;
+		const unsigned char* Face(unsigned int face, unsigned int level = 0) const { return data.data() + levelOffset[level] + face * FaceBytes(level); }
+	};
+	CubeRGB8 EngineCube(const std::array<Image, 6>& faces, bool flipRows = false, bool mips = false, int device = -1);
+
 	// Equirectangular panorama -> six N x N faces in the order +X,-X,+Y,-Y,+Z,-Z
 	// (right,left,up,down,front,back), same layout and sample format as the source.
 	// devices: CUDA ordinals to spread face/row-band work units over (empty = current device).

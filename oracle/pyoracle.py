@@ -96,6 +96,8 @@ def ref() -> C.CDLL:
 		lib.ref_batch_change_layout.argtypes = [vp, vp, u32, u32, i, i, i, i, i, C.POINTER(C.c_double)]
 		lib.ref_batch_depth16to8.argtypes = [vp, vp, u32, u32, i, i, i, C.POINTER(C.c_double)]
 		lib.ref_max_threads.restype = i
+		if hasattr(lib, "ref_engine_cube"):
+			lib.ref_engine_cube.argtypes = [vp, vp, u32, u32, i, i, i, i, C.POINTER(C.c_double)]
 		_ref = lib
 	return _ref
 
@@ -244,6 +246,43 @@ def ref_change_layout(src: np.ndarray, w: int, h: int, src_ch: int, dst_ch: int)
 	if rc != 0:
 		raise RuntimeError(ref().ref_last_error().decode())
 	return dst
+
+
+def ref_engine_cube(faces: np.ndarray, w: int, h: int, ch: int, flip: bool = False, threads: int = 6) -> tuple[np.ndarray, float]:
+	"""Six faces back to back through the reference's own load chain (Cubemap.cpp:28-31: Convert16To8BitColor,
+	ChangeChannelLayout -> RGB), a row mirror with Flip's intended semantics when `flip`, the six results
+	contiguous.  Returns (cube bytes, seconds of the chain)."""
+	bits = 8 if faces.dtype == np.uint8 else 16
+	s = np.ascontiguousarray(faces).reshape(-1)
+	assert s.size == 6 * w * h * ch
+	dst = np.empty(6 * w * h * 3, np.uint8)
+	secs = C.c_double()
+	rc = ref().ref_engine_cube(_ptr(s), _ptr(dst), w, h, ch, bits, 1 if flip else 0, threads, C.byref(secs))
+	if rc != 0:
+		raise RuntimeError("ref_engine_cube failed")
+	return dst, secs.value
+
+
+def engine_cube(faces: np.ndarray, w: int, h: int, ch: int, flip: bool = False, mips: bool = False) -> np.ndarray:
+	"""The same chain from the restatement (depth16to8, change_layout, row mirror, downsample2x per level):
+	level 0 = six RGB8 faces back to back, then every mip level face-major."""
+	f = np.ascontiguousarray(faces).reshape(6, -1)
+	out = []
+	for k in range(6):
+		img = f[k]
+		if img.dtype == np.uint16:
+			img = depth16to8(img)
+		if ch != 3:
+			img = change_layout(img, ch, 3)
+		img = img.reshape(h, w * 3)
+		out.append(np.ascontiguousarray(img[::-1] if flip else img).reshape(-1))
+	levels = [np.concatenate(out)]
+	lw, lh = w, h
+	while mips and (lw > 1 or lh > 1):
+		out = [downsample2x(o, lw, lh, 3, U8) for o in out]
+		lw, lh = max(1, lw // 2), max(1, lh // 2)
+		levels.append(np.concatenate(out))
+	return np.concatenate(levels)
 
 
 def ref_depth16to8(src: np.ndarray, w: int, h: int, ch: int) -> np.ndarray:

@@ -2,6 +2,7 @@
 // engine/src/core/Cubemap.cpp:20-32 and Tex2D.cpp:18 use it, against the known-answer vectors
 // extracted from the compiled reference.  Built and run by tests/test_cpp_api.py.
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -257,6 +258,43 @@ int main(int argc, char** argv) {
 		const auto two = EquirectToCubemap(deep, 12, L::RGB, SampleFormat::U8); // falls back to two passes
 		const auto ref = EquirectToCubemap(deep, 12);
 		for(int f = 0; f < 6; ++f) EXPECT(two[f].data == Convert(ref[f], L::RGB, SampleFormat::U8).data);
+	}
+	// ---- EngineCube: the whole load chain of Cacao::Cubemap (Cubemap.cpp:20-32) + Flip + contiguous faces in one call
+	{
+		std::array<Image, 6> faces;
+		for(int f = 0; f < 6; ++f) {
+			faces[f] = {};
+			faces[f].w = 48;
+			faces[f].h = 32;
+			faces[f].layout = L::RGBA;
+			faces[f].bitsPerChannel = 16;
+			faces[f].data.resize(48 * 32 * 8);
+			for(std::size_t b = 0; b < faces[f].data.size(); ++b) faces[f].data[b] = static_cast<unsigned char>(((b + 977 * f) * 2654435761u) >> 11);
+		}
+		const CubeRGB8 cube = EngineCube(faces, true, true);
+		EXPECT(cube.w == 48 && cube.h == 32 && cube.levelOffset.size() == 6 && cube.levelOffset[1] == 6 * 48 * 32 * 3 && cube.FaceBytes(1) == 24 * 16 * 3);
+		EXPECT(cube.data.size() == cube.levelOffset[5] + 6 * cube.FaceBytes(5) && cube.FaceBytes(5) == 3);
+		for(int f = 0; f < 6; ++f) {
+			// the reference's sequence, one face at a time: 16 -> 8 bit, -> RGB, Flip
+			const Image step = Flip(ChangeChannelLayout(Convert16To8BitColor(faces[f]), L::RGB));
+			EXPECT(std::memcmp(cube.Face(f), step.data.data(), step.data.size()) == 0);
+		}
+		// faces of different kinds: each is brought to RGB8 by its own rule first
+		faces[2] = ChangeChannelLayout(Convert16To8BitColor(faces[2]), L::Grayscale);
+		faces[4] = Convert16To8BitColor(faces[4]);
+		const CubeRGB8 mixed = EngineCube(faces);
+		for(int f = 0; f < 6; ++f) {
+			const Image step = ToRGB8(faces[f]);
+			EXPECT(std::memcmp(mixed.Face(f), step.data.data(), step.data.size()) == 0);
+		}
+		faces[3].w = 47;
+		bool threw = false;
+		try {
+			EngineCube(faces);
+		} catch(const std::runtime_error& e) {
+			threw = std::string(e.what()) == "Not all cubemap faces are the same size!";
+		}
+		EXPECT(threw);
 	}
 	std::printf(failures ? "%d FAILURES\n" : "cpp api ok\n", failures);
 	return failures ? 1 : 0;

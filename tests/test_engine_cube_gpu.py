@@ -1,0 +1,100 @@
+"""cacao_img_engine_cube: the engine's cubemap load chain as one call -- Convert16To8BitColor when 16-bit,
+ChangeChannelLayout to RGB when not RGB (engine/src/core/Cubemap.cpp:28-31), the GL backend's row mirror
+(engine/src/opengl/impls/OpenGLCubemap.cpp:25), the six faces contiguous (engine/src/vulkan/impls/VulkanCubemap.cpp:30-41),
+optionally the mip chain.  Checked against the restatement and, where oracle/_ref travelled, against the
+reference's OWN two functions run face by face."""
+import numpy as np
+import pytest
+
+from gpu_util import DevBuf
+
+
+def test_cube_size_is_a_host_side_calculation(built_lib):
+	from cacaoengine_b200 import device
+
+	assert device.engine_cube_bytes(4, 4) == 6 * 16 * 3
+	assert device.engine_cube_bytes(4, 4, device.CUBE_MIPS) == 6 * 3 * (16 + 4 + 1)
+	assert device.engine_cube_bytes(5, 3, device.CUBE_MIPS) == 6 * 3 * (15 + 2 + 1)
+	assert device.engine_cube_bytes(1, 1, device.CUBE_MIPS) == 18
+	assert device.engine_cube_bytes(2048, 2048, device.CUBE_FLIP_ROWS) == 6 * 2048 * 2048 * 3
+
+
+def _faces(oracle, w, h, ch, fmt, seed):
+	return oracle.synth(6 * w * h * ch, fmt, ch, seed)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ch", (1, 3, 4))
+@pytest.mark.parametrize("bits", (8, 16))
+def test_every_face_kind_every_flag_device_and_host(built_lib, oracle, ch, bits):
+	from cacaoengine_b200 import _capi as c, device
+
+	device.init()
+	fmt = c.FMT_U8 if bits == 8 else c.FMT_U16
+	for (w, h) in ((64, 64), (5, 3), (1, 1), (96, 40), (256, 256)):
+		src = _faces(oracle, w, h, ch, fmt, 60 + w)
+		face_bytes = w * h * ch * (bits // 8)
+		for flags in (0, device.CUBE_FLIP_ROWS, device.CUBE_MIPS, device.CUBE_FLIP_ROWS | device.CUBE_MIPS):
+			want = oracle.engine_cube(src, w, h, ch, flip=bool(flags & device.CUBE_FLIP_ROWS), mips=bool(flags & device.CUBE_MIPS))
+			assert want.size == device.engine_cube_bytes(w, h, flags)
+			if oracle.have_ref() and not (flags & device.CUBE_MIPS):
+				ref, _ = oracle.ref_engine_cube(src, w, h, ch, flip=bool(flags & device.CUBE_FLIP_ROWS))
+				assert (ref == want).all(), "restatement differs from the reference's own functions"
+			# host memory (pageable numpy), faces as six separate arrays
+			sep = [src.view(np.uint8)[f * face_bytes:(f + 1) * face_bytes].copy() for f in range(6)]
+			got = np.full(want.size, 0xEE, np.uint8)
+			device.engine_cube([s.ctypes.data for s in sep], w, h, ch, fmt, got.ctypes.data, flags, mem=c.MEM_HOST)
+			assert (got == want).all(), ("host", w, h, flags)
+			# device memory: contiguous faces (one launch) and scattered ones (six)
+			a, b = DevBuf(src.nbytes), DevBuf(want.size)
+			device.upload(a.ptr, src)
+			device.engine_cube([a.ptr + f * face_bytes for f in range(6)], w, h, ch, fmt, b.ptr, flags)
+			device.download(got, b.ptr)
+			assert (got == want).all(), ("device", w, h, flags)
+			a.free(), b.free()
+			bufs = [DevBuf(face_bytes) for _ in range(6)]
+			b = DevBuf(want.size)
+			for f in range(6):
+				device.upload(bufs[f].ptr, sep[f])
+			device.engine_cube([x.ptr for x in bufs], w, h, ch, fmt, b.ptr, flags)
+			device.download(got, b.ptr)
+			assert (got == want).all(), ("device, scattered", w, h, flags)
+			for x in bufs:
+				x.free()
+			b.free()
+
+
+@pytest.mark.gpu
+def test_pinned_pipeline_at_engine_size_against_the_compiled_reference(built_lib, oracle):
+	"""Six 1024^2 RGBA16 faces (the engine's case) from pinned buffers, flipped: equal to
+	Convert16To8BitColor + ChangeChannelLayout of the reference itself, face by face."""
+	from cacaoengine_b200 import _capi as c, device
+
+	device.init()
+	w = h = 1024
+	src = _faces(oracle, w, h, 4, c.FMT_U16, 99)
+	nbytes = device.engine_cube_bytes(w, h, device.CUBE_FLIP_ROWS)
+	hp_in, h_in = device.host_alloc(src.nbytes)
+	hp_out, h_out = device.host_alloc(nbytes)
+	h_in[:] = src.view(np.uint8)
+	device.engine_cube([hp_in + f * w * h * 8 for f in range(6)], w, h, 4, c.FMT_U16, hp_out, device.CUBE_FLIP_ROWS, mem=c.MEM_HOST)
+	want = oracle.ref_engine_cube(src, w, h, 4, flip=True)[0] if oracle.have_ref() else oracle.engine_cube(src, w, h, 4, flip=True)
+	assert (h_out == want).all()
+	device.host_free(hp_in), device.host_free(hp_out)
+
+
+@pytest.mark.gpu
+def test_argument_errors(built_lib, oracle):
+	from cacaoengine_b200 import _capi as c, device
+
+	device.init()
+	buf = np.zeros(6 * 16 * 4, np.uint8)
+	out = np.zeros(6 * 16 * 3, np.uint8)
+	ptrs = [buf.ctypes.data + f * 64 for f in range(6)]
+	for bad in (lambda: device.engine_cube(ptrs, 4, 4, 2, c.FMT_U8, out.ctypes.data, 0, mem=c.MEM_HOST),
+				lambda: device.engine_cube(ptrs, 4, 4, 4, c.FMT_F16, out.ctypes.data, 0, mem=c.MEM_HOST),
+				lambda: device.engine_cube(ptrs, 0, 4, 4, c.FMT_U8, out.ctypes.data, 0, mem=c.MEM_HOST),
+				lambda: device.engine_cube(ptrs, 4, 4, 4, c.FMT_U8, out.ctypes.data, 8, mem=c.MEM_HOST),
+				lambda: device.engine_cube(ptrs, 4, 4, 4, c.FMT_U8, buf.ctypes.data + 32, 0, mem=c.MEM_HOST)):
+		with pytest.raises(c.CacaoError):
+			bad()

@@ -233,3 +233,32 @@ def test_units_for_rank_random_sizes(built_lib):
 							cover[f & 7, N - 1 - j] += 1
 			assert (cover == mine).all(), (N, world, rank, folded)
 		assert (owner == 1).all(), (N, world)
+
+
+def test_latitude_dealing_for_host_jobs(built_lib):
+	"""units_for_rank_by_latitude (host-memory jobs: a rank pays for the source rows it uploads): the ranks'
+	lists tile the cube exactly once for any face size and rank count, every rank gets about the same number of
+	output rows, and at 8 ranks a rank's source window is a band of the panorama -- well under half of it --
+	where the cost-balanced device dealing reads most of it."""
+	from cacaoengine_b200 import sharding
+
+	rng = np.random.default_rng(7)
+	for _ in range(20):
+		N = int(rng.choice([1, 3, 16, 31, 100, 257, 1024]))
+		world = int(rng.integers(1, 9))
+		W, H = 4 * max(N, 2), 2 * max(N, 2)
+		owner = np.zeros((6, N), np.int32)
+		rows = []
+		for rank in range(world):
+			us = sharding.units_for_rank_by_latitude(rank, world, N, W, H)
+			assert us == sharding.units_for_rank_by_latitude(rank, world, N, W, H)
+			for u in us:
+				owner[u.face, u.row_begin:u.row_end] += 1
+			rows.append(sum(u.rows for u in us))
+		assert (owner == 1).all(), (N, world)
+		if N >= 100:
+			assert max(rows) - min(rows) <= 2 * (N // (2 * world) + 1), (N, world, rows)
+	W, H, N = 16384, 8192, 4096
+	by_lat = [sharding.source_window(sharding.units_for_rank_by_latitude(r, 8, N, W, H), W, H, N)[1] for r in range(8)]
+	by_cost = [sharding.source_window(sharding.units_for_rank(r, 8, N), W, H, N)[1] for r in range(8)]
+	assert max(by_lat) < 0.45 * H and sum(by_lat) < 0.5 * sum(by_cost), (by_lat, by_cost)
