@@ -108,6 +108,28 @@ namespace cacao {
 		}
 	}
 
+	// How many passes a block of a table shape makes over its contiguous range.  Every block stages the 8 KiB
+	// table first, so short ranges pay for it again and again; but a grid that is not a whole number of waves
+	// leaves SMs idle in the last one, and at the engine's sizes (six 2048^2 faces = 1.5 waves of 4-pass blocks)
+	// that cost more than the table: 0.72 of the roofline against 0.88 for a 64-face batch of the same shape
+	// (profiles/r2_lut_iters_by_size.log).  So: the fewest whole waves that keep a block at <= 8 passes, and the
+	// passes that fill them exactly.  `resident` = blocks the device holds at once (occupancy x SMs).
+	inline uint32_t wave_aligned_iters(uint64_t units, uint64_t units_per_pass, int resident) {
+		if(resident <= 0 || units_per_pass == 0) return 4;
+		const uint64_t per_wave = units_per_pass * static_cast<uint64_t>(resident);
+		const uint64_t waves = (units + per_wave * 8 - 1) / (per_wave * 8);
+		const uint64_t iters = (units + per_wave * waves - 1) / (per_wave * (waves ? waves : 1));
+		return static_cast<uint32_t>(iters < 1 ? 1 : (iters > 8 ? 8 : iters));
+	}
+
+	template<class K>
+	int resident_blocks(K kernel, int threads, size_t smem) {
+		int dev = 0, sms = 0, per_sm = 0;
+		if(cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+		if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess) return 0;
+		return sms * per_sm;
+	}
+
 	template<int SF, int DF, int SC, int DC>
 	cudaError_t launch_convert_wide(const void* src, void* dst, uint64_t n_runs, const uint8_t* lut_global, const uint16_t* lut2_global, uint32_t gray16_cap, cudaStream_t stream, FlipMap flip = FlipMap()) {
 		using S = WideShape<SF, DF, SC, DC>;
@@ -117,10 +139,16 @@ namespace cacao {
 		// 4.47 vs 5.23), on smooth images about level (dev/sweep_lut.py).
 		bool direct = false;
 		if(const char* e = getenv("CACAO_LUT_DIRECT")) direct = S::needs_lut && atoi(e) != 0 && !flip.per_row; // test switch; no flipped form
-		uint32_t iters = S::needs_lut ? (direct ? 16u : 4u) : 1u;
-		if(const char* e = getenv("CACAO_TILE_ITERS")) iters = static_cast<uint32_t>(atoi(e) > 0 ? atoi(e) : 1);
 		const int threads = direct ? 1024 : 256;
 		const size_t smem = S::needs_lut ? (direct ? 65536 : kLut2Bytes) : 0;
+		uint32_t iters = S::needs_lut ? (direct ? 16u : 4u) : 1u;
+		if constexpr(S::needs_lut) {
+			if(!direct) {
+				static const int resident = resident_blocks(convert_wide_kernel<SF, DF, SC, DC, false>, 256, kLut2Bytes); // per shape; one device kind per process
+				iters = wave_aligned_iters(n_runs, static_cast<uint64_t>(threads) * S::U, resident);
+			}
+		}
+		if(const char* e = getenv("CACAO_TILE_ITERS")) iters = static_cast<uint32_t>(atoi(e) > 0 ? atoi(e) : 1);
 		const uint64_t runs_per_block = static_cast<uint64_t>(threads) * S::U * iters;
 		const uint64_t blocks = (n_runs + runs_per_block - 1) / runs_per_block;
 		if(blocks == 0) return cudaSuccess;

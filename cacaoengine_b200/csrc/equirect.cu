@@ -56,8 +56,21 @@ namespace cacao {
 			constexpr int RY = 32 / WX; // a warp covers WX columns x RY rows, a block WX x 4*RY
 			const CubeUnit unit = prm.units[blockIdx.z];
 			const uint32_t i = blockIdx.x * WX + (threadIdx.x % WX);
-			const uint32_t j = unit.row_begin + (blockIdx.y * 4u + threadIdx.y) * RY + threadIdx.x / WX;
 			const uint32_t face = FACES ? unit.face : (unit.face & 7u);
+			uint32_t by = blockIdx.y;
+			if constexpr(!FACES) {
+				// Folded +-Y units run from the face's edge to its centre row, and the rows by the centre (the pole:
+				// neighbouring pixels fan out over all longitudes, every tap its own line) cost up to 2.5x the rows by
+				// the edge.  Blocks are dispatched in index order, so those units are walked centre first: in a sharded
+				// rank's launch -- its whole job, ~0.09 ms -- the expensive blocks then start early instead of being the
+				// tail (longest-processing-time-first, by construction of the index).
+				if((unit.face & kUnitMirror) && (face & 6u) == 2u) {
+					const uint32_t nb = (unit.row_end - unit.row_begin + 4u * RY - 1u) / (4u * RY);
+					if(by >= nb) return;
+					by = nb - 1u - by;
+				}
+			}
+			const uint32_t j = unit.row_begin + (by * 4u + threadIdx.y) * RY + threadIdx.x / WX;
 			const uint32_t half = (prm.N + 1u) >> 1;
 			// a unit flagged kUnitMirror lies in the upper half of the face (row_end <= half, the launcher
 			// sees to that) and stands for its rows AND their mirror rows N-1-j
@@ -533,7 +546,15 @@ namespace cacao {
 			}
 			todo.swap(cut);
 		}
-		std::stable_sort(todo.begin(), todo.end(), [](const CubeUnit& x, const CubeUnit& y) { return x.row_end - x.row_begin > y.row_end - y.row_begin; });
+		// tallest first (launches group similar heights); among equals the +-Y units first: their blocks are the
+		// expensive ones and blockIdx.z is the slowest dispatch index, so they start ahead of the side faces
+		auto polar = [](const CubeUnit& u) { return ((u.face & 6u) == 2u) ? 1 : 0; };
+		static const bool lpt = !(getenv("CACAO_EQUIRECT_NO_LPT") && getenv("CACAO_EQUIRECT_NO_LPT")[0] == '1');
+		std::stable_sort(todo.begin(), todo.end(), [&](const CubeUnit& x, const CubeUnit& y) {
+			const uint32_t hx = x.row_end - x.row_begin, hy = y.row_end - y.row_begin;
+			if(hx != hy) return hx > hy;
+			return lpt && polar(x) > polar(y);
+		});
 		size_t next = 0;
 		while(next < todo.size()) {
 			prm.n_units = 0;
