@@ -549,7 +549,17 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 		same = device.checksum(dst.data_ptr(), px * 3, device=dev, stream=stream) == device.checksum(dst2.data_ptr(), px * 3, device=dev, stream=stream)
 		out[key] = {"value": px / ms / 1e6, "unit": UNIT, "ms_per_step": ms, "n_gpus": 1, "roofline": roof(px * 11, ms, peak, traffic_for(key)),
 					"two_pass": {"value": px / ms2 / 1e6, "ms_per_step": ms2, "note": "cacao_img_convert_batch then cacao_img_flip_rows per face"}, "equals_two_pass": bool(same),
-					"note": "uniform-random samples: the 16->8 table gather is at its worst (bank conflicts); 100 MB problem, partly L2-resident"}
+					"note": "uniform-random samples: the 16->8 table gather is at its worst (bank conflicts, 3.5 data-pipe passes per lookup); a 55 us launch, ~5 us of it ramp and drain"}
+		# the same launch on image-like data (neighbouring samples close in value, so a warp's table lookups fall
+		# on the same words): what real cubemap faces see; the random-data figure above is the worst case
+		smooth = (torch.arange(px * 4, device=f"cuda:{dev}", dtype=torch.int64) // 64 % 65536).to(torch.int16)
+		keep = src.clone()
+		src.view(torch.int16).copy_(smooth)
+		del smooth
+		ms_s = timed_region(torch, dist, 1, fused, steps, 3)
+		out[key]["smooth_data"] = {"value": px / ms_s / 1e6, "unit": UNIT, "ms_per_step": ms_s, "frac": px * 11 / ms_s / 1e6 / peak, "note": "samples vary slowly along a row, as in a photograph"}
+		src.copy_(keep)
+		del keep
 		# ---- the same chain END TO END as the engine would call it: six host faces in, one contiguous flipped RGB8
 		# cube out (cacao_img_engine_cube, CACAO_MEM_HOST) -- against the UNMODIFIED reference doing the same job on
 		# the host cores: Convert16To8BitColor + ChangeChannelLayout per face (Cubemap.cpp:28-31) from oracle/_ref,

@@ -335,6 +335,19 @@ namespace cacao {
 			} else if(faces) {
 				EquirectParams whole = prm; // plain face numbers, as that form reads them
 				for(uint32_t u = 0; u < whole.n_units; ++u) whole.units[u].face &= 7u;
+#ifdef CACAO_ROWS_SWEEP // development build: warp footprint of whole-face launches selectable at run time (dev/sweep_rows.py --wx)
+				if(const char* we = getenv("CACAO_EQUIRECT_WX")) {
+					const int wx = atoi(we);
+					if(small && (wx == 8 || wx == 16 || wx == 32) && wx != WX) {
+						const uint32_t sbh = 4u * (32u / static_cast<uint32_t>(wx));
+						const dim3 sg((half + wx - 1) / wx, (rows + sbh - 1) / sbh, prm.n_units);
+						if(wx == 8) equirect_kernel<F, CH, uint32_t, kQuadFaces, 8><<<sg, block, 0, stream>>>(s8, d8, whole);
+						if(wx == 16) equirect_kernel<F, CH, uint32_t, kQuadFaces, 16><<<sg, block, 0, stream>>>(s8, d8, whole);
+						if(wx == 32) equirect_kernel<F, CH, uint32_t, kQuadFaces, 32><<<sg, block, 0, stream>>>(s8, d8, whole);
+						return cudaGetLastError();
+					}
+				}
+#endif
 				if(small)
 					equirect_kernel<F, CH, uint32_t, kQuadFaces, WX><<<ggrid, block, 0, stream>>>(s8, d8, whole);
 				else

@@ -55,5 +55,13 @@ for name, W, H, N, ch, fmt in shapes:
 				line += f"\n      minb {mb:2d} steps {st}: {t:7.4f} ms ({alg/t/1e6/6551.7:.3f}) {'ok' if ok else 'DIFFERENT'}"
 				if best is None or t < best[0]: best = (t, mb, st)
 		line += f"\n      best: minb {best[1]} steps {best[2]} {best[0]:.4f} ms ({alg/best[0]/1e6/6551.7:.3f})"
+	if "--wx" in sys.argv:  # gather kernel, warp footprint WX x 32/WX (development build)
+		os.environ["CACAO_EQUIRECT_ROWS"] = "0"
+		for wx in (8, 16, 32):
+			os.environ["CACAO_EQUIRECT_WX"] = str(wx)
+			d1.zero_()
+			t = timeit(run1, 10)
+			line += f"\n      gather, warp {wx}x{32 // wx}: {t:7.4f} ms ({alg/t/1e6/6551.7:.3f}) {'ok' if torch.equal(d0, d1) else 'DIFFERENT'}"
+		os.environ.pop("CACAO_EQUIRECT_WX", None)
 	print(line, flush=True)
 	del src, d0, d1

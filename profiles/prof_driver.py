@@ -1,7 +1,7 @@
 """Small driver for ncu captures: launches each hot kernel of the BASELINE configs a few times on
 device-resident synthetic data, through the C ABI only (no torch).  Usage:
 
-    python profiles/prof_driver.py [cfg1] [cfg2] [cfg3] [cfg5] [rgb32f] [fused] [shard8] [cfg4a] [cfg4b] [lut] [--reps N]
+    python profiles/prof_driver.py [cfg1] [cfg2] [cfg3] [cfg5] [rgb32f] [fused] [shard8] [cfg4a] [cfg4b] [lut] [engine] [narrow] [--reps N]
 """
 import os
 import sys
@@ -91,6 +91,25 @@ def main():
 			device.convert_batch(a, b, 2048 * 2048, 64, 4, 3, FMT_U16, FMT_U8)
 		device.sync()
 		device.free(a), device.free(b)
+	if "engine" in which:
+		# bench.py's extra.engine_cube_6x2048sq_rgba16_to_rgb8_flipped: six faces, 16 -> 8 bit, -> RGB, rows mirrored, one launch
+		w = h = 2048
+		a, b = device.malloc(6 * w * h * 8), device.malloc(6 * w * h * 3)
+		device.synth(a, 6 * w * h * 4, FMT_U16, 4, 0xC0FFEE + 9)
+		for _ in range(reps):
+			device.convert_flip(a, b, w, h, 6, 4, 3, FMT_U16, FMT_U8)
+		device.sync()
+		device.free(a), device.free(b)
+	if "narrow" in which:
+		# bench.py's extra.cfg3shape_equirect_8192x4096_*_to_6x2048 legs: config 3's geometry on the narrow formats
+		W, H, N = 8192, 4096, 2048
+		for ch, fmt, bps in ((4, FMT_U8, 1), (4, FMT_U16, 2), (4, FMT_F16, 2), (1, FMT_U8, 1), (3, FMT_U8, 1)):
+			a, b = device.malloc(W * H * ch * bps), device.malloc(6 * N * N * ch * bps)
+			device.synth(a, W * H * ch, fmt, ch, 0xC0FFEE + 3)
+			for _ in range(reps):
+				device.equirect_to_cube(a, W, H, ch, fmt, b, N)
+			device.sync()
+			device.free(a), device.free(b)
 	print("prof_driver done:", which, "launches", device.launch_count())
 
 

@@ -28,8 +28,15 @@ TRAFFIC_KEYS = {
 	"convert_tiles_kernel<0, 0, 3, 4": "cfg4a_16x_4096sq_rgb8_to_rgba8_per_launch",
 	"convert_tiles_kernel<0, 3, 3, 4": "cfg4b_16x_4096sq_rgb8_to_rgba32f_per_launch",
 	"convert_tiles_kernel<1, 0, 4, 3": "lut_64x_2048sq_rgba16_to_rgb8",
-	"convert_wide_kernel<1, 0, 4, 3": "lut_64x_2048sq_rgba16_to_rgb8",
+	"convert_wide_kernel<1, 0, 4, 3, 0, 0": "lut_64x_2048sq_rgba16_to_rgb8",  # plain (not the FLIP instantiation)
+	"convert_wide_kernel<1, 0, 4, 3, 0>": "lut_64x_2048sq_rgba16_to_rgb8",    # round-1 name, before FLIP was a template argument
 	"equirect_kernel<3, 4": "cfg3_equirect_8192x4096_rgba32f_to_6x2048",
+	"convert_wide_kernel<1, 0, 4, 3, 0, 1": "engine_cube_6x2048sq_rgba16_to_rgb8_flipped",  # FLIP instantiation
+	"equirect_rows_kernel<0, 4": "cfg3shape_equirect_8192x4096_rgba8_to_6x2048",
+	"equirect_rows_kernel<0, 1": "cfg3shape_equirect_8192x4096_gray8_to_6x2048",
+	"equirect_rows_kernel<0, 3": "cfg3shape_equirect_8192x4096_rgb8_to_6x2048",
+	"equirect_kernel<1, 4": "cfg3shape_equirect_8192x4096_rgba16_to_6x2048",
+	"equirect_kernel<2, 4": "cfg3shape_equirect_8192x4096_rgba16f_to_6x2048",
 }
 # equirect launches are told apart by their grid (same kernel for cfg3 and cfg5)
 GRID_KEYS = {
@@ -62,6 +69,8 @@ def main():
 						keys[frag] = key
 			# the fused resample + convert instantiations carry the destination format / channels as trailing
 			# template arguments: RGBA32F -> RGBA16F is equirect_kernel<3, 4, unsigned int, 1, 8, 2, 4>
+			if "equirect_kernel<2, 4" in name and not name.split("equirect_kernel<2, 4")[1].startswith(", unsigned int, 1, 8, 2, 4>"):
+				keys.pop("equirect_kernel<2, 4", None)  # a fused F16 instantiation, not the plain RGBA16F resampling
 			if "equirect_kernel<3, 4" in name and ", 2, 4>(" in name:
 				keys = {"equirect_kernel<3, 4": "cfg3_fused_rgba32f_to_rgba16f_cube"} if grid == "(128, 64, 6)" else {}
 			for frag, key in keys.items():
