@@ -610,6 +610,51 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 			out[key]["e2e"] = {"error": repr(e)}
 		del src, mid, dst2, dst
 
+	def engine_texture(key, w, h):
+		"""Tex2D's load chain host -> host: Convert16To8BitColor with the layout kept (Tex2D.cpp:18), Flip and the mip
+		chain (OpenGLTex2D.cpp:16,51) as ONE call, against the reference's Convert16To8BitColor alone on one host
+		thread (the function is single-threaded as shipped; its Flip and the driver's mips are not even counted)."""
+		from cacaoengine_b200 import FMT_U16
+
+		try:
+			from oracle import pyoracle as po
+
+			po.build()
+			flags = device.CUBE_FLIP_ROWS | device.CUBE_MIPS
+			n_in, n_out = w * h * 8, device.engine_texture_bytes(w, h, 4, flags)
+			hp_in, h_in = device.host_alloc(n_in)
+			hp_out, h_out = device.host_alloc(n_out)
+			h_in[:] = po.synth(w * h * 4, po.U16, 4, 0xC0FFEE + 11).view(np.uint8)
+			res = {}
+			for label, pin, pout, reps in (("pinned", hp_in, hp_out, 5), ("pageable", None, None, 3)):
+				if pin is None:
+					pg_in, pg_out = np.array(h_in, copy=True), np.empty(n_out, np.uint8)
+					pin, pout = pg_in.ctypes.data, pg_out.ctypes.data
+				device.engine_texture(pin, w, h, 4, FMT_U16, pout, flags, mem=MEM_HOST, device=dev)
+				t0 = time.perf_counter()
+				for _ in range(reps):
+					device.engine_texture(pin, w, h, 4, FMT_U16, pout, flags, mem=MEM_HOST, device=dev)
+				res[label] = (time.perf_counter() - t0) / reps
+			want = po.engine_texture(np.frombuffer(h_in, np.uint16), w, h, 4, flip=True, mips=True)
+			ok = bool(np.array_equal(want, h_out) and np.array_equal(want, pg_out))
+			entry = {"value": w * h / res["pinned"] / 1e9, "unit": UNIT, "ms_per_step": res["pinned"] * 1e3, "pageable_value": w * h / res["pageable"] / 1e9, "pageable_ms_per_step": res["pageable"] * 1e3,
+					 "h2d_bytes_per_step": n_in, "d2h_bytes_per_step": n_out, "readback_verified": ok, "verified_against": "oracle restatement of the chain (depth table pinned to the compiled reference)",
+					 "path": "cacao_img_engine_texture(CACAO_MEM_HOST, FLIP_ROWS | MIPS): bands of rows upload / convert+mirror / read back overlapped, 12 mip levels computed on the device and read back behind level 0"}
+			if po.have_ref():
+				import ctypes as C
+
+				secs = C.c_double()
+				best = None
+				for _ in range(2):
+					po.ref().ref_batch_depth16to8(h_in.ctypes.data, None, w, h, 4, 1, 1, C.byref(secs))
+					best = secs.value if best is None else min(best, secs.value)
+				entry["cpu_baseline"] = {"value": w * h / best / 1e9, "unit": UNIT, "ms": best * 1e3, "cores": 1, "kind": "reference", "cpu_model": cpu_model(),
+										 "sample": f"whole job minus Flip and mips: libcacaoimage::Convert16To8BitColor as shipped on one {w}x{h} RGBA16 image, one host thread (the function has no threading); best of 2"}
+			out[key] = {"e2e": entry}
+			device.host_free(hp_in), device.host_free(hp_out)
+		except Exception as e:
+			out[key] = {"e2e": {"error": repr(e)}}
+
 	if world == 1:
 		equirect("cfg1_equirect_2048x1024_rgba8_to_6x512", 2048, 1024, 512, 4, FMT_U8, 1, 50, "14.7 MB problem: fits L2, launch-latency bound")
 		equirect("cfg3_equirect_8192x4096_rgba32f_to_6x2048", 8192, 4096, 2048, 4, FMT_F32, 4, 20, e2e=True)
@@ -624,6 +669,7 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 	if world == 1:  # the fusions, after the BASELINE configs
 		equirect("cfg3_fused_rgba32f_to_rgba16f_cube", 8192, 4096, 2048, 4, FMT_F32, 4, 20, "config 3 with the cube written as RGBA16F in the same pass (Spec B.4): resample + format convert", dst=(4, FMT_F16, 2))
 		engine_chain("engine_cube_6x2048sq_rgba16_to_rgb8_flipped", 2048, 2048, 6, 50)
+		engine_texture("engine_texture_4096sq_rgba16_to_rgba8_flipped_mips", 4096, 4096)
 
 	# cfg4: 4096 x 4096^2 RGB8 -> RGBA8 / RGBA32F sharded by image index.  206 GB of input and up to
 	# 1.1 TB of output fit nowhere: each rank walks its logical image range over a

@@ -45,6 +45,8 @@ SIGNATURES = {
 	"cacao_img_convert_flip": (_i, [_i, _vp, _vp, _u32, _u32, _u64, _i, _i, _i, _i, _i, _i, _vp]),
 	"cacao_img_engine_cube_bytes": (_u64, [_u32, _u32, _u32]),
 	"cacao_img_engine_cube": (_i, [_i, C.POINTER(_vp), _u32, _u32, _i, _i, _vp, _u32, _i, _vp]),
+	"cacao_img_engine_texture_bytes": (_u64, [_u32, _u32, _i, _u32]),
+	"cacao_img_engine_texture": (_i, [_i, _vp, _u32, _u32, _i, _i, _vp, _u32, _i, _vp]),
 	"cacao_img_shift_left_u16": (_i, [_i, _vp, _vp, _u64, _u32, _i, _vp]),
 	"cacao_img_downsample2x": (_i, [_i, _vp, _vp, _u32, _u32, _i, _i, _i, _vp]),
 	"cacao_img_unpack_texels": (_i, [_i, _vp, _vp, _u64, C.c_char_p, C.POINTER(C.c_int), _i, _vp]),

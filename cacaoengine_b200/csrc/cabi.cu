@@ -1016,21 +1016,22 @@ int cacao_img_convert(int device, const void* src, void* dst, uint64_t pixels, i
 }
 
 namespace {
-	// Mip levels below a face-major cube level of six w x h RGB8 faces at `level` (device memory); the next levels
-	// are written behind it.  Six stacked faces of even height ARE one image of height 6h for a 2x2 box filter
-	// (no box straddles two faces), so such a level is one launch; odd heights go face by face.
-	int enqueue_cube_mips(uint8_t* level, uint32_t w, uint32_t h, cudaStream_t stream) {
+	// Mip levels below a level of `count` images of w x h pixels, `ch` 8-bit channels, stored back to back (device
+	// memory); the next levels are written behind it.  Stacked images of even height ARE one image of height
+	// count * h for a 2x2 box filter (no box straddles two images), so such a level is one launch; odd heights
+	// go image by image.
+	int enqueue_mips(uint8_t* level, uint32_t w, uint32_t h, uint32_t count, int ch, cudaStream_t stream) {
 		while(w > 1 || h > 1) {
 			const uint32_t wo = w / 2 ? w / 2 : 1, ho = h / 2 ? h / 2 : 1;
-			uint8_t* next = level + 6ull * w * h * 3;
+			uint8_t* next = level + static_cast<uint64_t>(count) * w * h * ch;
 			unsigned launches = 0, total = 0;
 			cudaError_t e = cudaSuccess;
-			if(h % 2 == 0) {
-				e = downsample2x_launch(level, next, w, 6 * h, 3, CACAO_FMT_U8, stream, &launches);
+			if(h % 2 == 0 || count == 1) {
+				e = downsample2x_launch(level, next, w, count * h, ch, CACAO_FMT_U8, stream, &launches);
 				total = launches;
 			} else {
-				for(uint32_t f = 0; f < 6 && e == cudaSuccess; ++f) {
-					e = downsample2x_launch(level + static_cast<uint64_t>(f) * w * h * 3, next + static_cast<uint64_t>(f) * wo * ho * 3, w, h, 3, CACAO_FMT_U8, stream, &launches);
+				for(uint32_t f = 0; f < count && e == cudaSuccess; ++f) {
+					e = downsample2x_launch(level + static_cast<uint64_t>(f) * w * h * ch, next + static_cast<uint64_t>(f) * wo * ho * ch, w, h, ch, CACAO_FMT_U8, stream, &launches);
 					total += launches;
 				}
 			}
@@ -1043,35 +1044,114 @@ namespace {
 		return CACAO_OK;
 	}
 
-	// one face (or six contiguous ones) -> RGB8, optionally bottom row first; RGB8 input is a copy / a row mirror
-	int enqueue_face_to_rgb8(DeviceCtx* c, const void* src, void* dst, uint32_t w, uint32_t h, uint64_t count, int ch, int fmt, bool flip, cudaStream_t stream) {
+	uint64_t chain_bytes(uint32_t w, uint32_t h, uint32_t count, int ch, bool mips) {
+		uint64_t total = static_cast<uint64_t>(count) * w * h * ch;
+		if(mips && w && h) {
+			while(w > 1 || h > 1) {
+				w = w / 2 ? w / 2 : 1;
+				h = h / 2 ? h / 2 : 1;
+				total += static_cast<uint64_t>(count) * w * h * ch;
+			}
+		}
+		return total;
+	}
+
+	// `count` images of w x h pixels stored back to back -> 8-bit samples of dst_ch channels, optionally each image
+	// bottom row first; input that already has the destination's form is a copy / a row mirror
+	int enqueue_to_u8(DeviceCtx* c, const void* src, void* dst, uint32_t w, uint32_t h, uint64_t count, int ch, int fmt, int dst_ch, bool flip, cudaStream_t stream) {
 		const uint64_t ppi = static_cast<uint64_t>(w) * h;
-		if(ch == 3 && fmt == CACAO_FMT_U8) {
+		if(ch == dst_ch && fmt == CACAO_FMT_U8) {
 			if(!flip || h == 1) {
-				CU_TRY(cudaMemcpyAsync(dst, src, ppi * count * 3, cudaMemcpyDefault, stream));
+				CU_TRY(cudaMemcpyAsync(dst, src, ppi * count * ch, cudaMemcpyDefault, stream));
 				return CACAO_OK;
 			}
 			for(uint64_t k = 0; k < count; ++k) {
-				cudaError_t e = flip_rows_launch(static_cast<const uint8_t*>(src) + k * ppi * 3, static_cast<uint8_t*>(dst) + k * ppi * 3, static_cast<uint64_t>(w) * 3, h, c->sm_count, stream);
+				cudaError_t e = flip_rows_launch(static_cast<const uint8_t*>(src) + k * ppi * ch, static_cast<uint8_t*>(dst) + k * ppi * ch, static_cast<uint64_t>(w) * ch, h, c->sm_count, stream);
 				if(e != cudaSuccess) return fail_cuda(e, "flip kernel launch");
 				g_launches.fetch_add(1, std::memory_order_relaxed);
 			}
 			return CACAO_OK;
 		}
-		return enqueue_convert(c, src, dst, ppi * count, ppi, ch, 3, fmt, CACAO_FMT_U8, CACAO_MODE_REF_EXACT, stream, (flip && h > 1) ? w : 0, (flip && h > 1) ? h : 0);
+		return enqueue_convert(c, src, dst, ppi * count, ppi, ch, dst_ch, fmt, CACAO_FMT_U8, CACAO_MODE_REF_EXACT, stream, (flip && h > 1) ? w : 0, (flip && h > 1) ? h : 0);
+	}
+
+	// One piece of a load chain's level 0: `rows` source rows at `src` (host), converted (and mirrored among
+	// themselves when the chain flips) into rows [dst_row, dst_row + rows) of level 0.
+	struct ChainPiece {
+		const uint8_t* src;
+		uint32_t rows, dst_row;
+	};
+
+	// Host-memory load chain: pieces flow upload -> convert -> readback over the three streams (piece k+1 goes up
+	// while piece k is converted and piece k-1 comes back), the mip levels follow the last piece.  Pageable sources
+	// are staged through the pinned ring by the copy pool, pageable destinations drained the same way.
+	int run_chain_host(DeviceCtx* c, const char* what, const std::vector<ChainPiece>& pieces, uint32_t w, uint32_t level_rows, int ch, int fmt, int dst_ch, bool flip, bool mips, uint32_t mip_h, uint32_t mip_count, uint8_t* h_out, uint64_t out_total) {
+		const uint64_t in_row = static_cast<uint64_t>(w) * ch * fmt_bytes(fmt), out_row = static_cast<uint64_t>(w) * dst_ch;
+		uint64_t in_total = 0;
+		for(const ChainPiece& p : pieces) in_total += p.rows * in_row;
+		HostTrace trace(what);
+		trace.in_bytes = in_total;
+		trace.out_bytes = out_total;
+		std::lock_guard<std::mutex> lock(c->pipe_mutex);
+		int rc = ensure_stage(c, in_total, out_total, 1);
+		if(rc) return rc;
+		bool src_pg = false;
+		for(const ChainPiece& p : pieces) src_pg = src_pg || is_pageable(p.src);
+		const bool dst_pg = is_pageable(h_out);
+		trace.path = (src_pg || dst_pg) ? "piecewise, pageable" : "piecewise, pinned";
+		if(src_pg || dst_pg) {
+			rc = ensure_pinned(c, src_pg ? kXferChunk : 0, dst_pg ? kXferChunk : 0);
+			if(rc) return rc;
+		}
+		uint8_t* d_in = c->stage_in[0];
+		uint8_t* d_out = c->stage_out[0];
+		uint64_t ring_use = 0, in_off = 0; // ring slots are reused round robin across pieces
+		std::vector<Segment> back;         // pageable destination: drained after the last piece has been issued
+		for(const ChainPiece& p : pieces) {
+			const uint64_t n_in = p.rows * in_row, n_out = p.rows * out_row, out_off = p.dst_row * out_row;
+			if(is_pageable(p.src) && n_in >= (1u << 20)) {
+				for(uint64_t off = 0; off < n_in; off += kXferChunk, ++ring_use) {
+					const int sl = static_cast<int>(ring_use % kSlots);
+					const uint64_t n = std::min<uint64_t>(kXferChunk, n_in - off);
+					if(ring_use >= kSlots) CU_TRY(cudaEventSynchronize(c->ev_in[sl]));
+					CopyPool::get().copy(c->pin_in[sl], p.src + off, n);
+					CU_TRY(cudaMemcpyAsync(d_in + in_off + off, c->pin_in[sl], n, cudaMemcpyHostToDevice, c->s_in));
+					CU_TRY(cudaEventRecord(c->ev_in[sl], c->s_in));
+				}
+			} else {
+				CU_TRY(cudaMemcpyAsync(d_in + in_off, p.src, n_in, cudaMemcpyHostToDevice, c->s_in));
+			}
+			CU_TRY(cudaEventRecord(c->ev_run[0], c->s_in)); // "this piece has landed"
+			CU_TRY(cudaStreamWaitEvent(c->s_run, c->ev_run[0], 0));
+			rc = enqueue_to_u8(c, d_in + in_off, d_out + out_off, w, p.rows, 1, ch, fmt, dst_ch, flip, c->s_run);
+			if(rc) return rc;
+			CU_TRY(cudaEventRecord(c->ev_run[1], c->s_run));
+			CU_TRY(cudaStreamWaitEvent(c->s_out, c->ev_run[1], 0));
+			if(dst_pg)
+				back.push_back({h_out + out_off, d_out + out_off, static_cast<size_t>(n_out)});
+			else
+				CU_TRY(cudaMemcpyAsync(h_out + out_off, d_out + out_off, n_out, cudaMemcpyDeviceToHost, c->s_out));
+			in_off += n_in;
+		}
+		if(mips) {
+			rc = enqueue_mips(d_out, w, mip_h, mip_count, dst_ch, c->s_run);
+			if(rc) return rc;
+			CU_TRY(cudaEventRecord(c->ev_run[2], c->s_run));
+			CU_TRY(cudaStreamWaitEvent(c->s_out, c->ev_run[2], 0));
+			const uint64_t level0 = level_rows * out_row;
+			if(dst_pg)
+				back.push_back({h_out + level0, d_out + level0, static_cast<size_t>(out_total - level0)});
+			else
+				CU_TRY(cudaMemcpyAsync(h_out + level0, d_out + level0, out_total - level0, cudaMemcpyDeviceToHost, c->s_out));
+		}
+		if(dst_pg) return download_segments(c, back, c->s_out);
+		CU_TRY(cudaStreamSynchronize(c->s_out));
+		return CACAO_OK;
 	}
 }
 
 uint64_t cacao_img_engine_cube_bytes(uint32_t w, uint32_t h, uint32_t flags) {
-	uint64_t total = 6ull * w * h * 3;
-	if((flags & CACAO_CUBE_MIPS) && w && h) {
-		while(w > 1 || h > 1) {
-			w = w / 2 ? w / 2 : 1;
-			h = h / 2 ? h / 2 : 1;
-			total += 6ull * w * h * 3;
-		}
-	}
-	return total;
+	return chain_bytes(w, h, 6, 3, (flags & CACAO_CUBE_MIPS) != 0);
 }
 
 int cacao_img_engine_cube(int device, const void* const* faces, uint32_t w, uint32_t h, int ch, int fmt, void* dst, uint32_t flags, int mem, void* stream) {
@@ -1098,77 +1178,57 @@ int cacao_img_engine_cube(int device, const void* const* faces, uint32_t w, uint
 		bool contiguous = true;
 		for(int f = 1; f < 6; ++f) contiguous = contiguous && static_cast<const uint8_t*>(faces[f]) == static_cast<const uint8_t*>(faces[0]) + f * in_face;
 		if(contiguous) {
-			rc = enqueue_face_to_rgb8(c, faces[0], dst, w, h, 6, ch, fmt, flip, s);
+			rc = enqueue_to_u8(c, faces[0], dst, w, h, 6, ch, fmt, 3, flip, s);
 			if(rc) return rc;
 		} else {
 			for(int f = 0; f < 6; ++f) {
-				rc = enqueue_face_to_rgb8(c, faces[f], static_cast<uint8_t*>(dst) + f * out_face, w, h, 1, ch, fmt, flip, s);
+				rc = enqueue_to_u8(c, faces[f], static_cast<uint8_t*>(dst) + f * out_face, w, h, 1, ch, fmt, 3, flip, s);
 				if(rc) return rc;
 			}
 		}
-		return mips ? enqueue_cube_mips(static_cast<uint8_t*>(dst), w, h, s) : CACAO_OK;
+		return mips ? enqueue_mips(static_cast<uint8_t*>(dst), w, h, 6, 3, s) : CACAO_OK;
 	}
-	// ---- host memory: faces flow upload -> convert -> readback over the three streams
-	HostTrace trace("engine_cube");
-	trace.in_bytes = 6 * in_face;
-	trace.out_bytes = out_total;
-	std::lock_guard<std::mutex> lock(c->pipe_mutex);
-	rc = ensure_stage(c, 6 * in_face, out_total, 1);
+	std::vector<ChainPiece> pieces;
+	for(uint32_t f = 0; f < 6; ++f) pieces.push_back({static_cast<const uint8_t*>(faces[f]), h, f * h});
+	return run_chain_host(c, "engine_cube", pieces, w, 6 * h, ch, fmt, 3, flip, mips, h, 6, static_cast<uint8_t*>(dst), out_total);
+}
+
+uint64_t cacao_img_engine_texture_bytes(uint32_t w, uint32_t h, int ch, uint32_t flags) {
+	return ch_ok(ch) ? chain_bytes(w, h, 1, ch, (flags & CACAO_CUBE_MIPS) != 0) : 0;
+}
+
+int cacao_img_engine_texture(int device, const void* src, uint32_t w, uint32_t h, int ch, int fmt, void* dst, uint32_t flags, int mem, void* stream) {
+	if(!src || !dst) return fail(CACAO_E_EMPTY, "%s", cacao_img_status_string(CACAO_E_EMPTY));
+	if(!ch_ok(ch)) return fail(CACAO_E_BAD_ARG, "channel count must be 1, 3 or 4 (got %d)", ch);
+	if(fmt != CACAO_FMT_U8 && fmt != CACAO_FMT_U16) return fail(CACAO_E_BAD_DEPTH, "%s", cacao_img_status_string(CACAO_E_BAD_DEPTH));
+	if(w == 0 || h == 0) return fail(CACAO_E_ZERO_DIM, "%s", cacao_img_status_string(CACAO_E_ZERO_DIM));
+	if(flags & ~(CACAO_CUBE_FLIP_ROWS | CACAO_CUBE_MIPS)) return fail(CACAO_E_BAD_ARG, "engine_texture: unknown flags 0x%x", flags);
+	if(mem != CACAO_MEM_HOST && mem != CACAO_MEM_DEVICE) return fail(CACAO_E_BAD_ARG, "unknown memory kind %d", mem);
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
 	if(rc) return rc;
-	bool src_pg = false;
-	for(int f = 0; f < 6; ++f) src_pg = src_pg || is_pageable(faces[f]);
-	const bool dst_pg = is_pageable(dst);
-	trace.path = (src_pg || dst_pg) ? "per face, pageable" : "per face, pinned";
-	uint8_t* d_in = c->stage_in[0];
-	uint8_t* d_out = c->stage_out[0];
-	uint8_t* h_out = static_cast<uint8_t*>(dst);
-	// Pageable faces go through the pinned ring in chunks on the upload stream; the copy pool fills slot k+1 while
-	// slot k is on the wire.  A face's kernel waits for its last chunk, its readback for the kernel.
-	uint64_t ring_use = 0; // chunks staged so far (ring slots are reused round robin)
-	if(src_pg || dst_pg) {
-		rc = ensure_pinned(c, src_pg ? kXferChunk : 0, dst_pg ? kXferChunk : 0);
+	const bool flip = (flags & CACAO_CUBE_FLIP_ROWS) != 0, mips = (flags & CACAO_CUBE_MIPS) != 0;
+	const uint64_t in_row = static_cast<uint64_t>(w) * ch * fmt_bytes(fmt), out_row = static_cast<uint64_t>(w) * ch;
+	const uint64_t out_total = cacao_img_engine_texture_bytes(w, h, ch, flags);
+	if(overlaps(src, in_row * h, dst, out_total)) return fail(CACAO_E_BAD_ARG, "engine_texture: source and destination overlap");
+	if(mem == CACAO_MEM_DEVICE) {
+		cudaStream_t s = static_cast<cudaStream_t>(stream);
+		rc = enqueue_to_u8(c, src, dst, w, h, 1, ch, fmt, ch, flip, s);
 		if(rc) return rc;
+		return mips ? enqueue_mips(static_cast<uint8_t*>(dst), w, h, 1, ch, s) : CACAO_OK;
 	}
-	std::vector<Segment> back; // pageable destination: drained after the last face has been issued
-	for(int f = 0; f < 6; ++f) {
-		const uint8_t* from = static_cast<const uint8_t*>(faces[f]);
-		if(is_pageable(from) && in_face >= (1u << 20)) {
-			for(uint64_t off = 0; off < in_face; off += kXferChunk, ++ring_use) {
-				const int sl = static_cast<int>(ring_use % kSlots);
-				const uint64_t n = std::min<uint64_t>(kXferChunk, in_face - off);
-				if(ring_use >= kSlots) CU_TRY(cudaEventSynchronize(c->ev_in[sl]));
-				CopyPool::get().copy(c->pin_in[sl], from + off, n);
-				CU_TRY(cudaMemcpyAsync(d_in + f * in_face + off, c->pin_in[sl], n, cudaMemcpyHostToDevice, c->s_in));
-				CU_TRY(cudaEventRecord(c->ev_in[sl], c->s_in));
-			}
-		} else {
-			CU_TRY(cudaMemcpyAsync(d_in + f * in_face, from, in_face, cudaMemcpyHostToDevice, c->s_in));
-		}
-		CU_TRY(cudaEventRecord(c->ev_run[0], c->s_in)); // "face f has landed"
-		CU_TRY(cudaStreamWaitEvent(c->s_run, c->ev_run[0], 0));
-		rc = enqueue_face_to_rgb8(c, d_in + f * in_face, d_out + f * out_face, w, h, 1, ch, fmt, flip, c->s_run);
-		if(rc) return rc;
-		CU_TRY(cudaEventRecord(c->ev_run[1], c->s_run));
-		CU_TRY(cudaStreamWaitEvent(c->s_out, c->ev_run[1], 0));
-		if(dst_pg)
-			back.push_back({h_out + f * out_face, d_out + f * out_face, static_cast<size_t>(out_face)});
-		else
-			CU_TRY(cudaMemcpyAsync(h_out + f * out_face, d_out + f * out_face, out_face, cudaMemcpyDeviceToHost, c->s_out));
+	// host memory: the image goes through as bands of whole rows (about 32 MiB of the wider side each, at least
+	// four so the three streams overlap); a band is mirrored in itself and lands at the mirrored band
+	const uint64_t wide = std::max(in_row, out_row);
+	uint32_t band = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(h, kXferChunk / wide)));
+	if(h >= 64 && (h + band - 1) / band < 4) band = (h + 3) / 4;
+	std::vector<ChainPiece> pieces;
+	for(uint32_t y0 = 0; y0 < h; y0 += band) {
+		const uint32_t y1 = std::min(h, y0 + band);
+		pieces.push_back({static_cast<const uint8_t*>(src) + y0 * in_row, y1 - y0, flip ? h - y1 : y0});
 	}
-	if(mips) {
-		rc = enqueue_cube_mips(d_out, w, h, c->s_run);
-		if(rc) return rc;
-		CU_TRY(cudaEventRecord(c->ev_run[2], c->s_run));
-		CU_TRY(cudaStreamWaitEvent(c->s_out, c->ev_run[2], 0));
-		const uint64_t level0 = 6 * out_face;
-		if(dst_pg)
-			back.push_back({h_out + level0, d_out + level0, static_cast<size_t>(out_total - level0)});
-		else
-			CU_TRY(cudaMemcpyAsync(h_out + level0, d_out + level0, out_total - level0, cudaMemcpyDeviceToHost, c->s_out));
-	}
-	if(dst_pg) return download_segments(c, back, c->s_out);
-	CU_TRY(cudaStreamSynchronize(c->s_out));
-	return CACAO_OK;
+	return run_chain_host(c, "engine_texture", pieces, w, h, ch, fmt, ch, flip, mips, h, 1, static_cast<uint8_t*>(dst), out_total);
 }
 
 int cacao_img_flip_rows(int device, const void* src, void* dst, uint32_t w, uint32_t h, uint32_t bytes_per_pixel, int mem, void* stream) {

@@ -1,20 +1,21 @@
-// equirect_rows.cu -- equirect -> cubemap for texels of 8 bytes or less: the row-strip kernel.
+// equirect_rows.cu -- equirect -> cubemap, the row-strip kernel: the form the launcher picks for one-channel
+// and 8-bit texels (equirect_rows_preferred), selectable on every plain resampling for tests and A/B timing.
 //
-// The gather kernel of equirect.cu is bound by the L1 data pipe on 16-byte texels and by nothing but
-// INSTRUCTION ISSUE on narrower ones: RGBA8, Gray8 and Gray32F all took ~0.1 ms for 25 Mpixel whatever
-// their bytes, ~95 % of the issue slots busy (profiles/r1b_equirect_cfg1_cfg5_rgb32f_summary.csv).  This
-// kernel computes the same pixels -- Spec B.2 bit for bit, the same four-fold mirror sharing -- with
-// fewer instructions per pixel:
-//   * a thread owns its column (and the mirror column) for R row steps.  On the four side faces the
-//     longitude and sqrt(x^2 + z^2) depend on the column only (SURVEY.md B.2 "structure worth
-//     exploiting"): they are computed once per thread and only the latitude -- one atan2 -- per row
-//     step.  The +-Y faces recompute everything per step (both angles depend on row and column there).
+// The gather kernel of equirect.cu is bound by the L1 data pipe on 16-byte texels and by INSTRUCTION ISSUE on
+// narrow ones: RGBA8, Gray8 and Gray32F all take ~0.1 ms for 25 Mpixel whatever their bytes, 76-79 % of the issue
+// slots busy at full occupancy (profiles/r2_equirect_rows_vs_gather_ncu.txt).  This kernel computes the same
+// pixels -- Spec B.2 bit for bit, the same four-fold mirror sharing, unit lists, flipped output -- with fewer
+// instructions per pixel (DESIGN.md 4.2a has the accounting and the measured gains):
 //   * floor() of the sample position and the truncation of the integer store use the FP32 pipe
 //     (FADD.RM / FADD.RZ with 1.5 * 2^23 / 2^23: the integer lands in the mantissa) instead of the
-//     quarter-rate conversion unit (F2I, FRND);
-//   * tap addresses are one IMAD.WIDE each off two 64-bit row pointers that the mirror column shares;
+//     quarter-rate conversion unit (F2I, FRND); integer results are rounded and truncated as packed pairs;
+//   * tap and store addresses are one IMAD.WIDE each off 64-bit row pointers that the mirror column shares;
 //   * the cube-face table is a handful of selects on the warp-uniform face number, not a jump table;
-//   * one-channel texels filter the pixel and its mirror-column pixel together in packed fp32 (FFMA2).
+//   * one-channel texels filter the pixel and its mirror-column pixel together in packed fp32 (FFMA2);
+//   * LOOP form (one-channel texels of up to two bytes): a thread keeps its column (and the mirror column) for
+//     several row steps.  On the four side faces the longitude and sqrt(x^2 + z^2) depend on the column only
+//     (SURVEY.md B.2 "structure worth exploiting"): they are computed once per thread and only the latitude --
+//     one atan2 -- per row step.  The +-Y faces recompute everything per step.
 // No reference counterpart (tools/cubetool/main.cpp:31-33 has only create / extract).
 #include <algorithm>
 #include <cstdlib>
@@ -127,20 +128,6 @@ namespace cacao {
 			return fma2(vy, fma2(top, m1, bot), top);
 		}
 
-		template<int F, int CH, int DF, int DC>
-		__device__ __forceinline__ void store_filtered(uint8_t* __restrict__ out_px, const float (&out)[CH]) {
-			if constexpr(DF == F && DC == CH) {
-				store_texel<F, CH, false, true>(out_px, out);
-			} else {
-				static_assert(!FmtTraits<F>::is_int, "fused format conversion is defined for float sources");
-				static_assert(DC == CH || (CH == 3 && DC == 4) || (CH == 4 && DC == 3), "fused layout change: RGB <-> RGBA only");
-				float o[DC];
-#pragma unroll
-				for(int c = 0; c < DC; ++c) o[c] = c < CH ? out[c < CH ? c : 0] : 1.0f;
-				store_texel<DF, DC, FmtTraits<DF>::is_int>(out_px, o);
-			}
-		}
-
 		// Integer results that are still packed pairs: + 0.5 and the truncation (round-toward-zero add of 2^23,
 		// see store_texel FASTINT) on both lanes at once.  Returns the two 0x4B00vvvv words.
 		__device__ __forceinline__ void quantise2(uint64_t v, uint32_t& lo, uint32_t& hi) {
@@ -149,12 +136,12 @@ namespace cacao {
 		}
 
 		// one output pixel
-		template<int F, int CH, int DF, int DC>
+		template<int F, int CH>
 		__device__ __forceinline__ void sample_one(const RowPtrs& rp, float xs, int W, uint32_t sbpp, uint8_t* __restrict__ out_px) {
 			constexpr bool kBiased = FmtTraits<F>::is_int;
 			float a[CH], b[CH], c[CH], d[CH];
 			const float fx = fetch_taps<F, CH>(rp, xs, W, sbpp, a, b, c, d);
-			if constexpr(CH == 4 && kBiased && DF == F && DC == CH) {
+			if constexpr(CH == 4 && kBiased) {
 				// four integer channels: filter, round and truncate as two packed pairs
 				const uint64_t vx = pk2(fx, fx), vy = pk2(rp.fy, rp.fy);
 				const uint64_t o01 = lerp2p<true>(vx, vy, pk2(a[0], a[1]), pk2(b[0], b[1]), pk2(c[0], c[1]), pk2(d[0], d[1]));
@@ -179,12 +166,12 @@ namespace cacao {
 					const float bot = fmaf(fx, d[k] - c[k], c[k] - kOff);
 					out[k] = fmaf(rp.fy, bot - top, top);
 				}
-				store_filtered<F, CH, DF, DC>(out_px, out);
+				store_texel<F, CH, false, true>(out_px, out);
 			}
 		}
 
 		// an output pixel and its mirror-column pixel (same rows, two longitudes)
-		template<int F, int CH, int DF, int DC>
+		template<int F, int CH>
 		__device__ __forceinline__ void sample_pair(const RowPtrs& rp, float xs_i, float xs_m, int W, uint32_t sbpp, uint8_t* __restrict__ out_i, uint8_t* __restrict__ out_m, bool has_m) {
 			if constexpr(CH == 1) {
 				// one channel: the two pixels share the packed-fp32 lanes
@@ -193,7 +180,7 @@ namespace cacao {
 				const float fx0 = fetch_taps<F, 1>(rp, xs_i, W, sbpp, a0, b0, c0, d0);
 				const float fx1 = fetch_taps<F, 1>(rp, xs_m, W, sbpp, a1, b1, c1, d1);
 				const uint64_t o = lerp2p<kBiased>(pk2(fx0, fx1), pk2(rp.fy, rp.fy), pk2(a0[0], a1[0]), pk2(b0[0], b1[0]), pk2(c0[0], c1[0]), pk2(d0[0], d1[0]));
-				if constexpr(kBiased && DF == F) {
+				if constexpr(kBiased) {
 					uint32_t s0, s1;
 					quantise2(o, s0, s1);
 					if constexpr(F == CACAO_FMT_U8) {
@@ -206,12 +193,12 @@ namespace cacao {
 				} else {
 					float r0[1], r1[1];
 					asm("mov.b64 {%0,%1}, %2;" : "=f"(r0[0]), "=f"(r1[0]) : "l"(o));
-					store_filtered<F, 1, DF, DC>(out_i, r0);
-					if(has_m) store_filtered<F, 1, DF, DC>(out_m, r1);
+					store_texel<F, 1, false, true>(out_i, r0);
+					if(has_m) store_texel<F, 1, false, true>(out_m, r1);
 				}
 			} else {
-				sample_one<F, CH, DF, DC>(rp, xs_i, W, sbpp, out_i);
-				if(has_m) sample_one<F, CH, DF, DC>(rp, xs_m, W, sbpp, out_m);
+				sample_one<F, CH>(rp, xs_i, W, sbpp, out_i);
+				if(has_m) sample_one<F, CH>(rp, xs_m, W, sbpp, out_m);
 			}
 		}
 
@@ -220,9 +207,9 @@ namespace cacao {
 		// LOOP: the thread walks `steps` rows that lie a block's height apart (the block sweeps a compact patch
 		// of the face per step) and keeps what depends on the column only -- on the four side faces both
 		// longitudes and sqrt(x^2 + z^2) -- across the steps; !LOOP: one row per thread, nothing carried.
-		// Unit lists with and without the mirror flag, flipped output (row_add / row_mul) and fused conversion
-		// all go through this one form.
-		template<int F, int CH, int WX, int DF, int DC, bool LOOP, int MINB>
+		// Unit lists with and without the mirror flag and flipped output (row_add / row_mul) all go through this one
+		// form; the fused conversions (Spec B.4) stay with the gather kernel.
+		template<int F, int CH, int WX, bool LOOP, int MINB>
 		__global__ void __launch_bounds__(128, MINB) equirect_rows_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, EquirectParams prm, Scales scl, uint32_t steps) {
 			constexpr uint32_t RY = 32 / WX, BH = 4 * RY; // a warp covers WX x RY pixels per step, a block WX x BH
 			const CubeUnit unit = prm.units[blockIdx.z];
@@ -259,12 +246,12 @@ namespace cacao {
 				const float theta = atan2_spec(ya, rxz);
 				const RowPtrs rt = row_ptrs(src, fmaf(-theta, prm.pc.ky, prm.pc.cy), prm, scl);
 				uint8_t* orow = at(dst, frow + j * prm.row_mul, scl.out_pitch);
-				sample_pair<F, CH, DF, DC>(rt, xs_a, xs_b, W, scl.sbpp, at(orow, i, scl.dbpp), at(orow, im, scl.dbpp), has_m);
+				sample_pair<F, CH>(rt, xs_a, xs_b, W, scl.sbpp, at(orow, i, scl.dbpp), at(orow, im, scl.dbpp), has_m);
 				const uint32_t jm = N - 1u - j;
 				if(mirror && jm != j) { // uniform per block: units are indexed by blockIdx.z
 					const RowPtrs rm = polar ? rt : row_ptrs(src, fmaf(theta, prm.pc.ky, prm.pc.cy), prm, scl);
 					uint8_t* mrow = at(dst, frow + jm * prm.row_mul, scl.out_pitch);
-					sample_pair<F, CH, DF, DC>(rm, xs_c, xs_d, W, scl.sbpp, at(mrow, i, scl.dbpp), at(mrow, im, scl.dbpp), has_m);
+					sample_pair<F, CH>(rm, xs_c, xs_d, W, scl.sbpp, at(mrow, i, scl.dbpp), at(mrow, im, scl.dbpp), has_m);
 				}
 			}
 		}
@@ -282,7 +269,7 @@ namespace cacao {
 
 		template<int F, int CH>
 		cudaError_t launch_rows(const void* src, void* dst, const EquirectParams& prm, int sm_count, cudaStream_t stream) {
-			constexpr int sbpp = FmtTraits<F>::bytes * CH, dbpp = sbpp, DF = F, DC = CH;
+			constexpr int sbpp = FmtTraits<F>::bytes * CH, dbpp = sbpp; // same format and layout out as in
 			// a warp's stores should fill whole 32-byte sectors; wider texels prefer squarer footprints
 			constexpr int WX = sbpp >= 4 ? 8 : (sbpp >= 2 ? 16 : 32);
 			constexpr uint32_t BH = 4 * (32 / WX);
@@ -308,9 +295,9 @@ namespace cacao {
 #define CACAO_ROWS_CASE(MB)                                                                                                     \
 	if(m == MB) {                                                                                                                \
 		if(se)                                                                                                                   \
-			equirect_rows_kernel<F, CH, WX, DF, DC, true, MB><<<grid_for(steps), block, 0, stream>>>(s8, d8, prm, scl, steps);   \
+			equirect_rows_kernel<F, CH, WX, true, MB><<<grid_for(steps), block, 0, stream>>>(s8, d8, prm, scl, steps);   \
 		else                                                                                                                     \
-			equirect_rows_kernel<F, CH, WX, DF, DC, false, MB><<<grid_for(1), block, 0, stream>>>(s8, d8, prm, scl, 1);          \
+			equirect_rows_kernel<F, CH, WX, false, MB><<<grid_for(1), block, 0, stream>>>(s8, d8, prm, scl, 1);          \
 		return cudaGetLastError();                                                                                               \
 	}
 				CACAO_ROWS_CASE(8)
@@ -321,7 +308,7 @@ namespace cacao {
 			}
 #endif
 			if(!Plan::loop) steps = 1;
-			equirect_rows_kernel<F, CH, WX, DF, DC, Plan::loop, Plan::minb><<<grid_for(steps), block, 0, stream>>>(s8, d8, prm, scl, steps);
+			equirect_rows_kernel<F, CH, WX, Plan::loop, Plan::minb><<<grid_for(steps), block, 0, stream>>>(s8, d8, prm, scl, steps);
 			return cudaGetLastError();
 		}
 

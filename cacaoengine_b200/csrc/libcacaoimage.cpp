@@ -257,6 +257,27 @@ namespace libcacaoimage {
 		return cube;
 	}
 
+	TextureU8 EngineTexture(const Image& image, bool flipRows, bool mips, int device) {
+		if(!(image.w > 0 && image.h > 0)) check(CACAO_E_ZERO_DIM);
+		if(!(image.bitsPerChannel == 8 || image.bitsPerChannel == 16)) check(CACAO_E_BAD_DEPTH);
+		const int ch = static_cast<int>(image.layout);
+		if(image.data.size() < static_cast<std::size_t>(image.w) * image.h * ch * (image.bitsPerChannel / 8)) throw std::runtime_error("Image data buffer is smaller than w * h * channels * bytes per channel!");
+		TextureU8 tex;
+		tex.w = image.w;
+		tex.h = image.h;
+		tex.layout = image.layout;
+		const uint32_t flags = (flipRows ? CACAO_CUBE_FLIP_ROWS : 0u) | (mips ? CACAO_CUBE_MIPS : 0u);
+		tex.data.resize(cacao_img_engine_texture_bytes(image.w, image.h, ch, flags));
+		std::size_t off = 0;
+		for(unsigned int lw = image.w, lh = image.h;; lw = lw / 2 ? lw / 2 : 1, lh = lh / 2 ? lh / 2 : 1) {
+			tex.levelOffset.push_back(off);
+			off += static_cast<std::size_t>(lw) * lh * ch;
+			if(!mips || (lw == 1 && lh == 1)) break;
+		}
+		check(cacao_img_engine_texture(device, image.data.data(), image.w, image.h, ch, fmt_of_bits(image.bitsPerChannel), tex.data.data(), flags, CACAO_MEM_HOST, nullptr));
+		return tex;
+	}
+
 	ImageEx Flip(const ImageEx& src) {
 		if(!(src.w > 0 && src.h > 0)) check(CACAO_E_ZERO_DIM);
 		if(src.data.empty()) check(CACAO_E_EMPTY);

@@ -119,6 +119,15 @@ def engine_cube(faces, w: int, h: int, ch: int, fmt: int, dst: int, flags: int =
 	capi.check(capi.lib().cacao_img_engine_cube(device, ptrs, w, h, ch, fmt, dst, flags, mem, stream))
 
 
+def engine_texture_bytes(w: int, h: int, ch: int, flags: int = 0) -> int:
+	return int(capi.lib().cacao_img_engine_texture_bytes(w, h, ch, flags))
+
+
+def engine_texture(src: int, w: int, h: int, ch: int, fmt: int, dst: int, flags: int = 0, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> None:
+	"""cacao_img_engine_texture: the Tex2D load chain -- 16 -> 8 bit when needed (layout kept), row mirror, mip chain."""
+	capi.check(capi.lib().cacao_img_engine_texture(device, src, w, h, ch, fmt, dst, flags, mem, stream))
+
+
 def equirect_to_cube(src: int, W: int, H: int, ch: int, fmt: int, dst: int, N: int, face_mask: int = 0x3F, row_begin: int = 0, row_end: int | None = None, src_row0: int = 0, src_rows: int | None = None, mem: int = capi.MEM_DEVICE, device: int = -1, stream=None) -> None:
 	capi.check(capi.lib().cacao_img_equirect_to_cube(device, src, W, H, src_row0, H if src_rows is None else src_rows, ch, fmt, dst, N, face_mask, row_begin, N if row_end is None else row_end, mem, stream))
 

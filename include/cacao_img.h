@@ -150,6 +150,19 @@ int cacao_img_engine_cube(int device, const void* const* faces, uint32_t w, uint
 						  uint32_t flags, int mem, void* stream);
 
 /*
+ * The same for a 2-D texture.  Cacao::Tex2D::Tex2D converts a 16-bit image with Convert16To8BitColor and keeps its
+ * layout (engine/src/core/Tex2D.cpp:18); the GL backend then Flips it and asks the driver for its mip levels
+ * (engine/src/opengl/impls/OpenGLTex2D.cpp:16,51).  One call: src (w x h pixels, `ch` channels of U8 or U16) ->
+ * dst = level 0 (w x h pixels of `ch` 8-bit channels; CACAO_CUBE_FLIP_ROWS: bottom row first) followed, with
+ * CACAO_CUBE_MIPS, by every mip level down to 1 x 1 (cacao_img_engine_texture_bytes sizes dst; 0 for a bad
+ * channel count).  Host memory: the image flows through in bands of rows, upload / conversion / readback
+ * overlapped; the mip levels are computed on the device from level 0 and follow it.
+ */
+uint64_t cacao_img_engine_texture_bytes(uint32_t w, uint32_t h, int ch, uint32_t flags);
+int cacao_img_engine_texture(int device, const void* src, uint32_t w, uint32_t h, int ch, int fmt, void* dst,
+							 uint32_t flags, int mem, void* stream);
+
+/*
  * dst[k] = (uint16_t)(src[k] << shift) over `samples` 16-bit samples, shift in [0,15].
  *   replaces the 12 -> 16 bit widening loop of the JPEG decoder, libs/image/src/JPEG.cpp:79-82
  *   (`imgDataSixteen[i] = uint16_t(twelveBit[i]) << 4`), one of the per-pixel loops next to the

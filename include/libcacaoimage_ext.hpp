@@ -64,6 +64,17 @@ namespace libcacaoimage {
 	};
 	CubeRGB8 EngineCube(const std::array<Image, 6>& faces, bool flipRows = false, bool mips = false, int device = -1);
 
+	// The same for a 2-D texture: Cacao::Tex2D::Tex2D's Convert16To8BitColor (engine/src/core/Tex2D.cpp:18, layout
+	// kept), the GL backend's Flip (engine/src/opengl/impls/OpenGLTex2D.cpp:16) and, on request, the mip levels it
+	// asks the driver for (:51) -- one pipelined pass.  data = level 0, then every mip level down to 1 x 1.
+	struct TextureU8 {
+		unsigned int w = 0, h = 0;
+		Image::Layout layout = Image::Layout::RGBA;
+		std::vector<unsigned char> data;
+		std::vector<std::size_t> levelOffset; // byte offset of every level in data (one entry without mips)
+	};
+	TextureU8 EngineTexture(const Image& image, bool flipRows = false, bool mips = false, int device = -1);
+
 	// Equirectangular panorama -> six N x N faces in the order +X,-X,+Y,-Y,+Z,-Z
 	// (right,left,up,down,front,back), same layout and sample format as the source.
 	// devices: CUDA ordinals to spread face/row-band work units over (empty = current device).

@@ -285,6 +285,22 @@ def engine_cube(faces: np.ndarray, w: int, h: int, ch: int, flip: bool = False, 
 	return np.concatenate(levels)
 
 
+def engine_texture(img: np.ndarray, w: int, h: int, ch: int, flip: bool = False, mips: bool = False) -> np.ndarray:
+	"""The Tex2D load chain from the restatement: depth16to8 when 16-bit (layout kept, Tex2D.cpp:18), row mirror
+	(OpenGLTex2D.cpp:16), downsample2x per level (the GL path's glGenerateMipmap): level 0, then every mip level."""
+	s = np.ascontiguousarray(img).reshape(-1)
+	if s.dtype == np.uint16:
+		s = depth16to8(s)
+	s = s.reshape(h, w * ch)
+	level = np.ascontiguousarray(s[::-1] if flip else s).reshape(-1)
+	out, lw, lh = [level], w, h
+	while mips and (lw > 1 or lh > 1):
+		level = downsample2x(level, lw, lh, ch, U8)
+		lw, lh = max(1, lw // 2), max(1, lh // 2)
+		out.append(level)
+	return np.concatenate(out)
+
+
 def ref_depth16to8(src: np.ndarray, w: int, h: int, ch: int) -> np.ndarray:
 	bits = 8 if src.dtype == np.uint8 else 16
 	s = np.ascontiguousarray(src).reshape(-1)

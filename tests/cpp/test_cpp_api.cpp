@@ -287,6 +287,13 @@ int main(int argc, char** argv) {
 			const Image step = ToRGB8(faces[f]);
 			EXPECT(std::memcmp(mixed.Face(f), step.data.data(), step.data.size()) == 0);
 		}
+		// EngineTexture: Tex2D's chain -- 16 -> 8 bit with the layout kept, Flip, mip levels -- against the calls it replaces
+		const TextureU8 tex = EngineTexture(faces[0], true, true);
+		const Image step = Flip(Convert16To8BitColor(faces[0]));
+		EXPECT(tex.w == 48 && tex.h == 32 && tex.layout == L::RGBA && tex.levelOffset.size() == 6 && tex.levelOffset[1] == 48 * 32 * 4);
+		EXPECT(std::memcmp(tex.data.data(), step.data.data(), step.data.size()) == 0);
+		const ImageEx mip1 = Downsample2x(FromImage(step));
+		EXPECT(std::memcmp(tex.data.data() + tex.levelOffset[1], mip1.data.data(), mip1.data.size()) == 0);
 		faces[3].w = 47;
 		bool threw = false;
 		try {

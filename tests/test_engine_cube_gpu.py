@@ -98,3 +98,63 @@ def test_argument_errors(built_lib, oracle):
 				lambda: device.engine_cube(ptrs, 4, 4, 4, c.FMT_U8, buf.ctypes.data + 32, 0, mem=c.MEM_HOST)):
 		with pytest.raises(c.CacaoError):
 			bad()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ch", (1, 3, 4))
+@pytest.mark.parametrize("bits", (8, 16))
+def test_texture_chain_every_kind_every_flag(built_lib, oracle, ch, bits):
+	"""cacao_img_engine_texture: Tex2D's load chain (Convert16To8BitColor with the layout kept, Tex2D.cpp:18; Flip
+	and the mip levels of OpenGLTex2D.cpp:16,51) -- device memory, pageable host memory in one band and in several
+	(a 2.4 Mpixel image goes through as four bands, each mirrored in itself and placed at the mirrored band)."""
+	from cacaoengine_b200 import _capi as c, device
+
+	device.init()
+	fmt = c.FMT_U8 if bits == 8 else c.FMT_U16
+	for (w, h) in ((64, 64), (5, 3), (1, 1), (97, 41), (1600, 1501)):
+		src = oracle.synth(w * h * ch, fmt, ch, 80 + w)
+		for flags in (0, device.CUBE_FLIP_ROWS, device.CUBE_MIPS, device.CUBE_FLIP_ROWS | device.CUBE_MIPS):
+			want = oracle.engine_texture(src, w, h, ch, flip=bool(flags & device.CUBE_FLIP_ROWS), mips=bool(flags & device.CUBE_MIPS))
+			assert want.size == device.engine_texture_bytes(w, h, ch, flags)
+			if oracle.have_ref() and bits == 16 and flags == 0:
+				assert (oracle.ref_depth16to8(src, w, h, ch) == want).all()
+			got = np.full(want.size, 0xEE, np.uint8)
+			device.engine_texture(src.ctypes.data, w, h, ch, fmt, got.ctypes.data, flags, mem=c.MEM_HOST)
+			assert (got == want).all(), ("host", w, h, flags)
+			a, b = DevBuf(src.nbytes), DevBuf(want.size)
+			device.upload(a.ptr, src)
+			device.engine_texture(a.ptr, w, h, ch, fmt, b.ptr, flags)
+			device.download(got, b.ptr)
+			assert (got == want).all(), ("device", w, h, flags)
+			a.free(), b.free()
+	assert device.engine_texture_bytes(4, 4, 2) == 0
+	with pytest.raises(c.CacaoError):
+		device.engine_texture(src.ctypes.data, 4, 4, 4, c.FMT_F32, got.ctypes.data, 0, mem=c.MEM_HOST)
+
+
+@pytest.mark.gpu
+def test_host_register_pins_caller_memory(built_lib, oracle, capfd, monkeypatch):
+	"""cacao_img_host_register: memory the caller owns (a numpy array here; a std::vector's storage or a
+	shared-memory segment in bench.py's sharded e2e leg) becomes DMA-able in place -- the host-memory call takes
+	the pinned pipeline instead of staging through the ring -- and the result is unchanged."""
+	from cacaoengine_b200 import _capi as c, device
+
+	device.init()
+	px = 3 << 20
+	src = oracle.synth(px * 4, c.FMT_U8, 4, 71)
+	out = np.empty(px * 4, np.float16)
+	want = oracle.convert(src, 4, 4, c.FMT_U8, c.FMT_F16)
+	monkeypatch.setenv("CACAO_TRACE", "1")
+	device.convert(src.ctypes.data, out.ctypes.data, px, 4, 4, c.FMT_U8, c.FMT_F16, mem=c.MEM_HOST)
+	assert (out.view(np.uint16) == want.view(np.uint16)).all()
+	device.host_register(src.ctypes.data, src.nbytes)
+	device.host_register(out.ctypes.data, out.nbytes)
+	try:
+		out[:] = 0
+		device.convert(src.ctypes.data, out.ctypes.data, px, 4, 4, c.FMT_U8, c.FMT_F16, mem=c.MEM_HOST)
+		assert (out.view(np.uint16) == want.view(np.uint16)).all()
+	finally:
+		device.host_unregister(src.ctypes.data)
+		device.host_unregister(out.ctypes.data)
+	with pytest.raises(c.CacaoError):
+		device.host_register(0, 16)
