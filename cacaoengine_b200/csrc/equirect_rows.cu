@@ -202,54 +202,6 @@ namespace cacao {
 			}
 		}
 
-		// ---- four-byte texels (RGBA8, Gray32F): all taps of a thread's pixels in flight before any is used --------
-		// Left to the compiler each pixel is load, wait, filter, store, then the next pixel's loads: the L1 latency is
-		// exposed once per pixel.  Raw words cost one register per tap, so a thread can afford to issue the sixteen
-		// loads of its four pixels back to back and wait for them once.
-		struct RawTaps {
-			uint32_t a, b, c, d;
-			float fx;
-		};
-		__device__ __forceinline__ RawTaps fetch_raw4(const RowPtrs& rp, float xs, int W, uint32_t sbpp) {
-			RawTaps t;
-			int x0;
-			t.fx = floor_split(xs, x0);
-			int x1 = x0 + 1;
-			if(x0 < 0) x0 = W - 1;
-			if(x1 >= W) x1 = 0;
-			t.a = __ldg(reinterpret_cast<const uint32_t*>(at(rp.p0, static_cast<uint32_t>(x0), sbpp)));
-			t.b = __ldg(reinterpret_cast<const uint32_t*>(at(rp.p0, static_cast<uint32_t>(x1), sbpp)));
-			t.c = __ldg(reinterpret_cast<const uint32_t*>(at(rp.p1, static_cast<uint32_t>(x0), sbpp)));
-			t.d = __ldg(reinterpret_cast<const uint32_t*>(at(rp.p1, static_cast<uint32_t>(x1), sbpp)));
-			return t;
-		}
-		// RGBA8: filter, round, truncate as two packed pairs, store one word
-		__device__ __forceinline__ void finish_rgba8(const RawTaps& t, float fy, uint8_t* __restrict__ out_px) {
-			const uint32_t w4[4] = {t.a, t.b, t.c, t.d};
-			float v[4][4];
-#pragma unroll
-			for(int k = 0; k < 4; ++k) {
-				const uint32_t one[4] = {w4[k], 0u, 0u, 0u};
-				words_to_floats<CACAO_FMT_U8, 4, true>(one, v[k]);
-			}
-			const uint64_t vx = pk2(t.fx, t.fx), vy = pk2(fy, fy);
-			const uint64_t o01 = lerp2p<true>(vx, vy, pk2(v[0][0], v[0][1]), pk2(v[1][0], v[1][1]), pk2(v[2][0], v[2][1]), pk2(v[3][0], v[3][1]));
-			const uint64_t o23 = lerp2p<true>(vx, vy, pk2(v[0][2], v[0][3]), pk2(v[1][2], v[1][3]), pk2(v[2][2], v[2][3]), pk2(v[3][2], v[3][3]));
-			uint32_t s0, s1, s2, s3;
-			quantise2(o01, s0, s1);
-			quantise2(o23, s2, s3);
-			*reinterpret_cast<uint32_t*>(out_px) = __byte_perm(__byte_perm(s0, s1, 0x0040u), __byte_perm(s2, s3, 0x0040u), 0x5410u);
-		}
-		// Gray32F: the pixel and its mirror-column pixel share the packed lanes
-		__device__ __forceinline__ void finish_gray32f(const RawTaps& ti, const RawTaps& tm, float fy, uint8_t* __restrict__ out_i, uint8_t* __restrict__ out_m, bool has_m) {
-			const uint64_t o = lerp2p<false>(pk2(ti.fx, tm.fx), pk2(fy, fy), pk2(__uint_as_float(ti.a), __uint_as_float(tm.a)), pk2(__uint_as_float(ti.b), __uint_as_float(tm.b)),
-											 pk2(__uint_as_float(ti.c), __uint_as_float(tm.c)), pk2(__uint_as_float(ti.d), __uint_as_float(tm.d)));
-			uint32_t r0, r1;
-			asm("mov.b64 {%0,%1}, %2;" : "=r"(r0), "=r"(r1) : "l"(o));
-			*reinterpret_cast<uint32_t*>(out_i) = r0;
-			if(has_m) *reinterpret_cast<uint32_t*>(out_m) = r1;
-		}
-
 		// One thread = column i and its mirror column N-1-i of one unit, plus -- for units flagged kUnitMirror --
 		// the mirror rows N-1-j: four pixels from one projection, exactly as equirect_kernel shares them.
 		// LOOP: the thread walks `steps` rows that lie a block's height apart (the block sweeps a compact patch
@@ -294,31 +246,6 @@ namespace cacao {
 				const float theta = atan2_spec(ya, rxz);
 				const RowPtrs rt = row_ptrs(src, fmaf(-theta, prm.pc.ky, prm.pc.cy), prm, scl);
 				uint8_t* orow = at(dst, frow + j * prm.row_mul, scl.out_pitch);
-				if constexpr(!LOOP && ((F == CACAO_FMT_U8 && CH == 4) || (F == CACAO_FMT_F32 && CH == 1))) {
-					// four-byte texels: every load of the thread's (up to) four pixels first, then the arithmetic
-					const uint32_t jq = N - 1u - j;
-					const bool both = mirror && jq != j; // uniform per block but for the centre row of an odd face
-					const RowPtrs rq = (polar || !both) ? rt : row_ptrs(src, fmaf(theta, prm.pc.ky, prm.pc.cy), prm, scl);
-					const RawTaps t0 = fetch_raw4(rt, xs_a, W, scl.sbpp), t1 = fetch_raw4(rt, xs_b, W, scl.sbpp);
-					RawTaps t2 = t0, t3 = t1;
-					if(both) {
-						t2 = fetch_raw4(rq, xs_c, W, scl.sbpp);
-						t3 = fetch_raw4(rq, xs_d, W, scl.sbpp);
-					}
-					uint8_t* qrow = at(dst, frow + jq * prm.row_mul, scl.out_pitch);
-					if constexpr(CH == 4) {
-						finish_rgba8(t0, rt.fy, at(orow, i, scl.dbpp));
-						if(has_m) finish_rgba8(t1, rt.fy, at(orow, im, scl.dbpp));
-						if(both) {
-							finish_rgba8(t2, rq.fy, at(qrow, i, scl.dbpp));
-							if(has_m) finish_rgba8(t3, rq.fy, at(qrow, im, scl.dbpp));
-						}
-					} else {
-						finish_gray32f(t0, t1, rt.fy, at(orow, i, scl.dbpp), at(orow, im, scl.dbpp), has_m);
-						if(both) finish_gray32f(t2, t3, rq.fy, at(qrow, i, scl.dbpp), at(qrow, im, scl.dbpp), has_m);
-					}
-					continue;
-				}
 				sample_pair<F, CH>(rt, xs_a, xs_b, W, scl.sbpp, at(orow, i, scl.dbpp), at(orow, im, scl.dbpp), has_m);
 				const uint32_t jm = N - 1u - j;
 				if(mirror && jm != j) { // uniform per block: units are indexed by blockIdx.z
