@@ -21,7 +21,7 @@ LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libcacaoimage_b200.so")
 TOOL = os.path.join(LIBDIR, "ce-cubetool")
 
-CU_SOURCES = ["convert_u8.cu", "convert_u16.cu", "convert_f16.cu", "convert_f32.cu", "equirect.cu", "equirect_rows.cu", "mip.cu", "misc_kernels.cu", "cabi.cu"]
+CU_SOURCES = ["convert_u8.cu", "convert_u16.cu", "convert_f16.cu", "convert_f32.cu", "equirect.cu", "equirect_rows.cu", "equirect_tma.cu", "mip.cu", "misc_kernels.cu", "cabi.cu"]
 CXX_SOURCES = ["libcacaoimage.cpp"]
 TOOL_SOURCES = ["tools/cubetool/main.cpp", "tools/cubetool/project.cpp", "tools/cubetool/create.cpp", "tools/cubetool/extract.cpp", "tools/cubetool/imageio.cpp", "tools/cubetool/vp8l.cpp", "tools/cubetool/xjc.cpp"]
 

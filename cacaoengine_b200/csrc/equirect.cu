@@ -118,193 +118,13 @@ namespace cacao {
 			}
 		}
 
-		// ---- staged variant: source footprints copied to shared memory by the TMA unit --------------
-		//
-		// EXPERIMENT, off by default (CACAO_EQUIRECT_STAGED=1 turns it on; tests keep it bit-identical).
-		// The gather kernel above is bound by L1 data-pipe wavefronts (ncu: l1tex__data_pipe_lsu_wavefronts
-		// 76 %; dev/l1_align_bench.cu shows tap alignment is irrelevant, the excess passes are the miss path).
-		// Here one thread asks the TMA unit (cp.async.bulk, one row segment per copy) to place the
-		// block's source footprint -- the bounding box of all taps of its 32x8 pixels, one box per
-		// mirror side -- in shared memory; taps then are LDS.128, which has no line granularity.  A side
-		// whose box is too large (polar caps), crosses the u=0/1 seam or is not 16-byte addressable
-		// falls back to global gathers, so results never depend on which path ran.
-		// Measured on B200 (dev/ab_equirect.py): 20-30 % SLOWER than the gather kernel on every shape
-		// (cfg3 0.208 -> 0.260 ms, cfg5 0.787 -> 1.002 ms): the block now waits for its whole footprint
-		// before any pixel starts (two __syncthreads + an mbarrier wait), which costs more latency
-		// hiding than the cheaper taps give back, and HBM traffic was already compulsory.  Kept as the
-		// measured answer to "stage source tiles in shared memory with TMA".
-		constexpr int kBoxW = 48; // texels
-		constexpr int kBoxH = 16; // rows
-
-		template<int BPP>
-		__device__ __forceinline__ void lds_texel(uint32_t saddr, uint32_t (&w)[4]) {
-			if constexpr(BPP == 16)
-				asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(saddr));
-			else if constexpr(BPP == 8)
-				asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(saddr));
-			else
-				asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[0]) : "r"(saddr));
-		}
-
-		template<int F, int CH>
-		__global__ void __launch_bounds__(256) equirect_staged_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, EquirectParams prm) {
-			constexpr int bpp = FmtTraits<F>::bytes * CH;
-			constexpr int kAlign = 16 / bpp;          // texels per 16 bytes (bpp in {4, 8, 16})
-			constexpr int kPitch = kBoxW * bpp;       // bytes per staged row
-			__shared__ __align__(128) uint8_t box[2][kBoxH * kPitch];
-			__shared__ __align__(8) unsigned long long bar;
-			__shared__ int red[8][6];
-			__shared__ int plan[8]; // xa_al, use_a, xb_al, use_b, rmin
-
-			const CubeUnit unit = prm.units[blockIdx.z];
-			const uint32_t i = blockIdx.x * 32u + threadIdx.x;
-			const uint32_t j = unit.row_begin + blockIdx.y * 8u + threadIdx.y;
-			const uint32_t face = unit.face;
-			const uint32_t half = (prm.N + 1u) >> 1;
-			const bool active = (i < half) && (j < unit.row_end);
-			const uint32_t ic = min(i, half - 1u), jc = min(j, unit.row_end - 1u); // inactive threads shadow the nearest real pixel
-			const uint32_t im = prm.N - 1u - ic;
-			const int tid = threadIdx.y * 32 + threadIdx.x;
-			if(tid == 0) {
-				asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&bar))));
-				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-			}
-
-			const float sc = face_coord(ic, prm.pc);
-			const float tc = face_coord(jc, prm.pc);
-			float xa, ya, za, xb, yb, zb;
-			face_direction(face, sc, tc, xa, ya, za);
-			face_direction(face, -sc, tc, xb, yb, zb);
-			const float rphi = atan2_core(fabsf(za), fabsf(xa));
-			const float rxz = sqrtf(fmaf(xa, xa, za * za));
-			const float theta = atan2_spec(ya, rxz);
-			const float ys = fmaf(-theta, prm.pc.ky, prm.pc.cy);
-			const float fy0 = floorf(ys);
-			const float fy = ys - fy0;
-			int y0 = static_cast<int>(fy0);
-			int y1 = y0 + 1;
-			const int W = static_cast<int>(prm.W), H = static_cast<int>(prm.H);
-			y0 = min(max(y0, 0), H - 1);
-			y1 = min(max(y1, 0), H - 1);
-			const int r0 = min(max(y0 - static_cast<int>(prm.src_row0), 0), static_cast<int>(prm.src_rows) - 1);
-			const int r1 = min(max(y1 - static_cast<int>(prm.src_row0), 0), static_cast<int>(prm.src_rows) - 1);
-			const float xs_a = fmaf(atan2_quadrant(rphi, xa, za), prm.pc.kx, prm.pc.cx);
-			const float xs_b = fmaf(atan2_quadrant(rphi, xb, zb), prm.pc.kx, prm.pc.cx);
-			const float fxa0 = floorf(xs_a), fxb0 = floorf(xs_b);
-			const int xa0 = static_cast<int>(fxa0), xb0 = static_cast<int>(fxb0);
-
-			// ---- block-wide bounding boxes (inactive threads repeat a valid pixel, so they do not widen them)
-			const unsigned full = 0xFFFFFFFFu;
-			const int wxa_lo = __reduce_min_sync(full, xa0), wxa_hi = __reduce_max_sync(full, xa0);
-			const int wxb_lo = __reduce_min_sync(full, xb0), wxb_hi = __reduce_max_sync(full, xb0);
-			const int wr_lo = __reduce_min_sync(full, r0), wr_hi = __reduce_max_sync(full, r1);
-			if(threadIdx.x == 0) {
-				red[threadIdx.y][0] = wxa_lo; red[threadIdx.y][1] = wxa_hi;
-				red[threadIdx.y][2] = wxb_lo; red[threadIdx.y][3] = wxb_hi;
-				red[threadIdx.y][4] = wr_lo;  red[threadIdx.y][5] = wr_hi;
-			}
-			__syncthreads();
-			if(tid == 0) {
-				int lo[3] = {red[0][0], red[0][2], red[0][4]}, hi[3] = {red[0][1], red[0][3], red[0][5]};
-				for(int w = 1; w < 8; ++w) {
-					lo[0] = min(lo[0], red[w][0]); hi[0] = max(hi[0], red[w][1]);
-					lo[1] = min(lo[1], red[w][2]); hi[1] = max(hi[1], red[w][3]);
-					lo[2] = min(lo[2], red[w][4]); hi[2] = max(hi[2], red[w][5]);
-				}
-				const int rows = hi[2] - lo[2] + 1;
-				uint32_t bytes = 0;
-				int al[2], bw[2], use[2];
-				for(int sde = 0; sde < 2; ++sde) {
-					al[sde] = lo[sde] - (((lo[sde] % kAlign) + kAlign) % kAlign);
-					bw[sde] = ((hi[sde] + 1 - al[sde] + 1 + kAlign - 1) / kAlign) * kAlign; // covers x0 .. x0+1
-					use[sde] = (rows <= kBoxH) && (lo[sde] >= 0) && (al[sde] + bw[sde] <= W) && (bw[sde] <= kBoxW);
-					if(use[sde]) bytes += static_cast<uint32_t>(rows * bw[sde] * bpp);
-				}
-				plan[0] = al[0]; plan[1] = use[0]; plan[2] = al[1]; plan[3] = use[1]; plan[4] = lo[2];
-				const uint32_t bar_s = static_cast<uint32_t>(__cvta_generic_to_shared(&bar));
-				if(bytes) {
-					asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
-					for(int sde = 0; sde < 2; ++sde) {
-						if(!use[sde]) continue;
-						const uint32_t seg = static_cast<uint32_t>(bw[sde] * bpp);
-						for(int r = 0; r < rows; ++r) {
-							const uint8_t* g = src + (static_cast<size_t>(lo[2] + r) * prm.W + static_cast<size_t>(al[sde])) * bpp;
-							const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(&box[sde][r * kPitch]));
-							asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(g), "r"(seg), "r"(bar_s) : "memory");
-						}
-					}
-				} else {
-					asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
-				}
-			}
-			__syncthreads();
-			const int xa_al = plan[0], use_a = plan[1], xb_al = plan[2], use_b = plan[3], rmin = plan[4];
-			{ // wait for the copies (phase 0)
-				const uint32_t bar_s = static_cast<uint32_t>(__cvta_generic_to_shared(&bar));
-				uint32_t done = 0;
-				while(!done) {
-					asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar_s) : "memory");
-				}
-			}
-			if(!active) return;
-
-			uint8_t* orow = dst + (static_cast<size_t>(face) * prm.N + j) * prm.N * bpp;
-			const size_t row0 = static_cast<size_t>(r0) * prm.W, row1 = static_cast<size_t>(r1) * prm.W;
-#pragma unroll
-			for(int sde = 0; sde < 2; ++sde) {
-				if(sde == 1 && im == i) break;
-				const float xs = sde ? xs_b : xs_a;
-				const float fx = xs - (sde ? fxb0 : fxa0);
-				int x0 = sde ? xb0 : xa0;
-				float a[CH], b[CH], c[CH], d[CH], out[CH];
-				if(sde ? use_b : use_a) {
-					const int al = sde ? xb_al : xa_al;
-					const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(&box[sde][0]));
-					const uint32_t o0 = base + static_cast<uint32_t>((r0 - rmin) * kPitch + (x0 - al) * bpp);
-					const uint32_t o1 = base + static_cast<uint32_t>((r1 - rmin) * kPitch + (x0 - al) * bpp);
-					uint32_t w[4] = {0, 0, 0, 0};
-					lds_texel<bpp>(o0, w); words_to_floats<F, CH>(w, a);
-					lds_texel<bpp>(o0 + bpp, w); words_to_floats<F, CH>(w, b);
-					lds_texel<bpp>(o1, w); words_to_floats<F, CH>(w, c);
-					lds_texel<bpp>(o1 + bpp, w); words_to_floats<F, CH>(w, d);
-				} else {
-					int x1 = x0 + 1;
-					if(x0 < 0) x0 += W;
-					if(x0 >= W) x0 -= W;
-					if(x1 < 0) x1 += W;
-					if(x1 >= W) x1 -= W;
-					load_texel<F, CH>(src + (row0 + static_cast<size_t>(x0)) * bpp, a);
-					load_texel<F, CH>(src + (row0 + static_cast<size_t>(x1)) * bpp, b);
-					load_texel<F, CH>(src + (row1 + static_cast<size_t>(x0)) * bpp, c);
-					load_texel<F, CH>(src + (row1 + static_cast<size_t>(x1)) * bpp, d);
-				}
-#pragma unroll
-				for(int k = 0; k < CH; ++k) {
-					const float top = fmaf(fx, b[k] - a[k], a[k]);
-					const float bot = fmaf(fx, d[k] - c[k], c[k]);
-					out[k] = fmaf(fy, bot - top, top);
-				}
-				store_texel<F, CH>(orow + static_cast<size_t>(sde ? im : i) * bpp, out);
-			}
-		}
-
 		template<int F, int CH, int DF = F, int DC = CH>
 		cudaError_t launch(const void* src, void* dst, const EquirectParams& prm, cudaStream_t stream) {
 			constexpr bool fused = DF != F || DC != CH;
-			dim3 block(32, 8, 1); // the staged experiment needs 32 x 8; the gather kernel re-shapes below
 			const uint32_t half = (prm.N + 1u) >> 1;
 			uint32_t max_rows = 0;
 			for(uint32_t u = 0; u < prm.n_units; ++u) max_rows = std::max(max_rows, prm.units[u].row_end - prm.units[u].row_begin);
-			const dim3 grid((half + 31) / 32, (max_rows + 7) / 8, prm.n_units);
 			constexpr int bpp = FmtTraits<F>::bytes * CH;
-			if constexpr(!fused && (bpp == 4 || bpp == 8 || bpp == 16)) {
-				const char* e = getenv("CACAO_EQUIRECT_STAGED");
-				const bool staged = e && e[0] == '1' && prm.row_mul == 1u && (static_cast<uint64_t>(prm.W) * bpp) % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
-				if(staged) {
-					equirect_staged_kernel<F, CH><<<grid, block, 0, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), prm);
-					return cudaGetLastError();
-				}
-			}
 			const bool small = static_cast<uint64_t>(prm.src_rows) * prm.W < (1ull << 32);
 			// gather kernel: 128-thread blocks (16 per SM at 32 registers), four warps stacked vertically.
 			// A warp covers WX columns x 32/WX rows.  Square-ish footprints (8 x 4) touch fewer distinct
@@ -313,7 +133,7 @@ namespace cacao {
 			// 0.180 -> 0.169 ms, cfg5 0.682 -> 0.657 ms; 16 x 2 is level, 4 x 8 loses again).  WX stays
 			// wide enough for a warp's store to fill whole 32-byte sectors.
 			constexpr int WX = bpp >= 4 ? 8 : (bpp >= 2 ? 16 : 32);
-			block = dim3(32, 4, 1);
+			const dim3 block(32, 4, 1);
 			// units that stand for a band and its mirror band (flagged by pair_mirror_units) need the
 			// four-fold kernel; it also serves unflagged units of the same launch two-fold
 			bool quad = false;
@@ -518,15 +338,13 @@ namespace cacao {
 			if(u.face > 5 || u.row_begin >= u.row_end) continue;
 			todo.push_back(u);
 		}
-		// test / A-B switches: two-fold sharing only; the staged experiment knows plain units only
+		// test / A-B switch: two-fold sharing only
 		const char* qe = getenv("CACAO_EQUIRECT_NO_QUAD");
-		const char* se = getenv("CACAO_EQUIRECT_STAGED");
-		if(!(qe && qe[0] == '1') && (fused || flip_rows || !(se && se[0] == '1'))) todo = pair_mirror_units(todo, N);
+		if(!(qe && qe[0] == '1')) todo = pair_mirror_units(todo, N);
 		// which kernel: the row-strip kernel where it measured ahead (one-channel and 8-bit texels: those shapes are
 		// bound by instruction issue, which is what it saves), the gather kernel everywhere else
 		bool use_rows = equirect_rows_supported(ch, fmt, dst_ch, dst_fmt, W, H) && equirect_rows_preferred(ch, fmt);
 		if(const char* re = getenv("CACAO_EQUIRECT_ROWS")) use_rows = re[0] == '1' ? equirect_rows_supported(ch, fmt, dst_ch, dst_fmt, W, H) : (re[0] == '0' ? false : use_rows);
-		if(se && se[0] == '1' && !fused && !flip_rows) use_rows = false; // the staged experiment
 		int sm_count = 148;
 		if(use_rows) {
 			static int cached[64] = {};
@@ -537,6 +355,23 @@ namespace cacao {
 					if(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached[dev] = n;
 				}
 				if(cached[dev] > 0) sm_count = cached[dev];
+			}
+		}
+		// the tensor-map TMA experiment: a whole cube (six folded whole faces), stored as is
+		if(const char* te = getenv("CACAO_EQUIRECT_TMA")) {
+			bool whole = te[0] == '1' && !fused && !flip_rows && todo.size() == 6 && equirect_tma_supported(ch, fmt, W, H, src);
+			uint32_t seen = 0;
+			for(const CubeUnit& u : todo) {
+				whole = whole && (u.face & kUnitMirror) && u.row_begin == 0 && u.row_end == ((N + 1u) >> 1);
+				seen |= 1u << (u.face & 7u);
+			}
+			if(whole && seen == 0x3Fu) {
+				int dev = 0, sms = 148;
+				if(cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+				prm.n_units = 0;
+				cudaError_t e = equirect_tma_launch(src, dst, ch, fmt, prm, sms, stream);
+				if(e == cudaSuccess && launches) *launches = 1;
+				if(e != cudaErrorNotSupported) return e;
 			}
 		}
 		uint32_t hmin = 0xFFFFFFFFu, hmax = 0;

@@ -47,6 +47,11 @@ namespace cacao {
 	bool equirect_rows_preferred(int ch, int fmt);
 	cudaError_t equirect_rows_launch(const void* src, void* dst, int ch, int fmt, const EquirectParams& prm, int sm_count, cudaStream_t stream);
 
+	// EXPERIMENT (equirect_tma.cu, CACAO_EQUIRECT_TMA=1): whole cubes of 4- / 8-byte texels through a persistent,
+	// warp-specialised kernel whose source footprints are staged by 2-D tensor-map TMA copies in a four-stage ring.
+	bool equirect_tma_supported(int ch, int fmt, uint32_t W, uint32_t H, const void* src);
+	cudaError_t equirect_tma_launch(const void* src, void* dst, int ch, int fmt, const EquirectParams& prm, int sm_count, cudaStream_t stream);
+
 	// The folding step of equirect_launch_units on its own (host only): mirror bands of the input become
 	// single units flagged kUnitMirror; units with face > 5 or no rows are dropped.
 	std::vector<CubeUnit> pair_mirror_units(const std::vector<CubeUnit>& in, uint32_t N);

@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 import torch
 from cacaoengine_b200 import FMT_F16, FMT_F32, FMT_U8, FMT_U16, device
 device.init(0)
-KEY = sys.argv[1] if len(sys.argv) > 1 else "CACAO_EQUIRECT_STAGED"
+KEY = sys.argv[1] if len(sys.argv) > 1 else "CACAO_EQUIRECT_TMA"
 VAL = sys.argv[2] if len(sys.argv) > 2 else "1"
 ONLY = sys.argv[3] if len(sys.argv) > 3 else ""
 stream = torch.cuda.current_stream().cuda_stream

@@ -339,28 +339,6 @@ def test_fused_resample_host_path_and_full_size_property(oracle):
 		buf.free()
 
 
-@pytest.mark.parametrize("fmt,ch", [(3, 4), (2, 4), (0, 4), (3, 1), (1, 4)], ids=["f32x4", "f16x4", "u8x4", "f32x1", "u16x4"])
-def test_tma_staged_variant_is_bit_identical(oracle, monkeypatch, fmt, ch):
-	"""The experimental TMA-staged kernel (CACAO_EQUIRECT_STAGED=1; cp.async.bulk row segments into
-	shared memory, LDS taps, per-side fallback to global gathers) must give exactly the gather kernel's
-	result: boxes that fit, boxes that do not (polar caps), the seam, odd sizes and row windows."""
-	from cacaoengine_b200 import device
-
-	monkeypatch.setenv("CACAO_EQUIRECT_STAGED", "1")
-	for (W, H, N) in ((512, 256, 128), (1000, 500, 333), (256, 128, 400)):
-		src = oracle.synth(W * H * ch, fmt, ch, 17)
-		want = oracle.equirect_to_cube(src, W, H, ch, fmt, N)
-		assert same_bits(gpu_equirect_device(src, W, H, ch, fmt, N), want), (W, H, N)
-	W, H, N = 512, 256, 96
-	src = oracle.synth(W * H * ch, fmt, ch, 18)
-	full = oracle.equirect_to_cube(src, W, H, ch, fmt, N)
-	for f in (0, 2, 5):
-		win = device.equirect_src_window(W, H, N, 1 << f, 24, 72)
-		part = gpu_equirect_device(src, W, H, ch, fmt, N, 1 << f, 24, 72, window=win)
-		sl = slice((f * N + 24) * N * ch, (f * N + 72) * N * ch)
-		assert same_bits(part[sl], full[sl]), f
-
-
 @pytest.mark.parametrize("fmt", FMTS, ids=[NAME[f] for f in FMTS])
 @pytest.mark.parametrize("ch", (1, 3, 4))
 @pytest.mark.parametrize("rows", ("0", "1"), ids=["gather", "row-strip"])
@@ -407,6 +385,24 @@ def test_both_resampling_kernels_on_every_shape(oracle, monkeypatch, fmt, ch, ro
 		part = gpu_equirect_device(src, W, H, ch, fmt, N, 1 << f, 20, 61, window=win)
 		sl = slice((f * N + 20) * N * ch, (f * N + 61) * N * ch)
 		assert same_bits(part[sl], full[sl]), f
+
+
+@pytest.mark.parametrize("fmt,ch", [(0, 4), (3, 1), (1, 4), (2, 4)], ids=["u8x4", "f32x1", "u16x4", "f16x4"])
+def test_tensor_map_tma_ring_is_bit_identical(oracle, monkeypatch, fmt, ch):
+	"""The tensor-map experiment (CACAO_EQUIRECT_TMA=1, equirect_tma.cu: persistent warp-specialised CTAs, four boxes
+	per 32 x 8 tile staged by cp.async.bulk.tensor.2d through a four-stage mbarrier ring, LDS taps) must give exactly
+	the product kernels' result: tiles whose boxes fit, tiles that fall back to gathers (polar caps, the seam on
+	the back face, magnifications the box does not cover), even / odd faces, faces smaller than a tile, more
+	tiles than CTAs (the ring wraps many times), and a CTA count forced to one per SM."""
+	monkeypatch.setenv("CACAO_EQUIRECT_TMA", "1")
+	for (W, H, N) in ((512, 256, 128), (1024, 512, 255), (256, 128, 400), (2048, 1024, 96), (64, 32, 7), (4096, 2048, 1024)):
+		src = oracle.synth(W * H * ch, fmt, ch, 19)
+		want = oracle.equirect_to_cube(src, W, H, ch, fmt, N)
+		assert same_bits(gpu_equirect_device(src, W, H, ch, fmt, N), want), (W, H, N)
+	monkeypatch.setenv("CACAO_EQUIRECT_TMA_CTAS", "1")
+	W, H, N = 1024, 512, 256
+	src = oracle.synth(W * H * ch, fmt, ch, 20)
+	assert same_bits(gpu_equirect_device(src, W, H, ch, fmt, N), oracle.equirect_to_cube(src, W, H, ch, fmt, N))
 
 
 def test_seam_and_poles(oracle):
