@@ -291,6 +291,11 @@ namespace {
 		}
 	};
 
+	struct DeviceCtx;
+	// A host-memory pipeline that fails half way must not return while copies that read or write the CALLER's
+	// buffers are still queued on its streams: the caller is free to release them as soon as it sees the error.
+	int drained(DeviceCtx* c, int rc);
+
 	int resolve_device(int device, int* out) {
 		int n = 0;
 		cudaError_t e = cudaGetDeviceCount(&n);
@@ -303,6 +308,17 @@ namespace {
 		if(device >= n || device >= kMaxDevices) return fail(CACAO_E_BAD_ARG, "device %d out of range (%d visible)", device, n);
 		*out = device;
 		return CACAO_OK;
+	}
+
+	int drained(DeviceCtx* c, int rc) {
+		if(rc == CACAO_OK) return rc; // the success paths end in a synchronise of their own
+		const std::string why = t_last_error;
+		cudaStreamSynchronize(c->s_in);
+		cudaStreamSynchronize(c->s_run);
+		cudaStreamSynchronize(c->s_out);
+		cudaGetLastError();
+		t_last_error = why;
+		return rc;
 	}
 
 	void destroy_ctx(DeviceCtx* c) {
@@ -809,7 +825,13 @@ namespace {
 	}
 
 	template<class Launch>
+	int run_host_op_body(DeviceCtx* c, const char* what, const void* src, uint64_t in_bytes, void* dst, uint64_t out_bytes, Launch launch);
+	template<class Launch>
 	int run_host_op(DeviceCtx* c, const char* what, const void* src, uint64_t in_bytes, void* dst, uint64_t out_bytes, Launch launch) {
+		return drained(c, run_host_op_body(c, what, src, in_bytes, dst, out_bytes, launch));
+	}
+	template<class Launch>
+	int run_host_op_body(DeviceCtx* c, const char* what, const void* src, uint64_t in_bytes, void* dst, uint64_t out_bytes, Launch launch) {
 		HostTrace trace(what);
 		trace.in_bytes = in_bytes;
 		trace.out_bytes = out_bytes;
@@ -992,7 +1014,7 @@ int cacao_img_convert_batch(int device, const void* src, void* dst, uint64_t pix
 	// the kernels read through the non-coherent path and promise the compiler disjoint buffers
 	if(overlaps(src, pixels * src_ch * fmt_bytes(src_fmt), dst, pixels * dst_ch * fmt_bytes(dst_fmt))) return fail(CACAO_E_BAD_ARG, "convert: source and destination overlap (the conversion is not an in-place operation)");
 	if(mem == CACAO_MEM_DEVICE) return enqueue_convert(c, src, dst, pixels, pixels_per_image, src_ch, dst_ch, src_fmt, dst_fmt, mode, static_cast<cudaStream_t>(stream));
-	return convert_host_pipeline(c, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), pixels, pixels_per_image, src_ch, dst_ch, src_fmt, dst_fmt, mode);
+	return drained(c, convert_host_pipeline(c, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), pixels, pixels_per_image, src_ch, dst_ch, src_fmt, dst_fmt, mode));
 }
 
 int cacao_img_convert_flip(int device, const void* src, void* dst, uint32_t w, uint32_t h, uint64_t count, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, int mem, void* stream) {
@@ -1008,7 +1030,7 @@ int cacao_img_convert_flip(int device, const void* src, void* dst, uint32_t w, u
 	if(overlaps(src, pixels * src_ch * fmt_bytes(src_fmt), dst, pixels * dst_ch * fmt_bytes(dst_fmt))) return fail(CACAO_E_BAD_ARG, "convert_flip: source and destination overlap (a row mirror cannot run in place)");
 	if(mem == CACAO_MEM_DEVICE) return enqueue_convert(c, src, dst, pixels, ppi, src_ch, dst_ch, src_fmt, dst_fmt, mode, static_cast<cudaStream_t>(stream), w, h);
 	// host memory: the same chunked upload / kernel / readback pipeline, cut into bands of whole rows
-	return convert_host_pipeline(c, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), pixels, ppi, src_ch, dst_ch, src_fmt, dst_fmt, mode, w, h);
+	return drained(c, convert_host_pipeline(c, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), pixels, ppi, src_ch, dst_ch, src_fmt, dst_fmt, mode, w, h));
 }
 
 int cacao_img_convert(int device, const void* src, void* dst, uint64_t pixels, int src_ch, int dst_ch, int src_fmt, int dst_fmt, int mode, int mem, void* stream) {
@@ -1190,7 +1212,7 @@ int cacao_img_engine_cube(int device, const void* const* faces, uint32_t w, uint
 	}
 	std::vector<ChainPiece> pieces;
 	for(uint32_t f = 0; f < 6; ++f) pieces.push_back({static_cast<const uint8_t*>(faces[f]), h, f * h});
-	return run_chain_host(c, "engine_cube", pieces, w, 6 * h, ch, fmt, 3, flip, mips, h, 6, static_cast<uint8_t*>(dst), out_total);
+	return drained(c, run_chain_host(c, "engine_cube", pieces, w, 6 * h, ch, fmt, 3, flip, mips, h, 6, static_cast<uint8_t*>(dst), out_total));
 }
 
 uint64_t cacao_img_engine_texture_bytes(uint32_t w, uint32_t h, int ch, uint32_t flags) {
@@ -1228,7 +1250,7 @@ int cacao_img_engine_texture(int device, const void* src, uint32_t w, uint32_t h
 		const uint32_t y1 = std::min(h, y0 + band);
 		pieces.push_back({static_cast<const uint8_t*>(src) + y0 * in_row, y1 - y0, flip ? h - y1 : y0});
 	}
-	return run_chain_host(c, "engine_texture", pieces, w, h, ch, fmt, ch, flip, mips, h, 1, static_cast<uint8_t*>(dst), out_total);
+	return drained(c, run_chain_host(c, "engine_texture", pieces, w, h, ch, fmt, ch, flip, mips, h, 1, static_cast<uint8_t*>(dst), out_total));
 }
 
 int cacao_img_flip_rows(int device, const void* src, void* dst, uint32_t w, uint32_t h, uint32_t bytes_per_pixel, int mem, void* stream) {
@@ -1413,7 +1435,7 @@ int cacao_img_equirect_to_cube(int device, const void* src, uint32_t W, uint32_t
 		faces[f] = static_cast<uint8_t*>(dst) + static_cast<uint64_t>(f) * N * N * bpp;
 		if(face_mask & (1u << f)) units[n++] = {f, row_begin, row_end};
 	}
-	return equirect_host_pipeline(c, static_cast<const uint8_t*>(src), W, H, src_row0, src_rows, ch, fmt, faces, N, units, n, ch, fmt, 0);
+	return drained(c, equirect_host_pipeline(c, static_cast<const uint8_t*>(src), W, H, src_row0, src_rows, ch, fmt, faces, N, units, n, ch, fmt, 0));
 }
 
 namespace {
@@ -1451,7 +1473,7 @@ int cacao_img_equirect_to_cube_units_host_cvt(int device, const void* src, uint3
 	if(rc) return rc;
 	CubeUnit whole[6];
 	const CubeUnit* list = units_or_whole_cube(units, n_units, N, whole);
-	return equirect_host_pipeline(c, static_cast<const uint8_t*>(src), W, H, src_row0, src_rows, ch, fmt, reinterpret_cast<uint8_t* const*>(faces), N, list, n_units, dst_ch, dst_fmt, flags);
+	return drained(c, equirect_host_pipeline(c, static_cast<const uint8_t*>(src), W, H, src_row0, src_rows, ch, fmt, reinterpret_cast<uint8_t* const*>(faces), N, list, n_units, dst_ch, dst_fmt, flags));
 }
 
 int cacao_img_equirect_to_cube_units_host(int device, const void* src, uint32_t W, uint32_t H, uint32_t src_row0, uint32_t src_rows, int ch, int fmt, void* const* faces, uint32_t N, const cacao_cube_unit* units, uint32_t n_units) {

@@ -158,3 +158,37 @@ def test_host_register_pins_caller_memory(built_lib, oracle, capfd, monkeypatch)
 		device.host_unregister(out.ctypes.data)
 	with pytest.raises(c.CacaoError):
 		device.host_register(0, 16)
+
+
+@pytest.mark.gpu
+def test_load_chains_from_concurrent_threads(built_lib, oracle):
+	"""The engine loads assets from thread-pool tasks: cube chains, texture chains and a resampling call issued
+	from eight threads at once (ctypes drops the GIL) share one device's staging buffers and streams behind the
+	pipeline mutex -- every result must still be exact."""
+	from concurrent.futures import ThreadPoolExecutor
+
+	from cacaoengine_b200 import _capi as c, device
+
+	device.init()
+	cube_src = oracle.synth(6 * 128 * 96 * 4, c.FMT_U16, 4, 91)
+	cube_want = oracle.engine_cube(cube_src, 128, 96, 4, flip=True, mips=True)
+	tex_src = oracle.synth(700 * 500 * 3, c.FMT_U16, 3, 92)
+	tex_want = oracle.engine_texture(tex_src, 700, 500, 3, flip=True, mips=True)
+	pano = oracle.synth(256 * 128 * 4, c.FMT_U8, 4, 93)
+	pano_want = oracle.equirect_to_cube(pano, 256, 128, 4, c.FMT_U8, 48)
+
+	def run(k):
+		if k % 3 == 0:
+			got = np.empty(cube_want.size, np.uint8)
+			device.engine_cube([cube_src.ctypes.data + f * 128 * 96 * 8 for f in range(6)], 128, 96, 4, c.FMT_U16, got.ctypes.data, device.CUBE_FLIP_ROWS | device.CUBE_MIPS, mem=c.MEM_HOST)
+			return bool((got == cube_want).all())
+		if k % 3 == 1:
+			got = np.empty(tex_want.size, np.uint8)
+			device.engine_texture(tex_src.ctypes.data, 700, 500, 3, c.FMT_U16, got.ctypes.data, device.CUBE_FLIP_ROWS | device.CUBE_MIPS, mem=c.MEM_HOST)
+			return bool((got == tex_want).all())
+		got = np.empty(pano_want.size, np.uint8)
+		c.check(c.lib().cacao_img_equirect_to_cube(-1, pano.ctypes.data, 256, 128, 0, 128, 4, c.FMT_U8, got.ctypes.data, 48, 0x3F, 0, 48, c.MEM_HOST, None))
+		return bool((got == pano_want).all())
+
+	with ThreadPoolExecutor(max_workers=8) as ex:
+		assert all(ex.map(run, range(48)))
