@@ -656,7 +656,7 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 			out[key] = {"e2e": {"error": repr(e)}}
 
 	if world == 1:
-		equirect("cfg1_equirect_2048x1024_rgba8_to_6x512", 2048, 1024, 512, 4, FMT_U8, 1, 50, "14.7 MB problem: fits L2, launch-latency bound")
+		equirect("cfg1_equirect_2048x1024_rgba8_to_6x512", 2048, 1024, 512, 4, FMT_U8, 1, 50, "14.7 MB problem: fits L2, launch-latency bound", e2e=True)
 		equirect("cfg3_equirect_8192x4096_rgba32f_to_6x2048", 8192, 4096, 2048, 4, FMT_F32, 4, 20, e2e=True)
 	# sharded, a step is one ~0.1 ms launch per rank: more of them, so that the Python call ahead of the
 	# first launch does not weigh in the per-step time
