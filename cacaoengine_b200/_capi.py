@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "libcacaoimage_b200.so")
+LIB_PATH = os.environ.get("CACAO_IMG_LIB") or os.path.join(PKG, "lib", "libcacaoimage_b200.so")  # the override is for A/B runs of two builds (dev/)
 
 # enum cacao_sample_fmt / cacao_mode / cacao_mem / cacao_status (include/cacao_img.h)
 FMT_U8, FMT_U16, FMT_F16, FMT_F32 = 0, 1, 2, 3

@@ -82,8 +82,10 @@ namespace {
 
 	struct HostLut {
 		uint8_t table[65536];
-		uint16_t two_level[4096]; // see lut_16to8<true> in convert_pixel.cuh
+		uint16_t two_level[4096];             // see lut_16to8<kLutTwoLevel> in convert_pixel.cuh
+		uint32_t lanes[cacao::kLanesEntries]; // see lut_16to8<kLutLanes>
 		bool two_level_ok = true;
+		bool lanes_ok = true;
 		HostLut() {
 			// level k starts at kLutThresholds[k-1]; the table is monotone with unit steps
 			int level = 0;
@@ -102,6 +104,36 @@ namespace {
 				two_level[k] = static_cast<uint16_t>(base | (step << 8));
 				for(uint32_t o = 0; o < 16; ++o) // the compact form must reproduce every entry
 					if(base + (o >= step ? 1u : 0u) != table[16 * k + o]) two_level_ok = false;
+			}
+			// log-indexed form: segment = upper half-word of float(v + bias), position = lower half-word
+			auto float_bits = [](uint32_t v) {
+				const float f = static_cast<float>(v + static_cast<uint32_t>(cacao::kLanesBias));
+				uint32_t b;
+				std::memcpy(&b, &f, 4);
+				return b;
+			};
+			bool seen[cacao::kLanesEntries] = {};
+			for(uint32_t v = 0; v < 65536u; ++v) {
+				const uint32_t b = float_bits(v), seg = (b >> 16) - cacao::kLanesHiBase;
+				if(seg >= static_cast<uint32_t>(cacao::kLanesEntries)) {
+					lanes_ok = false;
+					break;
+				}
+				if(seen[seg]) continue;
+				seen[seg] = true;
+				// v is the first input of its segment: find the one step inside it, if any
+				uint32_t step_pos = 0x10000u;
+				for(uint32_t u = v + 1; u < 65536u && (float_bits(u) >> 16) == (b >> 16); ++u)
+					if(table[u] != table[v]) {
+						step_pos = float_bits(u) & 0xFFFFu;
+						break;
+					}
+				lanes[seg] = (static_cast<uint32_t>(table[v]) << 16) + (0x10000u - step_pos) - ((b >> 16) << 16);
+			}
+			for(int k = 0; k < cacao::kLanesEntries; ++k) lanes_ok = lanes_ok && seen[k];
+			for(uint32_t v = 0; v < 65536u && lanes_ok; ++v) { // the form must reproduce every entry
+				const uint32_t b = float_bits(v), sum = b + lanes[(b >> 16) - cacao::kLanesHiBase];
+				if((sum >> 16) != table[v]) lanes_ok = false;
 			}
 		}
 	};
@@ -257,6 +289,7 @@ namespace {
 		size_t smem_optin = 0;
 		uint8_t* lut_dev = nullptr;
 		uint16_t* lut2_dev = nullptr;
+		uint32_t* lanes_dev = nullptr;
 		cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
 		cudaEvent_t ev_in[kSlots] = {}, ev_run[kSlots] = {}, ev_out[kSlots] = {};
 		uint8_t* stage_in[kSlots] = {};
@@ -340,6 +373,7 @@ namespace {
 		if(c->s_out) cudaStreamDestroy(c->s_out);
 		if(c->lut_dev) cudaFree(c->lut_dev);
 		if(c->lut2_dev) cudaFree(c->lut2_dev);
+		if(c->lanes_dev) cudaFree(c->lanes_dev);
 		if(c->checksum_dev) cudaFree(c->checksum_dev);
 		cudaSetDevice(prev);
 		delete c;
@@ -356,6 +390,9 @@ namespace {
 		if(!host_lut().two_level_ok) return fail(CACAO_E_BAD_ARG, "internal: two-level 16->8 table does not reproduce the reference table");
 		CU_TRY(cudaMalloc(&c->lut_dev, 65536));
 		CU_TRY(cudaMemcpy(c->lut_dev, host_lut().table, 65536, cudaMemcpyHostToDevice));
+		if(!host_lut().lanes_ok) return fail(CACAO_E_BAD_ARG, "internal: log-indexed 16->8 table does not reproduce the reference table");
+		CU_TRY(cudaMalloc(&c->lanes_dev, sizeof(host_lut().lanes)));
+		CU_TRY(cudaMemcpy(c->lanes_dev, host_lut().lanes, sizeof(host_lut().lanes), cudaMemcpyHostToDevice));
 		CU_TRY(cudaMalloc(&c->lut2_dev, sizeof(host_lut().two_level)));
 		CU_TRY(cudaMemcpy(c->lut2_dev, host_lut().two_level, sizeof(host_lut().two_level), cudaMemcpyHostToDevice));
 		CU_TRY(cudaMalloc(&c->checksum_dev, sizeof(unsigned long long)));
@@ -560,6 +597,7 @@ namespace {
 		job.mode = mode;
 		job.lut_dev = c->lut_dev;
 		job.lut2_dev = c->lut2_dev;
+		job.lanes_dev = c->lanes_dev;
 		job.dev.sm_count = c->sm_count;
 		job.dev.max_smem_optin = c->smem_optin;
 		job.stream = stream;

@@ -6,6 +6,7 @@
 
 #include "convert_tiles.cuh"
 #include "convert_wide.cuh"
+#include "convert_lanes.cuh"
 
 namespace cacao {
 
@@ -19,6 +20,7 @@ namespace cacao {
 		uint32_t flip_w = 0, flip_h = 0; // != 0: images are flip_w x flip_h pixels and come out bottom row first
 		const uint8_t* lut_dev;   // 65536-byte table in device global memory
 		const uint16_t* lut2_dev; // its 4096-entry two-level form (convert_pixel.cuh)
+		const uint32_t* lanes_dev = nullptr; // its 644-word bank-private log-indexed form (convert_pixel.cuh)
 		TileLaunch dev;
 		cudaStream_t stream;
 		unsigned launches; // out: kernels launched
@@ -33,6 +35,7 @@ namespace cacao {
 		PixelCtx ctx;
 		ctx.lut = lut_global;
 		ctx.lut2 = nullptr;
+		ctx.lanes = nullptr;
 		ctx.gray16_cap = gray16_cap;
 		const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
 		for(uint64_t p = p_begin + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < p_end; p += stride) {
@@ -70,12 +73,30 @@ namespace cacao {
 		// stores unit k of row y at row h-1-y; a width no unit divides goes through the byte-wise kernel.
 		const bool flipped = job.flip_w != 0 && job.flip_h > 1;
 		const bool tile_fits = !flipped || job.flip_w % S::tile_pixels == 0;
+		bool lanes = false;
+		if constexpr(SF == CACAO_FMT_U16 && DF == CACAO_FMT_U8) {
+			// the bank-private table form (convert_lanes.cuh): large 16 -> 8 bit jobs on 32-byte aligned buffers
+			using LS = LanesShape<SC, DC>;
+			const bool aligned32 = ((reinterpret_cast<uintptr_t>(job.src) | reinterpret_cast<uintptr_t>(job.dst)) & 31u) == 0;
+			const uint64_t n_runs = job.pixels / LS::G;
+			lanes = !quirk && aligned32 && job.lanes_dev != nullptr && (!flipped || job.flip_w % LS::G == 0) && lanes_preferred<SC, DC>(n_runs);
+			if(lanes) {
+				if(n_runs > 0) {
+					FlipMap fm;
+					if(flipped) fm.per_row = job.flip_w / LS::G, fm.rows = job.flip_h;
+					cudaError_t e = launch_convert_lanes<SC, DC>(job.src, job.dst, n_runs, job.lanes_dev, job.stream, fm);
+					if(e != cudaSuccess) return e;
+					job.launches += 1;
+				}
+				done = n_runs * LS::G;
+			}
+		}
 		if constexpr(WideShape<SF, DF, SC, DC>::ok) {
 			using WS = WideShape<SF, DF, SC, DC>;
 			const bool aligned32 = ((reinterpret_cast<uintptr_t>(job.src) | reinterpret_cast<uintptr_t>(job.dst)) & 31u) == 0;
 			const char* force = getenv("CACAO_FORCE_WIDE"); // dev/test switch: run every fitting shape on the sector kernel
 			const bool wide_fits = !flipped || job.flip_w % WS::G == 0;
-			wide = !quirk && aligned32 && !getenv("CACAO_NO_WIDE") && wide_fits && (WS::preferred || (force && force[0] == '1') || (flipped && !(tile_fits && aligned)));
+			wide = !lanes && !quirk && aligned32 && !getenv("CACAO_NO_WIDE") && wide_fits && (WS::preferred || (force && force[0] == '1') || (flipped && !(tile_fits && aligned)));
 			if(wide) {
 				const uint64_t n_runs = job.pixels / WS::G;
 				if(n_runs > 0) {
@@ -88,7 +109,7 @@ namespace cacao {
 				done = n_runs * WS::G;
 			}
 		}
-		if(!wide) {
+		if(!wide && !lanes) {
 			const uint64_t n_tiles = (quirk || !aligned || !tile_fits) ? 0 : job.pixels / S::tile_pixels;
 			if(n_tiles > 0) {
 				FlipMap fm;

@@ -90,8 +90,34 @@ namespace cacao {
 	struct PixelCtx {
 		const uint8_t* lut;   // 65536-entry table in global memory (edge kernel); only read for U16 -> U8
 		const uint16_t* lut2; // 4096-entry two-level form of the same table in shared memory (tile kernel)
+		const uint8_t* lanes; // this lane's column of the bank-private form in shared memory (sector kernel)
 		uint32_t gray16_cap;  // 255 in REF_EXACT mode (Layout.cpp:75), 65535 in FIXED mode
 	};
+
+	// Which form of the 16->8 table a kernel reads.
+	enum : int { kLutDirect = 0, kLutTwoLevel = 1, kLutLanes = 2 };
+
+	// The bank-private form (kLutLanes).  A warp's 32 independent 16-bit indices fall on the 32 shared-memory
+	// banks like balls into bins -- 3.5 data-pipe passes per LDS whatever the table's size (ncu: 62.8 M
+	// conflict wavefronts for 25.2 M gathers).  The only layout without conflicts gives every lane its own
+	// bank: word (entry * 32 + lane).  That is 128 bytes per entry, so the table has to be SHORT, and it is
+	// when it is indexed by the logarithm of the input: the table is an sRGB-style power curve, whose steps
+	// thin out as the input grows (19 inputs apart at the dark end, 580 at the bright end).  float(v + 2048)
+	// has its exponent and top 7 mantissa bits in its upper half-word: 128 segments per octave, 16 inputs wide
+	// in the lowest octave and 512 in the highest, 644 segments in all for v in [0, 65535], and none of them
+	// holds more than one step of the table (checked when the form is built, cabi.cu).  The low half-word of
+	// the float is the position inside the segment, so with entry = (level << 16) + (0x10000 - step position)
+	// - (segment's upper half-word << 16) the sum  bits + entry  carries into bit 16 exactly when v is at or
+	// past the step, and bits 16..23 of the sum are the table's output.  Per sample: PRMT + FADD (v + 2048 as a
+	// float, exact), shift + scaled add (address), LDS (one pass), IADD -- no compare, no select.
+	constexpr int kLanesBias = 2048;
+	constexpr int kLanesEntries = 644;
+	constexpr uint32_t kLanesHiBase = (127u + 11u) << 7; // upper half-word of float(2048)
+	constexpr int kLanesBytes = kLanesEntries * 128;
+#ifndef CACAO_LANES_THREADS
+#define CACAO_LANES_THREADS 512
+#endif
+	constexpr int kLanesThreads = CACAO_LANES_THREADS; // two blocks per SM
 
 	// The reference's 16->8 table (Colordepth.cpp:35) is monotone, moves in unit steps, and its steps
 	// are never closer than 19 inputs apart -- so a run of 16 consecutive inputs holds at most one
@@ -99,11 +125,27 @@ namespace cacao {
 	// high byte = offset of the step inside the run (16 = no step).  8 KiB instead of 64 KiB: it loads
 	// 8x faster, leaves shared memory for 8 blocks per SM, and costs the same single LDS per sample.
 	// cabi.cu builds it from the 65536-entry table and verifies it reproduces every entry.
-	template<bool TwoLevel>
+	// 0x4B00vvvv is the float 2^23 + v.  The constant lives in constant memory so that it reaches PRMT as a
+	// REGISTER operand and the byte selector as the immediate: with a literal, ptxas makes the literal the
+	// immediate and spends two more instructions on masking the sample and materialising the selector.
+	__constant__ uint32_t g_f32_2p23 = 0x4B000000u;
+	// word: two packed 16-bit samples; half: which one
+	__device__ __forceinline__ uint32_t lanes_magic(uint32_t word, int half) {
+		return __byte_perm(word, g_f32_2p23, half ? 0x7632u : 0x7610u);
+	}
+	// bits 16..23 of the result are table[v]; magic = lanes_magic(...)
+	__device__ __forceinline__ uint32_t lanes_sum(const PixelCtx& ctx, uint32_t magic) {
+		const uint32_t bits = __float_as_uint(__fadd_rn(__uint_as_float(magic), static_cast<float>(kLanesBias) - 8388608.0f)); // float(v + bias), exact
+		return bits + *reinterpret_cast<const uint32_t*>(ctx.lanes + ((bits >> 16) << 7));
+	}
+
+	template<int Mode>
 	__device__ __forceinline__ uint32_t lut_16to8(const PixelCtx& ctx, uint32_t v) {
-		if constexpr(TwoLevel) {
+		if constexpr(Mode == kLutTwoLevel) {
 			const uint32_t e = ctx.lut2[v >> 4];
 			return (e & 0xFFu) + (((v & 15u) >= (e >> 8)) ? 1u : 0u);
+		} else if constexpr(Mode == kLutLanes) {
+			return lanes_sum(ctx, lanes_magic(v, 0)) >> 16;
 		} else {
 			return ctx.lut[v];
 		}
@@ -111,10 +153,29 @@ namespace cacao {
 
 	// in[]: SC source samples; integer formats as their integer value, F16 as raw bits, F32 as
 	// float bits.  out[]: DC destination samples in the same register convention.
-	template<int SF, int DF, int SC, int DC, bool TwoLevelLut = false>
+	template<int SF, int DF, int SC, int DC, int LutMode = kLutDirect>
 	__device__ __forceinline__ void convert_pixel(const uint32_t (&in)[SC], uint32_t (&out)[DC], const PixelCtx& ctx) {
 		constexpr bool src_int = FmtTraits<SF>::is_int;
-		if constexpr(SF == CACAO_FMT_U16 && DF == CACAO_FMT_U8 && SC != DC) {
+		if constexpr(SF == CACAO_FMT_U16 && DF == CACAO_FMT_U8 && LutMode == kLutLanes) {
+			// ---- 16 -> 8 bit through the bank-private table form.  Register convention of THIS branch only:
+			// in[] = lanes_magic() of the packed source word (the sample as the float 2^23 + v), out[] = the
+			// result in bits 16..23, other bits unspecified -- the sector kernel builds and consumes both with
+			// one PRMT each.  Same semantics as the two branches below (depth first, then the 8-bit layout rules).
+			constexpr int used = (SC == DC) ? SC : (SC < 3 ? SC : 3);
+			uint32_t t[used];
+#pragma unroll
+			for(int c = 0; c < used; ++c) t[c] = lanes_sum(ctx, in[c]);
+			if constexpr(SC == DC) {
+#pragma unroll
+				for(int c = 0; c < DC; ++c) out[c] = t[c];
+			} else if constexpr(DC == 1) {
+				out[0] = min(trunc_2126(t[0] >> 16) + trunc_7152<false>(t[1] >> 16) + trunc_0722(t[2] >> 16), 255u) << 16;
+			} else {
+#pragma unroll
+				for(int c = 0; c < 3; ++c) out[c] = t[SC == 1 ? 0 : c];
+				if constexpr(DC == 4) out[3] = 255u << 16;
+			}
+		} else if constexpr(SF == CACAO_FMT_U16 && DF == CACAO_FMT_U8 && SC != DC) {
 			// ---- 16 -> 8 bit WITH a layout change: the one pair where the depth conversion comes first --
 			// the order of the engine's composition (Convert16To8BitColor, then ChangeChannelLayout:
 			// engine/src/core/Cubemap.cpp:28-31), so the fused call equals the reference's two calls for every
@@ -123,7 +184,7 @@ namespace cacao {
 			constexpr int used = SC < 3 ? SC : 3;
 			uint32_t t[used];
 #pragma unroll
-			for(int c = 0; c < used; ++c) t[c] = lut_16to8<TwoLevelLut>(ctx, in[c]);
+			for(int c = 0; c < used; ++c) t[c] = lut_16to8<LutMode>(ctx, in[c]);
 			if constexpr(DC == 1) {
 				out[0] = min(trunc_2126(t[0]) + trunc_7152<false>(t[1]) + trunc_0722(t[2]), 255u);
 			} else {
@@ -157,7 +218,7 @@ namespace cacao {
 				if constexpr(DF == SF) {
 					out[c] = mid[c];
 				} else if constexpr(DF == CACAO_FMT_U8) {
-					out[c] = lut_16to8<TwoLevelLut>(ctx, mid[c]);
+					out[c] = lut_16to8<LutMode>(ctx, mid[c]);
 				} else if constexpr(DF == CACAO_FMT_U16) {
 					out[c] = mid[c] * 257u;
 				} else if constexpr(DF == CACAO_FMT_F32) {

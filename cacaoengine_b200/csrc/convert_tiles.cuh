@@ -80,6 +80,7 @@ namespace cacao {
 		ctx.gray16_cap = gray16_cap;
 		ctx.lut = nullptr;
 		ctx.lut2 = nullptr;
+		ctx.lanes = nullptr;
 		uint8_t* stage_base = smem_raw;
 		if constexpr(S::needs_lut) {
 			uint4* l4 = reinterpret_cast<uint4*>(smem_raw);
@@ -141,7 +142,7 @@ namespace cacao {
 					uint32_t in[SC], out[DC];
 #pragma unroll
 					for(int c = 0; c < SC; ++c) in[c] = unpack_sample<S::sb>(w, p * SC + c);
-					convert_pixel<SF, DF, SC, DC, true>(in, out, ctx);
+					convert_pixel<SF, DF, SC, DC, kLutTwoLevel>(in, out, ctx);
 #pragma unroll
 					for(int c = 0; c < DC; ++c) pack_sample<S::db>(o, p * DC + c, out[c]);
 				}

@@ -56,6 +56,7 @@ namespace cacao {
 		ctx.gray16_cap = gray16_cap;
 		ctx.lut = nullptr;
 		ctx.lut2 = nullptr;
+		ctx.lanes = nullptr;
 		if constexpr(S::needs_lut) {
 			uint4* l4 = reinterpret_cast<uint4*>(smem_raw);
 			const uint4* g4 = reinterpret_cast<const uint4*>(LUT_DIRECT ? static_cast<const void*>(lut_global) : static_cast<const void*>(lut2_global));
@@ -92,7 +93,7 @@ namespace cacao {
 					uint32_t in[SC], out[DC];
 #pragma unroll
 					for(int c = 0; c < SC; ++c) in[c] = unpack_sample<S::sb>(w[u], p * SC + c);
-					convert_pixel<SF, DF, SC, DC, !LUT_DIRECT>(in, out, ctx);
+					convert_pixel<SF, DF, SC, DC, LUT_DIRECT ? kLutDirect : kLutTwoLevel>(in, out, ctx);
 #pragma unroll
 					for(int c = 0; c < DC; ++c) pack_sample<S::db>(o, p * DC + c, out[c]);
 				}
@@ -114,12 +115,12 @@ namespace cacao {
 	// that cost more than the table: 0.72 of the roofline against 0.88 for a 64-face batch of the same shape
 	// (profiles/r2_lut_iters_by_size.log).  So: the fewest whole waves that keep a block at <= 8 passes, and the
 	// passes that fill them exactly.  `resident` = blocks the device holds at once (occupancy x SMs).
-	inline uint32_t wave_aligned_iters(uint64_t units, uint64_t units_per_pass, int resident) {
+	inline uint32_t wave_aligned_iters(uint64_t units, uint64_t units_per_pass, int resident, uint64_t max_passes = 8) {
 		if(resident <= 0 || units_per_pass == 0) return 4;
 		const uint64_t per_wave = units_per_pass * static_cast<uint64_t>(resident);
-		const uint64_t waves = (units + per_wave * 8 - 1) / (per_wave * 8);
+		const uint64_t waves = (units + per_wave * max_passes - 1) / (per_wave * max_passes);
 		const uint64_t iters = (units + per_wave * waves - 1) / (per_wave * (waves ? waves : 1));
-		return static_cast<uint32_t>(iters < 1 ? 1 : (iters > 8 ? 8 : iters));
+		return static_cast<uint32_t>(iters < 1 ? 1 : (iters > max_passes ? max_passes : iters));
 	}
 
 	template<class K>
@@ -139,6 +140,7 @@ namespace cacao {
 		// 4.47 vs 5.23), on smooth images about level (dev/sweep_lut.py).
 		bool direct = false;
 		if(const char* e = getenv("CACAO_LUT_DIRECT")) direct = S::needs_lut && atoi(e) != 0 && !flip.per_row; // test switch; no flipped form
+		if(const char* e = getenv("CACAO_LUT_MODE")) direct = S::needs_lut && e[0] == 'd' && !flip.per_row;   // two | direct | lanes (convert_lanes.cuh)
 		const int threads = direct ? 1024 : 256;
 		const size_t smem = S::needs_lut ? (direct ? 65536 : kLut2Bytes) : 0;
 		uint32_t iters = S::needs_lut ? (direct ? 16u : 4u) : 1u;

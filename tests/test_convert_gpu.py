@@ -233,6 +233,60 @@ def test_convert_flip_every_shape(oracle, sf, df, sc, dc):
 			assert same_bits(got_h, want), (w, h, count, mode, "host")
 
 
+@pytest.mark.parametrize("form", ["two", "direct", "lanes"])
+def test_every_form_of_the_depth_table(oracle, golden, monkeypatch, form):
+	"""The 16 -> 8 bit table sits in shared memory in one of three forms (convert_pixel.cuh: two-level 8 KiB,
+	direct 64 KiB, bank-private log-indexed 80.5 KiB); CACAO_LUT_MODE pins one.  Each must give the compiled
+	reference's output for all 65,536 inputs (tests/golden) and the oracle's for every layout pair, plain and
+	with the row mirror folded in."""
+	from cacaoengine_b200 import _capi as c, device
+
+	monkeypatch.setenv("CACAO_LUT_MODE", form)
+	src_all, want_all = golden["depth_all_in"], golden["depth_all_out"]
+	assert (convert_device(src_all, 1, 1, c.FMT_U16, c.FMT_U8) == want_all).all()
+	rng = np.random.default_rng(11)
+	for sc, dc in itertools.product(CH, CH):
+		for mode in (0, 1):
+			if sc == 1 and dc == 4 and mode == 0:
+				continue  # pixel-0 quirk: byte-wise kernel, no table form involved
+			px = 40961
+			src = np.concatenate([np.repeat(np.arange(65536, dtype=np.uint16), sc)[: px * sc // 2], random_samples(rng, px * sc - px * sc // 2, c.FMT_U16)])
+			want = oracle.convert(src, sc, dc, c.FMT_U16, c.FMT_U8, mode)
+			assert same_bits(convert_device(src, sc, dc, c.FMT_U16, c.FMT_U8, mode), want), (sc, dc, mode)
+		if sc == 1 and dc == 4:
+			continue
+		# 192: no warp of runs stays inside a row (lane-wise stores); 512: whole warps per row (staged stores)
+		for w, h, count in ((192, 37, 3), (512, 9, 2)):
+			src = random_samples(rng, w * h * count * sc, c.FMT_U16)
+			want = oracle.convert(src, sc, dc, c.FMT_U16, c.FMT_U8, 1).reshape(count, h, w * dc)[:, ::-1, :].copy().reshape(-1)
+			a, b = DevBuf(src.nbytes), DevBuf(want.nbytes)
+			device.upload(a.ptr, src)
+			device.convert_flip(a.ptr, b.ptr, w, h, count, sc, dc, c.FMT_U16, c.FMT_U8, 1)
+			got = np.empty_like(want)
+			device.download(got, b.ptr)
+			a.free(), b.free()
+			assert same_bits(got, want), (sc, dc, w, "flipped")
+
+
+def test_large_table_jobs_take_the_bank_private_form(oracle):
+	"""From about a megapixel on the dispatcher picks the bank-private form by itself (lanes_preferred,
+	convert_lanes.cuh); RGBA16 -> RGB8 at six 1024^2 faces, plain and flipped, against the oracle."""
+	from cacaoengine_b200 import _capi as c, device
+
+	w, h, count = 1024, 1024, 6
+	rng = np.random.default_rng(5)
+	src = rng.integers(0, 65536, w * h * count * 4, dtype=np.uint16)
+	want = oracle.convert(src, 4, 3, c.FMT_U16, c.FMT_U8)
+	assert same_bits(convert_device(src, 4, 3, c.FMT_U16, c.FMT_U8), want)
+	a, b = DevBuf(src.nbytes), DevBuf(want.nbytes)
+	device.upload(a.ptr, src)
+	device.convert_flip(a.ptr, b.ptr, w, h, count, 4, 3, c.FMT_U16, c.FMT_U8)
+	got = np.empty_like(want)
+	device.download(got, b.ptr)
+	a.free(), b.free()
+	assert same_bits(got, want.reshape(count, h, w * 3)[:, ::-1, :].copy().reshape(-1))
+
+
 @pytest.mark.parametrize("w,h,count", [(2048, 1500, 1), (1000, 777, 3), (96, 4000, 2)])
 def test_convert_flip_host_pipeline_in_row_bands(oracle, w, h, count):
 	"""Host-memory cacao_img_convert_flip on images large enough for the chunked pipeline: chunks are bands
