@@ -30,6 +30,8 @@ TRAFFIC_KEYS = {
 	"convert_tiles_kernel<1, 0, 4, 3": "lut_64x_2048sq_rgba16_to_rgb8",
 	"convert_wide_kernel<1, 0, 4, 3, 0, 0": "lut_64x_2048sq_rgba16_to_rgb8",  # plain (not the FLIP instantiation)
 	"convert_wide_kernel<1, 0, 4, 3, 0>": "lut_64x_2048sq_rgba16_to_rgb8",    # round-1 name, before FLIP was a template argument
+	"convert_lanes_kernel<4, 3, 0": "lut_64x_2048sq_rgba16_to_rgb8",                 # bank-private table form (convert_lanes.cuh), plain
+	"convert_lanes_kernel<4, 3, 1": "engine_cube_6x2048sq_rgba16_to_rgb8_flipped",   # ... FLIP instantiation
 	"equirect_kernel<3, 4": "cfg3_equirect_8192x4096_rgba32f_to_6x2048",
 	"convert_wide_kernel<1, 0, 4, 3, 0, 1": "engine_cube_6x2048sq_rgba16_to_rgb8_flipped",  # FLIP instantiation
 	"equirect_rows_kernel<0, 4": "cfg3shape_equirect_8192x4096_rgba8_to_6x2048",
