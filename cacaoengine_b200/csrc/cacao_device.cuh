@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "cacao_img.h"
 
@@ -75,6 +76,22 @@ namespace cacao {
 		asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 	}
 
+	// ---- programmatic dependent launch ---------------------------------------------------------
+	// Kernels of this library are usually launched back to back on one stream (faces of a cube, images of a
+	// batch, a conversion after a resampling).  Launched with launch_pdl() below, a kernel's blocks may become
+	// resident while the previous kernel's last blocks are still running: everything that does not touch the
+	// caller's buffers -- index arithmetic, the projection of the block's first pixels, staging the depth table --
+	// then overlaps the predecessor's tail instead of following it.  pdl_wait() returns once the predecessor
+	// has completed and its writes are visible, so it MUST precede the first access to any caller buffer;
+	// pdl_launch_dependents() lets the successor in.  After a non-participating predecessor (a copy, another
+	// library's kernel) both are no-ops and the launch is an ordinary one.
+	__device__ __forceinline__ void pdl_launch_dependents() {
+		asm volatile("griddepcontrol.launch_dependents;");
+	}
+	__device__ __forceinline__ void pdl_wait() {
+		asm volatile("griddepcontrol.wait;" ::: "memory");
+	}
+
 	// ---- binary16 <-> binary32, round-to-nearest-even ------------------------------------------
 	// The bits come out of the packed two-lane convert into a 32-bit register on purpose: ptxas
 	// 12.9 miscompiles "cvt.rn.f16.f32 into a .b16 register, then store/extract its low byte" into
@@ -103,6 +120,25 @@ namespace cacao {
 	}
 	__host__ __device__ __forceinline__ uint32_t hash32(uint32_t seed, uint64_t idx) {
 		return fmix32(seed ^ (static_cast<uint32_t>(idx) * 0x9E3779B9u) ^ (static_cast<uint32_t>(idx >> 32) * 0x85EBCA6Bu));
+	}
+
+	// Host side: <<<>>> with the programmatic-stream-serialization attribute.  CACAO_NO_PDL=1 launches plainly
+	// (A/B switch).  Only for kernels that call pdl_wait() before their first global access.
+	template<class... KArgs, class... Args>
+	inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+		const char* e = getenv("CACAO_NO_PDL");
+		const bool off = e && e[0] == '1';
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = grid;
+		cfg.blockDim = block;
+		cfg.dynamicSmemBytes = smem;
+		cfg.stream = stream;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr;
+		cfg.numAttrs = off ? 0 : 1;
+		return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 	}
 
 } // namespace cacao

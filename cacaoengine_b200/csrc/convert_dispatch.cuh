@@ -37,6 +37,8 @@ namespace cacao {
 		ctx.lut2 = nullptr;
 		ctx.lanes = nullptr;
 		ctx.gray16_cap = gray16_cap;
+		pdl_launch_dependents();
+		pdl_wait(); // cacao_device.cuh: launched behind the vector kernel of the same call, whose tail it may overlap
 		const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
 		for(uint64_t p = p_begin + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < p_end; p += stride) {
 			const uint64_t sp = pixel0_quirk ? (p / pixels_per_image) * pixels_per_image : p;
@@ -128,8 +130,7 @@ namespace cacao {
 			FlipMap fm; // in pixels
 			if(flipped) fm.per_row = job.flip_w, fm.rows = job.flip_h;
 			auto edge = flipped ? convert_edge_kernel<SF, DF, SC, DC, true> : convert_edge_kernel<SF, DF, SC, DC, false>;
-			edge<<<static_cast<unsigned>(blocks), 256, 0, job.stream>>>(static_cast<const uint8_t*>(job.src), static_cast<uint8_t*>(job.dst), done, job.pixels, job.pixels_per_image, quirk ? 1 : 0, job.lut_dev, gray16_cap, fm);
-			cudaError_t e = cudaGetLastError();
+			cudaError_t e = launch_pdl(edge, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, job.stream, static_cast<const uint8_t*>(job.src), static_cast<uint8_t*>(job.dst), done, job.pixels, job.pixels_per_image, quirk ? 1 : 0, job.lut_dev, gray16_cap, fm);
 			if(e != cudaSuccess) return e;
 			job.launches += 1;
 		}

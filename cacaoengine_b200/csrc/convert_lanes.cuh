@@ -6,8 +6,8 @@
 // the limiter of every table shape on uniform-random samples.  Here each lane reads its own bank, so a gather
 // is one pass whatever the data, at 80.5 KiB of shared memory per block.  What the kernel is built around:
 //
-//   * two blocks per SM, each staging the 644-word table by itself (eight 16-byte stores per entry) AFTER it has
-//     issued the loads of its first pass;
+//   * two blocks per SM, each staging the 644-word table by itself (eight 16-byte stores per entry) -- before
+//     pdl_wait(), i.e. under the tail of the previous launch on the stream when there is one (cacao_device.cuh);
 //   * a lane owns a run of G pixels = KIN (2 or 3) whole 32-byte source sectors (LDG.256) and a whole number of
 //     8-byte output units.  128-byte runs (RGBA16 at 16 pixels) stream 5 % slower on B200 (dev/stream_bench.cu)
 //     and leave no registers to overlap passes, so RGBA16 runs are 8 pixels here, not 16 as in convert_wide.cuh;
@@ -58,17 +58,20 @@ namespace cacao {
 		auto issue = [&](int k, uint64_t run) {
 			if(run < n_runs) ldg256_stream(src + run * (32ull * S::KIN) + 32 * k, &w[8 * k]);
 		};
-#pragma unroll
-		for(int k = 0; k < S::KIN; ++k) issue(k, r);
+		pdl_launch_dependents();
 		{
-			// entry e becomes 32 equal words, one per bank: eight 16-byte stores
+			// entry e becomes 32 equal words, one per bank: eight 16-byte stores.  The table is the library's own
+			// constant data, so this happens BEFORE pdl_wait(): under the previous launch's tail when there is one.
 			uint4* l4 = reinterpret_cast<uint4*>(smem_raw);
 			for(int i = threadIdx.x; i < kLanesEntries * 8; i += blockDim.x) {
 				const uint32_t e = __ldg(lanes_global + (i >> 3));
 				l4[i] = make_uint4(e, e, e, e);
 			}
-			__syncthreads();
 		}
+		pdl_wait();
+#pragma unroll
+		for(int k = 0; k < S::KIN; ++k) issue(k, r);
+		__syncthreads();
 		PixelCtx ctx;
 		ctx.gray16_cap = 255u; // unused: 16 -> 8 bit takes the depth step first, gray is the 8-bit rule (convert_pixel.cuh)
 		ctx.lut = nullptr;
@@ -176,11 +179,7 @@ namespace cacao {
 		const uint64_t runs_per_block = static_cast<uint64_t>(S::threads) * iters;
 		const uint64_t blocks = (n_runs + runs_per_block - 1) / runs_per_block;
 		if(blocks > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
-		if(flip.per_row)
-			flipped<<<static_cast<unsigned>(blocks), S::threads, S::smem_bytes, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lanes_global, flip);
-		else
-			plain<<<static_cast<unsigned>(blocks), S::threads, S::smem_bytes, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lanes_global, flip);
-		return cudaGetLastError();
+		return launch_pdl(flip.per_row ? flipped : plain, dim3(static_cast<unsigned>(blocks)), dim3(S::threads), S::smem_bytes, stream, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lanes_global, flip);
 	}
 
 } // namespace cacao

@@ -82,6 +82,7 @@ namespace cacao {
 		ctx.lut2 = nullptr;
 		ctx.lanes = nullptr;
 		uint8_t* stage_base = smem_raw;
+		pdl_launch_dependents(); // cacao_device.cuh: the table (the library's own constant data) is staged before pdl_wait()
 		if constexpr(S::needs_lut) {
 			uint4* l4 = reinterpret_cast<uint4*>(smem_raw);
 			const uint4* g4 = reinterpret_cast<const uint4*>(lut2_global);
@@ -97,6 +98,7 @@ namespace cacao {
 		// the access pattern of a plain one-shot elementwise kernel.  (Measured on B200: a classic
 		// persistent grid-stride loop, where each warp's next tile is a whole grid away, loses 15%.)
 		const uint64_t block_base = static_cast<uint64_t>(blockIdx.x) * warps_per_block * S::U * iters;
+		pdl_wait(); // first touch of the caller's buffers
 		for(uint32_t it = 0; it < iters; ++it) {
 			const uint64_t t0 = block_base + (static_cast<uint64_t>(it) * warps_per_block + warp) * S::U;
 			if(t0 >= n_tiles) break;
@@ -196,8 +198,7 @@ namespace cacao {
 		if(blocks == 0) return cudaSuccess;
 		if(blocks > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
 		(void)dev;
-		kern<<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), n_tiles, iters, lut2_global, gray16_cap, flip);
-		return cudaGetLastError();
+		return launch_pdl(kern, dim3(static_cast<unsigned>(blocks)), dim3(warps * 32), smem, stream, static_cast<const uint4*>(src), static_cast<uint4*>(dst), n_tiles, iters, lut2_global, gray16_cap, flip);
 	}
 
 } // namespace cacao

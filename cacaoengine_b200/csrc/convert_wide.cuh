@@ -57,6 +57,7 @@ namespace cacao {
 		ctx.lut = nullptr;
 		ctx.lut2 = nullptr;
 		ctx.lanes = nullptr;
+		pdl_launch_dependents(); // cacao_device.cuh: the table (the library's own constant data) is staged before pdl_wait()
 		if constexpr(S::needs_lut) {
 			uint4* l4 = reinterpret_cast<uint4*>(smem_raw);
 			const uint4* g4 = reinterpret_cast<const uint4*>(LUT_DIRECT ? static_cast<const void*>(lut_global) : static_cast<const void*>(lut2_global));
@@ -70,6 +71,7 @@ namespace cacao {
 		}
 		// a block owns a contiguous range of blockDim * U * iters runs and walks it front to back
 		const uint64_t block_base = static_cast<uint64_t>(blockIdx.x) * blockDim.x * S::U * iters;
+		pdl_wait(); // first touch of the caller's buffers
 		for(uint32_t it = 0; it < iters; ++it) {
 			const uint64_t r0 = block_base + (static_cast<uint64_t>(it) * blockDim.x + threadIdx.x) * S::U;
 			if(r0 >= n_runs) break;
@@ -160,15 +162,13 @@ namespace cacao {
 				auto kern = convert_wide_kernel<SF, DF, SC, DC, true>;
 				cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
 				if(e != cudaSuccess) return e;
-				kern<<<static_cast<unsigned>(blocks), threads, smem, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lut_global, lut2_global, gray16_cap, flip);
-				return cudaGetLastError();
+				return launch_pdl(kern, dim3(static_cast<unsigned>(blocks)), dim3(threads), smem, stream, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lut_global, lut2_global, gray16_cap, flip);
 			}
 		}
 		if(flip.per_row)
-			convert_wide_kernel<SF, DF, SC, DC, false, true><<<static_cast<unsigned>(blocks), threads, smem, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lut_global, lut2_global, gray16_cap, flip);
+			return launch_pdl(convert_wide_kernel<SF, DF, SC, DC, false, true>, dim3(static_cast<unsigned>(blocks)), dim3(threads), smem, stream, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lut_global, lut2_global, gray16_cap, flip);
 		else
-			convert_wide_kernel<SF, DF, SC, DC, false><<<static_cast<unsigned>(blocks), threads, smem, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lut_global, lut2_global, gray16_cap, flip);
-		return cudaGetLastError();
+			return launch_pdl(convert_wide_kernel<SF, DF, SC, DC, false>, dim3(static_cast<unsigned>(blocks)), dim3(threads), smem, stream, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lut_global, lut2_global, gray16_cap, flip);
 	}
 
 } // namespace cacao

@@ -212,6 +212,7 @@ namespace cacao {
 		template<int F, int CH, int WX, bool LOOP, int MINB>
 		__global__ void __launch_bounds__(128, MINB) equirect_rows_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, EquirectParams prm, Scales scl, uint32_t steps) {
 			constexpr uint32_t RY = 32 / WX, BH = 4 * RY; // a warp covers WX x RY pixels per step, a block WX x BH
+			pdl_launch_dependents(); // the first projection overlaps the previous launch's tail (cacao_device.cuh)
 			const CubeUnit unit = prm.units[blockIdx.z];
 			const uint32_t face = unit.face & 7u;
 			const bool mirror = (unit.face & kUnitMirror) != 0;
@@ -228,6 +229,7 @@ namespace cacao {
 			// face row j is stored at row row_add + row_mul * j: (0, 1) normally, (N-1, -1) for flipped output
 			const uint32_t frow = face * N + prm.row_add;
 			float xs_a = 0.0f, xs_b = 0.0f, xs_c = 0.0f, xs_d = 0.0f, rxz = 1.0f;
+			pdl_wait(); // before the first touch of the caller's buffers (later, inside the loop, it costs the 32-register forms a spill)
 			for(uint32_t step = 0; step < (LOOP ? steps : 1u) && j < unit.row_end; ++step, j += BH) {
 				const float tc = face_coord(j, prm.pc);
 				float xa, ya, za;
@@ -285,6 +287,7 @@ namespace cacao {
 			if(se) steps = static_cast<uint32_t>(std::max(1, atoi(se)));
 			const uint8_t* s8 = static_cast<const uint8_t*>(src);
 			uint8_t* d8 = static_cast<uint8_t*>(dst);
+			cudaError_t pe = cudaSuccess;
 			const dim3 block(32, 4, 1);
 			const Scales scl = {static_cast<uint32_t>(sbpp), static_cast<uint32_t>(dbpp), prm.W * static_cast<uint32_t>(sbpp), prm.N * static_cast<uint32_t>(dbpp)};
 			auto grid_for = [&](uint32_t st) { return dim3((half + WX - 1) / WX, (max_rows + BH * st - 1) / (BH * st), prm.n_units); };
@@ -295,10 +298,10 @@ namespace cacao {
 #define CACAO_ROWS_CASE(MB)                                                                                                     \
 	if(m == MB) {                                                                                                                \
 		if(se)                                                                                                                   \
-			equirect_rows_kernel<F, CH, WX, true, MB><<<grid_for(steps), block, 0, stream>>>(s8, d8, prm, scl, steps);   \
+			pe = launch_pdl(equirect_rows_kernel<F, CH, WX, true, MB>, grid_for(steps), block, 0, stream, s8, d8, prm, scl, steps);   \
 		else                                                                                                                     \
-			equirect_rows_kernel<F, CH, WX, false, MB><<<grid_for(1), block, 0, stream>>>(s8, d8, prm, scl, 1);          \
-		return cudaGetLastError();                                                                                               \
+			pe = launch_pdl(equirect_rows_kernel<F, CH, WX, false, MB>, grid_for(1), block, 0, stream, s8, d8, prm, scl, 1);          \
+		return pe;                                                                                                               \
 	}
 				CACAO_ROWS_CASE(8)
 				CACAO_ROWS_CASE(10)
@@ -308,8 +311,8 @@ namespace cacao {
 			}
 #endif
 			if(!Plan::loop) steps = 1;
-			equirect_rows_kernel<F, CH, WX, Plan::loop, Plan::minb><<<grid_for(steps), block, 0, stream>>>(s8, d8, prm, scl, steps);
-			return cudaGetLastError();
+			pe = launch_pdl(equirect_rows_kernel<F, CH, WX, Plan::loop, Plan::minb>, grid_for(steps), block, 0, stream, s8, d8, prm, scl, steps);
+			return pe;
 		}
 
 		template<int F>

@@ -46,6 +46,8 @@ namespace cacao {
 		template<int F, int CH>
 		__global__ void __launch_bounds__(256) downsample2x_vec_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t runs_per_row, uint32_t h, uint32_t ho, uint64_t src_pitch, uint64_t dst_pitch) {
 			using S = MipShape<F, CH>;
+			pdl_launch_dependents(); // a mip chain is a string of short dependent launches: each one's launch
+			pdl_wait();              // latency and block scheduling overlap its predecessor (cacao_device.cuh)
 			const uint32_t rx = blockIdx.x * blockDim.x + threadIdx.x;
 			const uint32_t y = blockIdx.y;
 			if(rx >= runs_per_row || y >= ho) return;
@@ -79,6 +81,8 @@ namespace cacao {
 		template<int F, int CH>
 		__global__ void __launch_bounds__(256) downsample2x_px_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t w, uint32_t h, uint32_t wo, uint32_t ho, uint32_t x_begin) {
 			using T = typename FmtTraits<F>::type;
+			pdl_launch_dependents();
+			pdl_wait();
 			const uint32_t x = x_begin + blockIdx.x * blockDim.x + threadIdx.x;
 			const uint32_t y = blockIdx.y;
 			if(x >= wo || y >= ho) return;
@@ -118,13 +122,13 @@ namespace cacao {
 				const uint32_t h_left = h - 2u * y0;
 				if(runs) {
 					const dim3 grid((runs + 255) / 256, rows, 1);
-					downsample2x_vec_kernel<F, CH><<<grid, 256, 0, stream>>>(s8 + 2ull * y0 * src_pitch, d8 + y0 * dst_pitch, runs, h_left, rows, src_pitch, dst_pitch);
+					if(cudaError_t e = launch_pdl(downsample2x_vec_kernel<F, CH>, grid, dim3(256), 0, stream, s8 + 2ull * y0 * src_pitch, d8 + y0 * dst_pitch, runs, h_left, rows, src_pitch, dst_pitch); e != cudaSuccess) return e;
 					if(launches) *launches += 1;
 				}
 				if(runs * S::K < wo) {
 					const uint32_t rest = wo - runs * S::K;
 					const dim3 grid((rest + 255) / 256, rows, 1);
-					downsample2x_px_kernel<F, CH><<<grid, 256, 0, stream>>>(s8 + 2ull * y0 * src_pitch, d8 + y0 * dst_pitch, w, h_left, wo, rows, runs * S::K);
+					if(cudaError_t e = launch_pdl(downsample2x_px_kernel<F, CH>, grid, dim3(256), 0, stream, s8 + 2ull * y0 * src_pitch, d8 + y0 * dst_pitch, w, h_left, wo, rows, runs * S::K); e != cudaSuccess) return e;
 					if(launches) *launches += 1;
 				}
 			}

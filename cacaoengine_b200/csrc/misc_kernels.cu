@@ -11,6 +11,8 @@ namespace cacao {
 		// 16-byte aligned every row moves as coalesced 16-B vectors, otherwise byte by byte.
 		__global__ void __launch_bounds__(256) flip_rows_vec_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t units_per_row, uint32_t h) {
 			const uint64_t total = units_per_row * h;
+			pdl_launch_dependents();
+			pdl_wait(); // cacao_device.cuh
 			const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
 			for(uint64_t u = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; u < total; u += stride) {
 				const uint64_t y = u / units_per_row, x = u - y * units_per_row;
@@ -19,6 +21,8 @@ namespace cacao {
 		}
 		__global__ void __launch_bounds__(256) flip_rows_byte_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint64_t pitch, uint32_t h) {
 			const uint64_t total = pitch * h;
+			pdl_launch_dependents();
+			pdl_wait();
 			const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
 			for(uint64_t u = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; u < total; u += stride) {
 				const uint64_t y = u / pitch, x = u - y * pitch;
@@ -159,11 +163,8 @@ namespace cacao {
 
 	cudaError_t flip_rows_launch(const void* src, void* dst, uint64_t pitch, uint32_t h, int sm_count, cudaStream_t stream) {
 		const bool vec = (pitch % 16 == 0) && (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0);
-		if(vec)
-			flip_rows_vec_kernel<<<grid_for(pitch / 16 * h, sm_count), 256, 0, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), pitch / 16, h);
-		else
-			flip_rows_byte_kernel<<<grid_for(pitch * h, sm_count), 256, 0, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), pitch, h);
-		return cudaGetLastError();
+		if(vec) return launch_pdl(flip_rows_vec_kernel, dim3(grid_for(pitch / 16 * h, sm_count)), dim3(256), 0, stream, static_cast<const uint4*>(src), static_cast<uint4*>(dst), pitch / 16, h);
+		return launch_pdl(flip_rows_byte_kernel, dim3(grid_for(pitch * h, sm_count)), dim3(256), 0, stream, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), pitch, h);
 	}
 
 	cudaError_t shift_left_u16_launch(const void* src, void* dst, uint64_t samples, uint32_t shift, cudaStream_t stream) {
