@@ -165,13 +165,11 @@ namespace cacao {
 	cudaError_t launch_convert_lanes(const void* src, void* dst, uint64_t n_runs, const uint32_t* lanes_global, cudaStream_t stream, FlipMap flip = FlipMap()) {
 		using S = LanesShape<SC, DC>;
 		if(n_runs == 0) return cudaSuccess;
-		auto plain = convert_lanes_kernel<SC, DC, false>;
-		auto flipped = convert_lanes_kernel<SC, DC, true>;
-		static const int resident = [&] {
-			cudaFuncSetAttribute(plain, cudaFuncAttributeMaxDynamicSharedMemorySize, S::smem_bytes);
-			cudaFuncSetAttribute(flipped, cudaFuncAttributeMaxDynamicSharedMemorySize, S::smem_bytes);
-			return resident_blocks(plain, S::threads, S::smem_bytes);
-		}(); // per shape; one device kind per process
+		auto kern = flip.per_row ? convert_lanes_kernel<SC, DC, true> : convert_lanes_kernel<SC, DC, false>;
+		// a function attribute belongs to the device it was set on, and one process may drive several
+		// (ConvertBatch(..., devices)): set it with every launch, as the other kernels above 48 KiB do
+		if(cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::smem_bytes); e != cudaSuccess) return e;
+		static const int resident = resident_blocks(kern, S::threads, S::smem_bytes); // per shape (the mirrored form has the same footprint); one device kind per process
 		// passes per block: whole waves of long contiguous ranges; the shapes that write 96+ bytes per run measure
 		// better with short ranges (profiles/r2_lut_forms_sweep.log)
 		uint32_t iters = wave_aligned_iters(n_runs, S::threads, resident, S::OB >= 96 ? 8 : 32);
@@ -179,7 +177,7 @@ namespace cacao {
 		const uint64_t runs_per_block = static_cast<uint64_t>(S::threads) * iters;
 		const uint64_t blocks = (n_runs + runs_per_block - 1) / runs_per_block;
 		if(blocks > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
-		return launch_pdl(flip.per_row ? flipped : plain, dim3(static_cast<unsigned>(blocks)), dim3(S::threads), S::smem_bytes, stream, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lanes_global, flip);
+		return launch_pdl(kern, dim3(static_cast<unsigned>(blocks)), dim3(S::threads), S::smem_bytes, stream, static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), n_runs, iters, lanes_global, flip);
 	}
 
 } // namespace cacao

@@ -98,3 +98,27 @@ def test_cubetool_project_on_two_gpus(built_lib, oracle, tmp_path):
 	for k, nm in enumerate(["right", "left", "up", "down", "front", "back"]):
 		got = np.load(tmp_path / "o" / f"p_{nm}.npy")
 		assert (got.view(np.uint32) == want[k].view(np.uint32)).all(), nm
+
+
+def test_table_kernel_on_every_device(built_lib, oracle):
+	"""The 16 -> 8 bit kernel of convert_lanes.cuh needs 80 KiB of dynamic shared memory, an opt-in that is a
+	per-device function attribute: one process driving several devices must set it on each.  A job large
+	enough for that kernel (1.3 Mpixel RGBA16 -> RGB8, plain and mirrored) on every device of the box."""
+	from cacaoengine_b200 import _capi as c, device
+
+	w, h = 1280, 1024
+	src = oracle.synth(w * h * 4, c.FMT_U16, 4, 24)
+	want = oracle.convert(src, 4, 3, c.FMT_U16, c.FMT_U8)
+	flipped = want.reshape(h, w * 3)[::-1].copy().reshape(-1)
+	for d in reversed(range(_devices())):  # last device first: the attribute must not only exist where it was set first
+		device.init(d)
+		a, b = device.malloc(src.nbytes, d), device.malloc(want.nbytes, d)
+		device.upload(a, src, device=d)
+		got = np.empty_like(want)
+		device.convert(a, b, w * h, 4, 3, c.FMT_U16, c.FMT_U8, device=d)
+		device.download(got, b, device=d)
+		assert same_bits(got, want), d
+		device.convert_flip(a, b, w, h, 1, 4, 3, c.FMT_U16, c.FMT_U8, device=d)
+		device.download(got, b, device=d)
+		assert same_bits(got, flipped), d
+		device.free(a, d), device.free(b, d)
