@@ -33,6 +33,9 @@ SIGNATURES = {
 	"cacao_img_launch_count": (_u64, []),
 	"cacao_img_malloc": (_i, [_i, C.POINTER(_vp), _u64]),
 	"cacao_img_free": (_i, [_i, _vp]),
+	"cacao_img_malloc_shareable": (_i, [_i, C.POINTER(_vp), _u64, C.POINTER(C.c_int), C.POINTER(_u64)]),
+	"cacao_img_import_shareable": (_i, [_i, C.c_int, _u64, C.POINTER(_vp)]),
+	"cacao_img_free_shareable": (_i, [_i, _vp]),
 	"cacao_img_host_alloc": (_i, [C.POINTER(_vp), _u64]),
 	"cacao_img_host_free": (_i, [_vp]),
 	"cacao_img_host_register": (_i, [_vp, _u64]),

@@ -3,8 +3,12 @@
 //
 // There is deliberately no CPU implementation of any pixel loop in this file or anywhere in the
 // library: without a CUDA device every compute entry point returns CACAO_E_NO_DEVICE.
+#include <cuda.h> // CUmem* types for the shareable allocations; entry points come from cudaGetDriverEntryPoint
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
+#include <map>
 #include <chrono>
 #include <condition_variable>
 #include <thread>
@@ -1615,6 +1619,147 @@ int cacao_img_checksum(int device, const void* src_dev, uint64_t bytes, uint64_t
 	CU_TRY(cudaMemcpyAsync(&host, c->checksum_dev, sizeof host, cudaMemcpyDeviceToHost, s));
 	CU_TRY(cudaStreamSynchronize(s));
 	*out = host;
+	return CACAO_OK;
+}
+
+// ---- device memory that another API or process takes over without a copy -------------------------
+namespace {
+	// The CUDA driver's virtual-memory calls, fetched at run time like cuTensorMapEncodeTiled in equirect_tma.cu
+	// (the library links the runtime statically and has no link-time dependency on libcuda).
+	struct VmmApi {
+		CUresult (*get_granularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+		CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+		CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+		CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+		CUresult (*address_free)(CUdeviceptr, size_t) = nullptr;
+		CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+		CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+		CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+		CUresult (*export_handle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+		CUresult (*import_handle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+		bool ok = false;
+		VmmApi() {
+			auto get = [](const char* name, auto& fn) {
+				void* p = nullptr;
+				cudaDriverEntryPointQueryResult q;
+				if(cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+				fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(p);
+				return p != nullptr;
+			};
+			ok = get("cuMemGetAllocationGranularity", get_granularity) & get("cuMemCreate", create) & get("cuMemRelease", release) & get("cuMemAddressReserve", reserve) &
+				 get("cuMemAddressFree", address_free) & get("cuMemMap", map) & get("cuMemUnmap", unmap) & get("cuMemSetAccess", set_access) &
+				 get("cuMemExportToShareableHandle", export_handle) & get("cuMemImportFromShareableHandle", import_handle);
+		}
+	};
+	const VmmApi& vmm() {
+		static const VmmApi api;
+		return api;
+	}
+	struct Shareable {
+		CUmemGenericAllocationHandle handle;
+		size_t bytes;
+	};
+	std::mutex g_shareable_mutex;
+	std::map<void*, Shareable> g_shareable;
+
+	CUmemAllocationProp shareable_prop(int device) {
+		CUmemAllocationProp prop = {};
+		prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+		prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+		prop.location.id = device;
+		prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+		return prop;
+	}
+
+	// reserve + map + allow read/write from `device`; on failure everything taken so far is given back
+	int map_shareable(int device, CUmemGenericAllocationHandle handle, size_t bytes, void** dev_ptr) {
+		const VmmApi& v = vmm();
+		CUdeviceptr va = 0;
+		if(v.reserve(&va, bytes, 0, 0, 0) != CUDA_SUCCESS) {
+			v.release(handle);
+			return fail(CACAO_E_NO_MEMORY, "cuMemAddressReserve(%llu) failed", static_cast<unsigned long long>(bytes));
+		}
+		CUmemAccessDesc access = {};
+		access.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+		access.location.id = device;
+		access.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+		if(v.map(va, bytes, 0, handle, 0) != CUDA_SUCCESS) {
+			v.address_free(va, bytes);
+			v.release(handle);
+			return fail(CACAO_E_CUDA, "cuMemMap failed");
+		}
+		if(v.set_access(va, bytes, &access, 1) != CUDA_SUCCESS) {
+			v.unmap(va, bytes);
+			v.address_free(va, bytes);
+			v.release(handle);
+			return fail(CACAO_E_CUDA, "cuMemSetAccess failed");
+		}
+		*dev_ptr = reinterpret_cast<void*>(va);
+		std::lock_guard<std::mutex> lock(g_shareable_mutex);
+		g_shareable[*dev_ptr] = {handle, bytes};
+		return CACAO_OK;
+	}
+}
+
+int cacao_img_malloc_shareable(int device, void** dev_ptr, uint64_t bytes, int* fd, uint64_t* mapped_bytes) {
+	if(!dev_ptr || !fd || !mapped_bytes) return fail(CACAO_E_BAD_ARG, "null out-pointer");
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	const VmmApi& v = vmm();
+	if(!v.ok) return fail(CACAO_E_CUDA, "the CUDA driver lacks the virtual-memory API");
+	const CUmemAllocationProp prop = shareable_prop(c->device);
+	size_t gran = 0;
+	if(v.get_granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0) return fail(CACAO_E_CUDA, "cuMemGetAllocationGranularity failed");
+	const size_t size = ((bytes ? bytes : 1) + gran - 1) / gran * gran;
+	CUmemGenericAllocationHandle handle = 0;
+	if(v.create(&handle, size, &prop, 0) != CUDA_SUCCESS) return fail(CACAO_E_NO_MEMORY, "cuMemCreate(%llu) failed", static_cast<unsigned long long>(size));
+	int out_fd = -1;
+	if(v.export_handle(&out_fd, handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS) {
+		v.release(handle);
+		return fail(CACAO_E_CUDA, "cuMemExportToShareableHandle failed");
+	}
+	rc = map_shareable(c->device, handle, size, dev_ptr);
+	if(rc) {
+		close(out_fd);
+		return rc;
+	}
+	*fd = out_fd;
+	*mapped_bytes = size;
+	return CACAO_OK;
+}
+
+int cacao_img_import_shareable(int device, int fd, uint64_t mapped_bytes, void** dev_ptr) {
+	if(!dev_ptr || fd < 0 || mapped_bytes == 0) return fail(CACAO_E_BAD_ARG, "import_shareable: null out-pointer, bad descriptor or empty size");
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	const VmmApi& v = vmm();
+	if(!v.ok) return fail(CACAO_E_CUDA, "the CUDA driver lacks the virtual-memory API");
+	CUmemGenericAllocationHandle handle = 0;
+	if(v.import_handle(&handle, reinterpret_cast<void*>(static_cast<uintptr_t>(fd)), CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) != CUDA_SUCCESS) return fail(CACAO_E_CUDA, "cuMemImportFromShareableHandle failed (descriptor %d)", fd);
+	return map_shareable(c->device, handle, static_cast<size_t>(mapped_bytes), dev_ptr);
+}
+
+int cacao_img_free_shareable(int device, void* dev_ptr) {
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	Shareable sh;
+	{
+		std::lock_guard<std::mutex> lock(g_shareable_mutex);
+		auto it = g_shareable.find(dev_ptr);
+		if(it == g_shareable.end()) return fail(CACAO_E_BAD_ARG, "free_shareable: not a pointer from malloc_shareable / import_shareable");
+		sh = it->second;
+		g_shareable.erase(it);
+	}
+	CU_TRY(cudaDeviceSynchronize());
+	const VmmApi& v = vmm();
+	const CUdeviceptr va = reinterpret_cast<CUdeviceptr>(dev_ptr);
+	if(v.unmap(va, sh.bytes) != CUDA_SUCCESS || v.address_free(va, sh.bytes) != CUDA_SUCCESS || v.release(sh.handle) != CUDA_SUCCESS) return fail(CACAO_E_CUDA, "unmapping a shareable allocation failed");
 	return CACAO_OK;
 }
 

@@ -34,6 +34,23 @@ def free(ptr: int, device: int = -1) -> None:
 	capi.check(capi.lib().cacao_img_free(device, ptr))
 
 
+def malloc_shareable(nbytes: int, device: int = -1) -> tuple[int, int, int]:
+	"""Device memory exported as a POSIX file descriptor: (device pointer, fd, mapped size).  See cacao_img.h."""
+	p, fd, size = C.c_void_p(), C.c_int(-1), C.c_uint64(0)
+	capi.check(capi.lib().cacao_img_malloc_shareable(device, C.byref(p), nbytes, C.byref(fd), C.byref(size)))
+	return int(p.value), int(fd.value), int(size.value)
+
+
+def import_shareable(fd: int, mapped_bytes: int, device: int = -1) -> int:
+	p = C.c_void_p()
+	capi.check(capi.lib().cacao_img_import_shareable(device, fd, mapped_bytes, C.byref(p)))
+	return int(p.value)
+
+
+def free_shareable(ptr: int, device: int = -1) -> None:
+	capi.check(capi.lib().cacao_img_free_shareable(device, ptr))
+
+
 def host_alloc(nbytes: int) -> tuple[int, np.ndarray]:
 	"""Pinned host buffer: (address, uint8 numpy view).  Release with host_free(address)."""
 	p = C.c_void_p()

@@ -74,6 +74,19 @@ uint64_t cacao_img_launch_count(void);           /* kernels launched by this lib
 /* ---- device-buffer / upload / readback layer (new; no reference counterpart) -------------- */
 int cacao_img_malloc(int device, void** dev_ptr, uint64_t bytes);
 int cacao_img_free(int device, void* dev_ptr);
+/* Device memory another API or another process takes over WITHOUT a copy (the hand-off of a finished
+ * cube / texture to the graphics backend, which today memcpy's six faces into a staging buffer --
+ * engine/src/vulkan/impls/VulkanCubemap.cpp:30-41).  The allocation is a CUDA virtual-memory allocation exported as
+ * a POSIX file descriptor: the handle type VK_KHR_external_memory_fd (VkImportMemoryFdInfoKHR, OPAQUE_FD) and
+ * GL_EXT_memory_object_fd import, and what cacao_img_import_shareable maps in another process or context.  Use the
+ * pointer as `dst` of any CACAO_MEM_DEVICE call (cacao_img_engine_cube writes the contiguous RGB8 cube straight
+ * into it).  `*mapped_bytes` is the size rounded up to the allocation granularity -- the size the importer must
+ * name.  The descriptor belongs to the caller (close() it once it has been handed over; the memory lives until
+ * every mapping is freed).  The other direction needs no call here: memory a Vulkan / GL allocation exported and
+ * the application imported (cudaImportExternalMemory) is an ordinary device pointer to this library. */
+int cacao_img_malloc_shareable(int device, void** dev_ptr, uint64_t bytes, int* fd, uint64_t* mapped_bytes);
+int cacao_img_import_shareable(int device, int fd, uint64_t mapped_bytes, void** dev_ptr);
+int cacao_img_free_shareable(int device, void* dev_ptr); /* for pointers of either call; synchronises the device */
 int cacao_img_host_alloc(void** host_ptr, uint64_t bytes); /* pinned, portable across devices */
 int cacao_img_host_free(void* host_ptr);
 /* Pin memory the caller already owns (a std::vector's storage, a shared-memory segment several processes map,

@@ -192,3 +192,61 @@ def test_load_chains_from_concurrent_threads(built_lib, oracle):
 
 	with ThreadPoolExecutor(max_workers=8) as ex:
 		assert all(ex.map(run, range(48)))
+
+
+_CONSUMER = r"""
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, sys.argv[4])
+from cacaoengine_b200 import device
+fd, mapped, n = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+device.init(0)
+p = device.import_shareable(fd, mapped)
+out = np.empty(n, np.uint8)
+device.download(out, p)
+device.sync()
+device.free_shareable(p)
+print(hashlib.sha256(out.tobytes()).hexdigest())
+"""
+
+
+@pytest.mark.gpu
+def test_cube_handed_over_through_a_file_descriptor(built_lib, oracle):
+	"""SURVEY 8 f-4, the hand-off itself: the finished cube is written into device memory that was exported as a
+	POSIX file descriptor (cacao_img_malloc_shareable -- the handle VK_KHR_external_memory_fd / GL_EXT_memory_object_fd
+	import), and ANOTHER PROCESS with its own CUDA context maps that descriptor and finds the contiguous RGB8 cube
+	there: no host copy, no staging buffer (engine/src/vulkan/impls/VulkanCubemap.cpp:30-41 builds one by hand).
+	The consumer here is a CUDA context rather than a Vulkan device -- the image has no graphics headers -- but the
+	exporting side is the same call either way."""
+	import hashlib
+	import os
+	import subprocess
+	import sys
+
+	from cacaoengine_b200 import _capi as c, device
+
+	device.init()
+	w = h = 160
+	src = _faces(oracle, w, h, 4, c.FMT_U16, 77)
+	flags = device.CUBE_FLIP_ROWS | device.CUBE_MIPS
+	want = oracle.engine_cube(src, w, h, 4, flip=True, mips=True)
+	a = DevBuf(src.nbytes)
+	device.upload(a.ptr, src)
+	ptr, fd, mapped = device.malloc_shareable(want.size)
+	assert fd >= 0 and mapped >= want.size
+	face_bytes = w * h * 8
+	device.engine_cube([a.ptr + f * face_bytes for f in range(6)], w, h, 4, c.FMT_U16, ptr, flags)
+	device.sync()
+	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+	r = subprocess.run([sys.executable, "-c", _CONSUMER, str(fd), str(mapped), str(want.size), root], pass_fds=(fd,), capture_output=True, text=True, timeout=300)
+	assert r.returncode == 0, r.stderr[-2000:]
+	assert r.stdout.strip().splitlines()[-1] == hashlib.sha256(want.tobytes()).hexdigest()
+	# the producer's own mapping still reads the same bytes, and a plain pointer is refused by free_shareable
+	got = np.empty_like(want)
+	device.download(got, ptr)
+	assert (got == want).all()
+	with pytest.raises(Exception):
+		device.free_shareable(a.ptr)
+	os.close(fd)
+	device.free_shareable(ptr)
+	a.free()
