@@ -76,7 +76,7 @@ namespace cacao {
 		ctx.gray16_cap = 255u; // unused: 16 -> 8 bit takes the depth step first, gray is the 8-bit rule (convert_pixel.cuh)
 		ctx.lut = nullptr;
 		ctx.lut2 = nullptr;
-		ctx.lanes = smem_raw + (lane << 2) - (static_cast<int>(kLanesHiBase) << 7);
+		ctx.lanes = smem_raw + (lane << 2);
 		uint8_t* stage = smem_raw + kLanesBytes + (threadIdx.x >> 5) * (32 * S::OB);
 		// with the row mirror, a warp's 32 runs leave as one contiguous piece only if no warp straddles a row
 		const bool warp_rows = !FLIP || (flip.per_row % 32u == 0u);

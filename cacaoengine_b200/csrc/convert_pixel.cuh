@@ -136,7 +136,7 @@ namespace cacao {
 	// bits 16..23 of the result are table[v]; magic = lanes_magic(...)
 	__device__ __forceinline__ uint32_t lanes_sum(const PixelCtx& ctx, uint32_t magic) {
 		const uint32_t bits = __float_as_uint(__fadd_rn(__uint_as_float(magic), static_cast<float>(kLanesBias) - 8388608.0f)); // float(v + bias), exact
-		return bits + *reinterpret_cast<const uint32_t*>(ctx.lanes + ((bits >> 16) << 7));
+		return bits + *reinterpret_cast<const uint32_t*>(ctx.lanes + (((bits >> 16) - kLanesHiBase) << 7)); // the constant folds into the LDS offset
 	}
 
 	template<int Mode>
