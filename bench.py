@@ -664,8 +664,18 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 	if world == 1:
 		# config 3's geometry on the narrow sample formats (one launch each): the shapes of VERDICT r1 item 2
 		from cacaoengine_b200 import FMT_U16
+		# what bounds them is not HBM (ncu, profiles/r2_equirect_rows_vs_gather_ncu.txt): the roofline fraction is
+		# reported as the contract asks, the measured limiter next to it
+		limiter = {"rgba8": "instruction issue: 126 warp instructions per pixel, issue-active 79 %, DRAM 21 % (48 of them are the four taps, 16 integer->float and the packed fp32 filter the spec fixes)",
+			"rgba16": "L1 data pipe 78 % and instruction issue 73 % together (8-byte taps: two requests per tap row)",
+			"rgba16f": "L1 data pipe 78 % and instruction issue 73 % together (8-byte taps: two requests per tap row)",
+			"gray8": "instruction issue: 77 warp instructions per pixel for 2.3 bytes, issue-active 69 %, DRAM 5 % (the projection alone is ~45)",
+			"rgb8": "instruction issue (3-byte texels are realigned from an aligned window), DRAM 14 %"}
 		for nm, c_, f_, b_ in (("rgba8", 4, FMT_U8, 1), ("rgba16", 4, FMT_U16, 2), ("rgba16f", 4, FMT_F16, 2), ("gray8", 1, FMT_U8, 1), ("rgb8", 3, FMT_U8, 1)):
-			equirect(f"cfg3shape_equirect_8192x4096_{nm}_to_6x2048", 8192, 4096, 2048, c_, f_, b_, 20, "config 3's geometry on another sample format / layout")
+			key = f"cfg3shape_equirect_8192x4096_{nm}_to_6x2048"
+			equirect(key, 8192, 4096, 2048, c_, f_, b_, 20, "config 3's geometry on another sample format / layout")
+			if key in out:
+				out[key]["limiter"] = limiter[nm]
 	if world == 1:  # the fusions, after the BASELINE configs
 		equirect("cfg3_fused_rgba32f_to_rgba16f_cube", 8192, 4096, 2048, 4, FMT_F32, 4, 20, "config 3 with the cube written as RGBA16F in the same pass (Spec B.4): resample + format convert", dst=(4, FMT_F16, 2))
 		engine_chain("engine_cube_6x2048sq_rgba16_to_rgb8_flipped", 2048, 2048, 6, 50)
