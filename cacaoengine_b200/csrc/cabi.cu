@@ -799,8 +799,12 @@ namespace {
 		uint64_t out_bytes = 0;
 		for(const Piece& p : pieces) out_bytes += static_cast<uint64_t>(p.u.row_end - p.u.row_begin) * row_bytes;
 		trace.out_bytes = out_bytes;
-		trace.path = (src_pg || dst_pg) ? "sequential, pageable" : (static_cast<uint64_t>(hi - lo) * pitch + out_bytes < (32ull << 20) ? "sequential, small" : "pipelined, pinned");
-		if(src_pg || dst_pg || static_cast<uint64_t>(hi - lo) * pitch + out_bytes < (32ull << 20)) {
+		uint64_t pipe_min = 32ull << 20, chunk_bytes = kXferChunk;
+		if(const char* e = getenv("CACAO_EQ_PIPE_MIN_KIB")) pipe_min = static_cast<uint64_t>(atoll(e)) << 10; // dev switches (dev/time_equirect_host.py)
+		if(const char* e = getenv("CACAO_EQ_CHUNK_KIB")) chunk_bytes = std::max<uint64_t>(4096, static_cast<uint64_t>(atoll(e)) << 10);
+		const bool small_job = static_cast<uint64_t>(hi - lo) * pitch + out_bytes < pipe_min;
+		trace.path = (src_pg || dst_pg) ? "sequential, pageable" : (small_job ? "sequential, small" : "pipelined, pinned");
+		if(src_pg || dst_pg || small_job) {
 			rc = upload_any(c, c->stage_in[0], up_base, static_cast<uint64_t>(hi - lo) * pitch, c->s_run);
 			if(rc) return rc;
 			unsigned launches = 0;
@@ -817,7 +821,7 @@ namespace {
 			}
 			return download_segments(c, segs, c->s_run);
 		}
-		const uint64_t rows_per_chunk = std::max<uint64_t>(1, kXferChunk / pitch);
+		const uint64_t rows_per_chunk = std::max<uint64_t>(1, chunk_bytes / pitch);
 		auto read_back = [&](const Piece& p) -> int {
 			const uint64_t off = stored_at(p.u), n = static_cast<uint64_t>(p.u.row_end - p.u.row_begin) * row_bytes;
 			CU_TRY(cudaMemcpyAsync(faces[p.u.face] + off, c->stage_out[0] + p.u.face * face_bytes + off, n, cudaMemcpyDeviceToHost, c->s_out));
