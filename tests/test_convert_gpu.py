@@ -412,6 +412,41 @@ def test_full_size_cfg2_batch_by_sampling(oracle):
 		b.free()
 
 
+def test_depth_table_kernel_beyond_4_gib(oracle, monkeypatch):
+	"""The 16 -> 8 bit kernel of convert_lanes.cuh on a stream whose byte offsets exceed 2^32 (640 Mpixel RGBA16 =
+	5.1 GB -> RGB8, flipped as 40 images of 4096^2): equal to the two-level form of the same conversion as a whole
+	(checksum), equal to the oracle on sampled rows of the first, a middle and the last image, and equal to the
+	conversion of each half on its own."""
+	from cacaoengine_b200 import _capi as c, device
+	from gpu_util import DevBuf
+
+	w = h = 4096
+	count = 40
+	ppi = w * h
+	src, dst, dst2 = DevBuf(ppi * count * 8), DevBuf(ppi * count * 3), DevBuf(ppi * count * 3)
+	device.synth(src.ptr, ppi * count * 4, c.FMT_U16, 4, 0xC0FFEE + 11)
+	device.convert_flip(src.ptr, dst.ptr, w, h, count, 4, 3, c.FMT_U16, c.FMT_U8)
+	whole = device.checksum(dst.ptr, ppi * count * 3)
+	rows = 8
+	for k in (0, 19, count - 1):
+		for y in (0, 1777, h - rows):  # source rows [y, y + rows) land, mirrored, at rows [h - y - rows, h - y)
+			got = np.empty(rows * w * 3, np.uint8)
+			device.download(got, dst.ptr + (k * ppi + (h - y - rows) * w) * 3)
+			band = oracle.synth(rows * w * 4, c.FMT_U16, 4, 0xC0FFEE + 11, first_sample=(k * ppi + y * w) * 4)
+			want = oracle.convert(band, 4, 3, c.FMT_U16, c.FMT_U8).reshape(rows, w * 3)[::-1].reshape(-1)
+			assert same_bits(got, want), (k, y)
+	monkeypatch.setenv("CACAO_LUT_MODE", "two")
+	device.convert_flip(src.ptr, dst2.ptr, w, h, count, 4, 3, c.FMT_U16, c.FMT_U8)
+	assert device.checksum(dst2.ptr, ppi * count * 3) == whole
+	monkeypatch.delenv("CACAO_LUT_MODE")
+	half = count // 2
+	device.convert_flip(src.ptr, dst2.ptr, w, h, half, 4, 3, c.FMT_U16, c.FMT_U8)
+	device.convert_flip(src.ptr + half * ppi * 8, dst2.ptr + half * ppi * 3, w, h, count - half, 4, 3, c.FMT_U16, c.FMT_U8)
+	assert device.checksum(dst2.ptr, ppi * count * 3) == whole
+	for b in (src, dst, dst2):
+		b.free()
+
+
 def test_round_trip_properties():
 	"""Size-independent properties at a large size: RGB->RGBA->RGB is the identity, U8->U16->(>>8) too,
 	and U8->F32->U8 returns every byte."""
