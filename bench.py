@@ -503,6 +503,72 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 			pano_done()
 		else:
 			res["e2e"] = {"unavailable": "/dev/shm on this box cannot hold the shared panorama + cube"}
+		# ---- (3) the cube assembled on ONE GPU ("optional device-resident assembly on GPU 0 ... over NVLink").
+		# Rank 0 exports a cube buffer (cacao_img_ipc_export); every other rank opens it and hands the mapping to its
+		# launch as the destination, so resampling and gather are ONE kernel per rank whose stores cross NVLink and
+		# land in place.  Beside it the same job as the library formulation: each rank resamples into its own buffer,
+		# then grouped NCCL send / recv of every unit into its place in rank 0's cube.
+		try:
+			cube_bytes = 6 * N * N * bpp
+			hbuf = torch.zeros(64 + 8, dtype=torch.uint8, device=f"cuda:{dev}")
+			target = None
+			if rank == 0:
+				target = device.malloc(cube_bytes, dev)
+				torch.cuda.synchronize()
+				handle, off = device.ipc_export(target, dev)
+				hbuf.copy_(torch.tensor(list(handle) + list(off.to_bytes(8, "little")), dtype=torch.uint8))
+			dist.broadcast(hbuf, 0)
+			raw = bytes(hbuf.cpu().tolist())
+			handle, off = raw[:64], int.from_bytes(raw[64:], "little")
+			remote = target if rank == 0 else device.ipc_import(handle, off, dev)
+
+			def fused():
+				device.equirect_to_cube_units(src.data_ptr(), W, H, ch, fmt, remote, N, units, src_row0=w0, src_rows=wn, device=dev, stream=stream)
+
+			ms_f = timed_region(torch, dist, world, fused, 20, 3)
+			ok_f = None
+			if rank == 0:
+				ok_f = device.checksum(target, cube_bytes, device=dev, stream=stream) == device.checksum(whole.data_ptr(), cube_bytes, device=dev, stream=stream)
+			# the library formulation: kernel, then NCCL point-to-point of every unit into rank 0's cube
+			everyone_units = [None] * world
+			dist.all_gather_object(everyone_units, [(u.face, u.row_begin, u.row_end) for u in units])
+			target_t = alloc(cube_bytes) if rank == 0 else None
+
+			def two_step():
+				device.equirect_to_cube_units(src.data_ptr(), W, H, ch, fmt, dst.data_ptr(), N, units, src_row0=w0, src_rows=wn, device=dev, stream=stream)
+				ops = []
+				if rank == 0:
+					for f, r0, r1 in everyone_units[0]:
+						a = (f * N + r0) * N * bpp
+						target_t[a:a + (r1 - r0) * N * bpp].copy_(dst[a:a + (r1 - r0) * N * bpp], non_blocking=True)
+					for r in range(1, world):
+						for f, r0, r1 in everyone_units[r]:
+							a = (f * N + r0) * N * bpp
+							ops.append(dist.P2POp(dist.irecv, target_t[a:a + (r1 - r0) * N * bpp], r))
+				else:
+					for f, r0, r1 in everyone_units[rank]:
+						a = (f * N + r0) * N * bpp
+						ops.append(dist.P2POp(dist.isend, dst[a:a + (r1 - r0) * N * bpp], 0))
+				for w_ in dist.batch_isend_irecv(ops):
+					w_.wait()
+
+			ms_n = timed_region(torch, dist, world, two_step, 10, 3)
+			ok_n = None
+			if rank == 0:
+				ok_n = device.checksum(target_t.data_ptr(), cube_bytes, device=dev, stream=stream) == device.checksum(whole.data_ptr(), cube_bytes, device=dev, stream=stream)
+			remote_bytes = cube_bytes - sum((r1 - r0) * N * bpp for f, r0, r1 in everyone_units[0])
+			res["gather_on_gpu0"] = {"value": 6 * N * N / ms_f / 1e6, "unit": UNIT, "ms_per_step": ms_f, "cube_equals_single_gpu_cube": ok_f, "bytes_over_nvlink_per_step": remote_bytes, "nvlink_gbs_into_gpu0": remote_bytes / ms_f / 1e6,
+				"path": f"{world} ranks: each rank's one resampling launch stores its (face, band) rows straight into rank 0's cube through a CUDA IPC mapping (cacao_img_ipc_export / _import): compute + gather in one kernel, no per-rank output buffer; CUDA events, max over ranks",
+				"kernel_then_nccl": {"ms_per_step": ms_n, "value": 6 * N * N / ms_n / 1e6, "cube_equals_single_gpu_cube": ok_n, "path": "each rank resamples into its own buffer, then torch.distributed.batch_isend_irecv (NCCL) of every unit into its place in rank 0's cube"}}
+			del target_t
+			torch.cuda.synchronize()
+			dist.barrier()
+			if rank == 0:
+				device.free(target, dev)
+			else:
+				device.ipc_close(remote, off, dev)
+		except Exception as e:  # the leg is an extra: never take the line down with it
+			res["gather_on_gpu0"] = {"unavailable": repr(e)}
 		del whole
 		return res
 

@@ -36,6 +36,10 @@ SIGNATURES = {
 	"cacao_img_malloc_shareable": (_i, [_i, C.POINTER(_vp), _u64, C.POINTER(C.c_int), C.POINTER(_u64)]),
 	"cacao_img_import_shareable": (_i, [_i, C.c_int, _u64, C.POINTER(_vp)]),
 	"cacao_img_free_shareable": (_i, [_i, _vp]),
+	"cacao_img_ipc_export": (_i, [_i, _vp, C.c_char_p, C.POINTER(_u64)]),
+	"cacao_img_ipc_import": (_i, [_i, C.c_char_p, _u64, C.POINTER(_vp)]),
+	"cacao_img_ipc_close": (_i, [_i, _vp, _u64]),
+	"cacao_img_enable_peer_access": (_i, [_i, _i]),
 	"cacao_img_host_alloc": (_i, [C.POINTER(_vp), _u64]),
 	"cacao_img_host_free": (_i, [_vp]),
 	"cacao_img_host_register": (_i, [_vp, _u64]),

@@ -1767,6 +1767,86 @@ int cacao_img_free_shareable(int device, void* dev_ptr) {
 	return CACAO_OK;
 }
 
+// ---- one buffer, several processes: the device-side gather of a sharded job ---------------------------
+// One process per GPU is how a box is driven (bench.py under torchrun, ce-cubetool --gpus in threads).  A rank that
+// opens another rank's buffer gets a pointer to the SAME memory; handed to any CACAO_MEM_DEVICE call as `dst`, the
+// kernel's own stores then cross NVLink and land in place -- a sharded cubemap is assembled on one GPU by the
+// resampling launches themselves, with no gather step and no intermediate buffer.
+int cacao_img_ipc_export(int device, void* dev_ptr, unsigned char* handle64, uint64_t* offset) {
+	if(!dev_ptr || !handle64 || !offset) return fail(CACAO_E_BAD_ARG, "ipc_export: null pointer");
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the handle is 64 opaque bytes");
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	// the handle names the whole allocation: find where in it the pointer lies
+	using GetRange = CUresult (*)(CUdeviceptr*, size_t*, CUdeviceptr);
+	static const GetRange get_range = [] {
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if(cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+		return reinterpret_cast<GetRange>(p);
+	}();
+	CUdeviceptr base = 0;
+	size_t size = 0;
+	if(!get_range || get_range(&base, &size, reinterpret_cast<CUdeviceptr>(dev_ptr)) != CUDA_SUCCESS) return fail(CACAO_E_BAD_ARG, "ipc_export: not a device allocation of this process");
+	cudaIpcMemHandle_t h;
+	CU_TRY(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+	std::memcpy(handle64, &h, 64);
+	*offset = reinterpret_cast<CUdeviceptr>(dev_ptr) - base;
+	return CACAO_OK;
+}
+
+int cacao_img_ipc_import(int device, const unsigned char* handle64, uint64_t offset, void** dev_ptr) {
+	if(!handle64 || !dev_ptr) return fail(CACAO_E_BAD_ARG, "ipc_import: null pointer");
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	cudaIpcMemHandle_t h;
+	std::memcpy(&h, handle64, 64);
+	void* base = nullptr;
+	CU_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess)); // peer access to the owner's GPU comes with it
+	*dev_ptr = static_cast<uint8_t*>(base) + offset;
+	return CACAO_OK;
+}
+
+int cacao_img_ipc_close(int device, void* dev_ptr, uint64_t offset) {
+	if(!dev_ptr) return fail(CACAO_E_BAD_ARG, "ipc_close: null pointer");
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	CU_TRY(cudaDeviceSynchronize());
+	CU_TRY(cudaIpcCloseMemHandle(static_cast<uint8_t*>(dev_ptr) - offset));
+	return CACAO_OK;
+}
+
+// Same idea inside ONE process that drives several devices (EquirectToCubemap(..., devices)): let kernels on
+// `device` read and write memory of `peer`.  Already enabled / same device: success.
+int cacao_img_enable_peer_access(int device, int peer) {
+	DeviceGuard g;
+	DeviceCtx* c = nullptr;
+	int rc = get_ctx(device, &c, g);
+	if(rc) return rc;
+	DeviceGuard g2;
+	DeviceCtx* cp = nullptr;
+	rc = get_ctx(peer, &cp, g2);
+	if(rc) return rc;
+	if(c->device == cp->device) return CACAO_OK;
+	int can = 0;
+	CU_TRY(cudaSetDevice(c->device));
+	CU_TRY(cudaDeviceCanAccessPeer(&can, c->device, cp->device));
+	if(!can) return fail(CACAO_E_CUDA, "device %d cannot access device %d", c->device, cp->device);
+	cudaError_t e = cudaDeviceEnablePeerAccess(cp->device, 0);
+	if(e == cudaErrorPeerAccessAlreadyEnabled) {
+		cudaGetLastError();
+		return CACAO_OK;
+	}
+	if(e != cudaSuccess) return fail_cuda(e, "cudaDeviceEnablePeerAccess");
+	return CACAO_OK;
+}
+
 int cacao_img_get_lut(uint8_t* out65536) {
 	if(!out65536) return fail(CACAO_E_BAD_ARG, "null out-pointer");
 	std::memcpy(out65536, host_lut().table, 65536);

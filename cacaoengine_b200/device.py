@@ -51,6 +51,27 @@ def free_shareable(ptr: int, device: int = -1) -> None:
 	capi.check(capi.lib().cacao_img_free_shareable(device, ptr))
 
 
+def ipc_export(ptr: int, device: int = -1) -> tuple[bytes, int]:
+	"""(64-byte handle, offset) of a device buffer for another process on the same box; see cacao_img.h."""
+	buf, off = C.create_string_buffer(64), C.c_uint64(0)
+	capi.check(capi.lib().cacao_img_ipc_export(device, ptr, buf, C.byref(off)))
+	return buf.raw, int(off.value)
+
+
+def ipc_import(handle: bytes, offset: int, device: int = -1) -> int:
+	p = C.c_void_p()
+	capi.check(capi.lib().cacao_img_ipc_import(device, C.create_string_buffer(handle, 64), offset, C.byref(p)))
+	return int(p.value)
+
+
+def ipc_close(ptr: int, offset: int, device: int = -1) -> None:
+	capi.check(capi.lib().cacao_img_ipc_close(device, ptr, offset))
+
+
+def enable_peer_access(device: int, peer: int) -> None:
+	capi.check(capi.lib().cacao_img_enable_peer_access(device, peer))
+
+
 def host_alloc(nbytes: int) -> tuple[int, np.ndarray]:
 	"""Pinned host buffer: (address, uint8 numpy view).  Release with host_free(address)."""
 	p = C.c_void_p()

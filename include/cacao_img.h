@@ -87,6 +87,17 @@ int cacao_img_free(int device, void* dev_ptr);
 int cacao_img_malloc_shareable(int device, void** dev_ptr, uint64_t bytes, int* fd, uint64_t* mapped_bytes);
 int cacao_img_import_shareable(int device, int fd, uint64_t mapped_bytes, void** dev_ptr);
 int cacao_img_free_shareable(int device, void* dev_ptr); /* for pointers of either call; synchronises the device */
+/* The device-side gather of a sharded job ("optional device-resident assembly on GPU 0 ... over NVLink"):
+ * a rank exports a buffer (64 opaque bytes + the pointer's offset inside its allocation), another PROCESS imports it
+ * and gets a pointer to the same memory, valid as `dst` (or `src`) of every CACAO_MEM_DEVICE call on the importer's
+ * own GPU -- the kernel's stores cross NVLink and land in place, so the resampling launches of all ranks assemble
+ * one cube on one GPU with no gather step.  cacao_img_ipc_close(ptr, offset) unmaps it (synchronises the device).
+ * Inside one process that drives several devices, cacao_img_enable_peer_access(device, peer) does the same for
+ * plain pointers.  The memory must come from cacao_img_malloc / cudaMalloc (not cacao_img_malloc_shareable). */
+int cacao_img_ipc_export(int device, void* dev_ptr, unsigned char* handle64, uint64_t* offset);
+int cacao_img_ipc_import(int device, const unsigned char* handle64, uint64_t offset, void** dev_ptr);
+int cacao_img_ipc_close(int device, void* dev_ptr, uint64_t offset);
+int cacao_img_enable_peer_access(int device, int peer);
 int cacao_img_host_alloc(void** host_ptr, uint64_t bytes); /* pinned, portable across devices */
 int cacao_img_host_free(void* host_ptr);
 /* Pin memory the caller already owns (a std::vector's storage, a shared-memory segment several processes map,

@@ -122,3 +122,91 @@ def test_table_kernel_on_every_device(built_lib, oracle):
 		device.download(got, b, device=d)
 		assert same_bits(got, flipped), d
 		device.free(a, d), device.free(b, d)
+
+
+def test_sharded_cubemap_assembled_on_one_device_by_the_launches(built_lib, oracle):
+	"""SURVEY 8e, the device-side gather: every rank's resampling launch gets device 0's cube as its destination
+	(peer access inside one process), so the bands cross NVLink as the kernel's own stores and the cube is complete
+	on device 0 when the launches are -- no gather step, no per-rank output buffer.  On a one-GPU box all ranks are
+	device 0 and the peer call is a no-op; on the 2- and 8-GPU boxes the stores really are remote."""
+	from cacaoengine_b200 import _capi as c, device, sharding
+
+	n, phys = _ranks()
+	W, H, N, ch, fmt = 1024, 512, 256, 4, c.FMT_F32
+	pano = oracle.synth(W * H * ch, fmt, ch, 25)
+	want = oracle.equirect_to_cube(pano, W, H, ch, fmt, N)
+	row_bytes = W * ch * 4
+	device.init(0)
+	cube = device.malloc(want.nbytes, 0)
+	device.upload(cube, np.zeros(want.nbytes, np.uint8), device=0)
+	device.sync(0)
+	srcs = []
+	for r in range(n):
+		d = phys[r]
+		device.init(d)
+		device.enable_peer_access(d, 0)
+		units = sharding.units_for_rank(r, n, N)
+		w0, wn = sharding.source_window(units, W, H, N)
+		a = device.malloc(wn * row_bytes, d)
+		device.upload(a, pano.reshape(H, -1)[w0:w0 + wn].copy(), device=d)
+		device.equirect_to_cube_units(a, W, H, ch, fmt, cube, N, units, src_row0=w0, src_rows=wn, device=d)
+		srcs.append((a, d))
+	for a, d in srcs:
+		device.sync(d)
+		device.free(a, d)
+	got = np.empty_like(want)
+	device.download(got, cube, device=0)
+	device.free(cube, 0)
+	assert same_bits(got, want)
+
+
+_IPC_WRITER = r"""
+import sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from cacaoengine_b200 import _capi as c, device, sharding
+from oracle import pyoracle as po
+handle, offset, dev, rank, world = bytes.fromhex(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
+W, H, N, ch, fmt = 1024, 512, 256, 4, c.FMT_F32
+device.init(dev)
+cube = device.ipc_import(handle, offset, dev)
+pano = po.synth(W * H * ch, fmt, ch, 26)
+units = sharding.units_for_rank(rank, world, N)
+w0, wn = sharding.source_window(units, W, H, N)
+a = device.malloc(wn * W * ch * 4, dev)
+device.upload(a, pano.reshape(H, -1)[w0:w0 + wn].copy(), device=dev)
+device.equirect_to_cube_units(a, W, H, ch, fmt, cube, N, units, src_row0=w0, src_rows=wn, device=dev)
+device.sync(dev)
+device.ipc_close(cube, offset, dev)
+device.free(a, dev)
+print("done", len(units))
+"""
+
+
+def test_another_process_resamples_into_this_process_cube(built_lib, oracle):
+	"""The same gather across PROCESSES (one process per GPU, as under torchrun): this process exports its cube
+	buffer (cacao_img_ipc_export), each writer process opens it, resamples its rank's units straight into it from
+	the last device of the box, and the cube read back here equals the oracle's."""
+	import os
+	import subprocess
+	import sys
+
+	from cacaoengine_b200 import _capi as c, device
+
+	W, H, N, ch, fmt = 1024, 512, 256, 4, c.FMT_F32
+	want = oracle.equirect_to_cube(oracle.synth(W * H * ch, fmt, ch, 26), W, H, ch, fmt, N)
+	device.init(0)
+	cube = device.malloc(want.nbytes, 0)
+	device.upload(cube, np.zeros(want.nbytes, np.uint8), device=0)
+	device.sync(0)
+	handle, offset = device.ipc_export(cube, 0)
+	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+	world = 2
+	for rank in range(world):
+		dev = (_devices() - 1) if rank else 0
+		r = subprocess.run([sys.executable, "-c", _IPC_WRITER, root, handle.hex(), str(offset), str(dev), str(rank), str(world)], capture_output=True, text=True, timeout=300)
+		assert r.returncode == 0 and "done" in r.stdout, r.stderr[-2000:]
+	got = np.empty_like(want)
+	device.download(got, cube, device=0)
+	device.free(cube, 0)
+	assert same_bits(got, want)
