@@ -510,17 +510,36 @@ def extra_configs(torch, dist, world, rank, dev, stream, peak):
 		# then grouped NCCL send / recv of every unit into its place in rank 0's cube.
 		try:
 			cube_bytes = 6 * N * N * bpp
-			hbuf = torch.zeros(64 + 8, dtype=torch.uint8, device=f"cuda:{dev}")
-			target = None
+			# every rank must take the same path through the collectives below: a failure on one rank is agreed on first
+			hbuf = torch.zeros(64 + 8 + 1, dtype=torch.uint8, device=f"cuda:{dev}")
+			target, remote, off, why = None, None, 0, ""
 			if rank == 0:
-				target = device.malloc(cube_bytes, dev)
-				torch.cuda.synchronize()
-				handle, off = device.ipc_export(target, dev)
-				hbuf.copy_(torch.tensor(list(handle) + list(off.to_bytes(8, "little")), dtype=torch.uint8))
+				try:
+					target = device.malloc(cube_bytes, dev)
+					torch.cuda.synchronize()
+					handle, off = device.ipc_export(target, dev)
+					hbuf.copy_(torch.tensor(list(handle) + list(off.to_bytes(8, "little")) + [1], dtype=torch.uint8))
+				except Exception as e:
+					why = repr(e)
 			dist.broadcast(hbuf, 0)
 			raw = bytes(hbuf.cpu().tolist())
-			handle, off = raw[:64], int.from_bytes(raw[64:], "little")
-			remote = target if rank == 0 else device.ipc_import(handle, off, dev)
+			agreed = torch.tensor([float(raw[72])], device=f"cuda:{dev}")
+			if raw[72] and rank != 0:
+				try:
+					off = int.from_bytes(raw[64:72], "little")
+					remote = device.ipc_import(raw[:64], off, dev)
+				except Exception as e:
+					why = repr(e)
+					agreed.zero_()
+			elif rank == 0:
+				remote = target
+			dist.all_reduce(agreed, op=dist.ReduceOp.MIN)
+			if agreed.item() == 0:
+				if rank != 0 and remote is not None:
+					device.ipc_close(remote, off, dev)
+				if rank == 0 and target is not None:
+					device.free(target, dev)
+				raise RuntimeError("CUDA IPC between the ranks is unavailable on this box " + why)
 
 			def fused():
 				device.equirect_to_cube_units(src.data_ptr(), W, H, ch, fmt, remote, N, units, src_row0=w0, src_rows=wn, device=dev, stream=stream)
