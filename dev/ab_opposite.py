@@ -1,4 +1,6 @@
-"""dev: the row-strip kernel with and without opposite-face sharing (CACAO_EQUIRECT_NO_OPPOSITE=1), outputs compared."""
+"""dev: the row-strip kernel with and without opposite-face sharing (CACAO_EQUIRECT_NO_OPPOSITE=1), outputs compared.
+Record of a rejected experiment: the switch belongs to an experimental build that is not in the tree
+(profiles/r2_equirect_rows_opposite_face_rejected.log); with the shipped library both columns are the same kernel."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
