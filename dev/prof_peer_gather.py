@@ -17,3 +17,23 @@ for dst in (remote, local):
 		device.equirect_to_cube_units(src, W, H, 4, FMT_F32, dst, N, units, src_row0=w0, src_rows=wn, device=1)
 	device.sync(1)
 print("rows", sum(u.rows for u in units), "bytes", sum(u.rows for u in units) * N * 16)
+
+if "--time" in sys.argv:
+	import time
+	for wide in ("0", "1"):
+		os.environ["CACAO_EQUIRECT_WIDE_STORES"] = wide
+		for name, dst in (("remote", remote), ("local", local)):
+			for _ in range(5):
+				device.equirect_to_cube_units(src, W, H, 4, FMT_F32, dst, N, units, src_row0=w0, src_rows=wn, device=1)
+			device.sync(1)
+			t0 = time.perf_counter()
+			for _ in range(30):
+				device.equirect_to_cube_units(src, W, H, 4, FMT_F32, dst, N, units, src_row0=w0, src_rows=wn, device=1)
+			device.sync(1)
+			dt = (time.perf_counter() - t0) / 30
+			print(f"wide_stores={wide} {name}: {dt * 1e3:.4f} ms  ({sum(u.rows for u in units) * N * 16 / dt / 1e9:.0f} GB/s of output)")
+	c0 = device.checksum(remote, 6 * N * N * 16, device=0)
+	os.environ["CACAO_EQUIRECT_WIDE_STORES"] = "0"
+	device.equirect_to_cube_units(src, W, H, 4, FMT_F32, remote, N, units, src_row0=w0, src_rows=wn, device=1)
+	device.sync(1)
+	print("identical:", c0 == device.checksum(remote, 6 * N * N * 16, device=0))
