@@ -191,7 +191,10 @@ namespace cacao {
 		}
 		// tiles per block: one pass for plain shapes; LUT shapes amortise their 64 KiB table load over
 		// several passes
-		uint32_t iters = S::needs_lut ? 4u : 1u;
+		// Two float shapes whose blocks write little per pass measure ahead with four passes per block (RGBA32F -> Gray8
+		// +8-12 %, RGB16F -> RGB8 +7-10 %: dev/sweep_to_gray.py all, profiles/r2_to_gray_passes_per_block.log)
+		constexpr bool four_passes = DF == CACAO_FMT_U8 && ((SF == CACAO_FMT_F32 && SC == 4 && DC == 1) || (SF == CACAO_FMT_F16 && SC == 3 && DC == 3));
+		uint32_t iters = (S::needs_lut || four_passes) ? 4u : 1u;
 		if(const char* e = getenv("CACAO_TILE_ITERS")) iters = static_cast<uint32_t>(atoi(e) > 0 ? atoi(e) : 1);
 		const uint64_t tiles_per_block = static_cast<uint64_t>(warps) * S::U * iters;
 		const uint64_t blocks = (n_tiles + tiles_per_block - 1) / tiles_per_block;

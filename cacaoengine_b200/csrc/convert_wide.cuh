@@ -147,9 +147,9 @@ namespace cacao {
 		const size_t smem = S::needs_lut ? (direct ? 65536 : kLut2Bytes) : 0;
 		// Four narrow channels -> one channel (RGBA8 -> Gray8, RGBA16 -> Gray16, ...): a block's pass writes so little that
 		// two passes per block measure 3-15 % ahead of one (dev/sweep_to_gray.py, profiles/r2_to_gray_passes_per_block.log:
-		// RGBA8 -> Gray8 0.87 -> 0.93 of the roofline at 64 Mpixel, RGBA16 -> Gray16 0.92 -> 0.98); everything else
+		// RGBA8 -> Gray8 0.87 -> 0.93 of the roofline at 64 Mpixel, RGBA16 -> Gray16 0.92 -> 0.98; RGB8 -> Gray8 +4 %); everything else
 		// streams best with one.
-		constexpr bool two_passes = !S::needs_lut && DC == 1 && SC == 4 && S::sb <= 2 && DF != CACAO_FMT_F32 && (FmtTraits<SF>::is_int || DF == SF);
+		constexpr bool two_passes = !S::needs_lut && DC == 1 && ((SC == 4 && S::sb <= 2 && DF != CACAO_FMT_F32 && (FmtTraits<SF>::is_int || DF == SF)) || (SC == 3 && SF == CACAO_FMT_U8 && DF == CACAO_FMT_U8));
 		uint32_t iters = S::needs_lut ? (direct ? 16u : 4u) : (two_passes ? 2u : 1u);
 		if constexpr(S::needs_lut) {
 			if(!direct) {
