@@ -14,11 +14,14 @@ def timeit(fn, reps=5):
 	for _ in range(2): fn()
 	torch.cuda.synchronize()
 	if "--back-to-back" in sys.argv:  # K launches between one pair of events, as bench.py times its steps
-		a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-		a.record()
-		for _ in range(4 * reps): fn()
-		b.record(); torch.cuda.synchronize()
-		return a.elapsed_time(b) / (4 * reps)
+		ts = []
+		for _ in range(3):  # median of three groups of 20
+			a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+			a.record()
+			for _ in range(4 * reps): fn()
+			b.record(); torch.cuda.synchronize()
+			ts.append(a.elapsed_time(b) / (4 * reps))
+		return sorted(ts)[1]
 	ts = []
 	for _ in range(reps):
 		a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
