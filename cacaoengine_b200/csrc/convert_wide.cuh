@@ -40,7 +40,8 @@ namespace cacao {
 		// (shared memory is their bottleneck, and this kernel needs none for re-shaping: +15..30 %) and
 		// multi-channel -> gray with narrow samples (large source runs, tiny outputs: +5..20 %).
 		// Elsewhere the 128-bit tile kernel is equal or a few percent ahead and stays the default.
-		static constexpr bool preferred = ok && ((SF == CACAO_FMT_U16 && DF == CACAO_FMT_U8) || (DC == 1 && SC > 1 && sb <= 2));
+		// (+ Gray16F -> RGB8, the slowest shape of the tile kernel: 0.86 -> 0.95 here, dev/sweep_low_shapes.py)
+		static constexpr bool preferred = ok && ((SF == CACAO_FMT_U16 && DF == CACAO_FMT_U8) || (DC == 1 && SC > 1 && sb <= 2) || (SF == CACAO_FMT_F16 && DF == CACAO_FMT_U8 && SC == 1 && DC == 3));
 		static constexpr bool needs_lut = (SF == CACAO_FMT_U16 && DF == CACAO_FMT_U8);
 		// runs per lane per pass: keep at least two sector loads in flight per lane
 		static constexpr int U = KIN >= 2 ? 1 : 2;
